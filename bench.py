@@ -1,0 +1,341 @@
+"""Headline benchmark of the victim hot path (BASELINE.json): one LightGCN BPR epoch + one
+full-ranking evaluation on the synthetic 1M x 200k x 50M graph (D=64, L=3), plus the SpMM roofline.
+
+    python bench.py --gpus 1 --steps 2 --warmup 3                  # this implementation
+    python bench.py --impl reference --gpus 1 --steps 1 --warmup 0 # reference arm: the reference's own
+                                                                   # CPU algorithm (oracle port) on host cores
+
+A "step" = one BPR epoch (all batches: propagate, BPR, Horner backward, dense Adam) followed by one
+full-rank evaluation of every user (top-20 + target rank, Recall/NDCG@20).  `value` is timed with
+the epoch's samples already resident in HBM; `e2e` goes through the public API (`train_step()`,
+`evaluate.*`): host sampler, pinned host->device copy of the samples, loss / metric read back.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[3] / SURVEY.md 8(d) input 4
+    "synthetic": dict(n_users=1_000_000, n_items=200_000, n_edges=50_000_000, D=64, L=3, batch=1_048_576),
+    # BASELINE.json configs[1] shape (ml1m.zip is absent: shape-matched synthetic), default batch of the reference
+    "ml1m": dict(n_users=5950, n_items=3702, n_edges=468_649, D=64, L=3, batch=1024),
+    # quick functional check of this script
+    "tiny": dict(n_users=20_000, n_items=5_000, n_edges=400_000, D=64, L=3, batch=65_536),
+}
+METRIC = "lightgcn_bpr_epoch_plus_fullrank_eval_seconds"
+
+
+def synth_edges(w, device, seed=0):
+    """Distinct (u, i) pairs: user activity ~ lognormal, item popularity ~ Zipf(0.8), every user >= 1 item.
+    Generated with torch on `device` (a 50M-edge graph takes seconds on the GPU)."""
+    U, I, E = w["n_users"], w["n_items"], w["n_edges"]
+    g = torch.Generator(device=device).manual_seed(seed)
+    uw = torch.exp(torch.randn(U, device=device, generator=g, dtype=torch.float64))
+    ucdf = torch.cumsum(uw / uw.sum(), 0)
+    iw = torch.arange(1, I + 1, device=device, dtype=torch.float64) ** -0.8
+    icdf = torch.cumsum(iw / iw.sum(), 0)
+    perm = torch.randperm(I, device=device, generator=g)
+
+    def draw(n):
+        u = torch.searchsorted(ucdf, torch.rand(n, device=device, generator=g, dtype=torch.float64)).clamp_(max=U - 1)
+        i = perm[torch.searchsorted(icdf, torch.rand(n, device=device, generator=g, dtype=torch.float64)).clamp_(max=I - 1)]
+        return u * I + i
+    first = torch.arange(U, device=device) * I + perm[
+        torch.searchsorted(icdf, torch.rand(U, device=device, generator=g, dtype=torch.float64)).clamp_(max=I - 1)]
+    keys = torch.unique(first)
+    while keys.numel() < E:
+        need = int((E - keys.numel()) * 1.3) + 1024
+        keys = torch.unique(torch.cat([keys, draw(need)]))
+    if keys.numel() > E:       # drop surplus at random, never a user's first pair
+        u = keys // I
+        is_first = torch.ones_like(u, dtype=torch.bool)
+        is_first[1:] = u[1:] != u[:-1]
+        cand = torch.nonzero(~is_first).flatten()
+        drop = cand[torch.randperm(cand.numel(), device=device, generator=g)[: keys.numel() - E]]
+        keep = torch.ones_like(u, dtype=torch.bool)
+        keep[drop] = False
+        keys = keys[keep]
+    return keys // I, keys % I
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout.readlines()), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0]))
+            mx = max(mx, int(f[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# this implementation
+# ----------------------------------------------------------------------------------------------
+def run_b200(args, w):
+    import torch.distributed as dist
+    from recad_b200 import dataset, evaluate, model, ops
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from recad_b200 import dist as rdist
+        return rdist.bench_sharded(args, w, dev, rank, world, METRIC, synth_edges, ClockSampler, peaks)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)     # noqa: E731
+    U, I, D, L, B = w["n_users"], w["n_items"], w["D"], w["L"], args.batch or w["batch"]
+    t0 = time.time()
+    eu, ei = synth_edges(w, dev)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t0
+    t0 = time.time()
+    graph = ops.Graph.from_edges(eu, ei, U, I)
+    torch.cuda.synchronize()
+    t_graph = time.time() - t0
+    data = dataset.ArrayImplicitData(args.workload, U, I, (eu.cpu().numpy(), ei.cpu().numpy()), dev, batch_size=B, graph=graph)
+    del eu, ei
+    torch.manual_seed(2023)
+    m = model.from_config("victim", "lightgcn", latent_dim_rec=D, lightGCN_n_layers=L, device=dev).I(dataset=data)
+    rp, rc = data.train_csr(dev)
+    users_all = torch.arange(U, device=dev)
+    target = [0]
+    # two resident sample sets, alternated between steps (the exact C++ MT19937 sampler produces them)
+    np.random.seed(2023)
+    t0 = time.time()
+    sets = [data.epoch_samples(dev) for _ in range(2)]
+    torch.cuda.synchronize()
+    t_sampler = (time.time() - t0) / 2
+    n = int(sets[0][0].numel())
+    n_batches = (n + B - 1) // B
+    import ctypes as C
+    from recad_b200 import _lib
+    lib = _lib.lib()
+
+    def epoch(samples):
+        us, ps, ns = samples
+        _lib.check(lib.recad_lightgcn_train_epoch(C.byref(m._st), m._vp(us), m._vp(ps), m._vp(ns), int(us.numel()), B, m._steps,
+                                                  ops._stream(dev)), "recad_lightgcn_train_epoch")
+        m._steps += (int(us.numel()) + B - 1) // B
+        m._O_valid = False
+
+    def full_eval():
+        topi, topv, rank_, score, _ = m.full_rank(users_all, target, 20, rp, rc)
+        return topi, rank_
+
+    for k in range(args.warmup):
+        epoch(sets[k % 2])
+        full_eval()
+    torch.cuda.synchronize()
+    marks = []
+    with ClockSampler(local) as clocks:
+        for k in range(args.steps):
+            a, b, c = ev(), ev(), ev()
+            a.record()
+            epoch(sets[k % 2])
+            b.record()
+            full_eval()
+            c.record()
+            marks.append((a, b, c))
+        torch.cuda.synchronize()
+    ep_ms = [a.elapsed_time(b) for a, b, _ in marks]
+    evl_ms = [b.elapsed_time(c) for _, b, c in marks]
+    step_ms = float(np.mean(ep_ms) + np.mean(evl_ms))
+    loss = m._read_loss(m.loss_acc, n_batches)[0]
+
+    # dominant kernel: the fused SpMM (6 per batch).  Algorithmic bytes: SURVEY 8(d) no-reuse gather model.
+    X, Y, Z = m.E, m.X0, m.X1
+    for _ in range(3):
+        ops.spmm(graph, X, Y, X, Z, 1.0)
+    reps = 10 if args.workload == "synthetic" else 50
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(reps):
+        ops.spmm(graph, X, Y, X, Z, 1.0)
+    b.record()
+    torch.cuda.synchronize()
+    spmm_ms = a.elapsed_time(b) / reps
+    pk, pk_src = peaks()
+    alg = graph.algorithmic_bytes(D) + graph.n_rows * 4 * D * 2       # + read C, write Z of the fused epilogue
+    achieved = alg / (spmm_ms * 1e-3) / 1e9
+
+    # end to end through the public API: host sampler + pinned H2D + epoch + loss D2H, then evaluation + metric D2H
+    e2e = []
+    for k in range(max(1, min(args.steps, 2))):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        m.train_step()
+        res = evaluate.recall_ndcg(m, data, K=20, split="train", users=users_all)
+        torch.cuda.synchronize()
+        e2e.append(time.time() - t0)
+    h2d = n * 3 * 8
+    d2h = 4 * 8 + 3 * 8
+
+    out = {
+        "metric": METRIC, "value": round(step_ms / 1e3, 6), "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(step_ms, 3), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: LightGCN {U} users x {I} items x {w['n_edges']} interactions, D={D}, L={L}, "
+                               f"BPR batch {B} ({n_batches} batches/epoch, {n} samples), full-rank eval of all {U} users K=20",
+                   "l2": "inputs exceed L2 (graph + tables > 126 MB)" if graph.nnz * 8 > 126e6 else "L2-resident workload; absolute times only",
+                   "parallelism": "single GPU"},
+        "epoch_s": round(float(np.mean(ep_ms)) / 1e3, 6), "eval_s": round(float(np.mean(evl_ms)) / 1e3, 6),
+        "eval_users_per_s": round(U / (float(np.mean(evl_ms)) / 1e3), 1), "epoch_loss": loss,
+        "graph_build_s": round(t_graph, 4), "edge_gen_s": round(t_gen, 3), "host_sampler_s": round(t_sampler, 3),
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "kernel": "spmm_seg_kernel<64,4>",
+                     "ms_per_launch": round(spmm_ms, 4), "algorithmic_bytes": alg, "peak_source": pk_src,
+                     "model": "no-reuse gather: nnz*(8+4D) + 3*N*4D + (N+1)*4"},
+        "e2e": {"value": round(float(np.mean(e2e)), 6), "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "includes": "C++ MT19937 sampler + shuffle on host, pinned H2D of the samples, epoch, loss D2H, full-rank eval, metric D2H"},
+        "gpu_launches": args.steps * (n_batches * (2 * L * (2 if graph.n_mrow else 1) + 2) + 3),
+        "clocks": clocks.summary(),
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_reference(w, B, graph, m, data, steps=1)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU algorithm (oracle port: torch CPU restatement of
+# recad/model/victim/lightgcn.py) on the host cores, bounded sample, extrapolated to the metric's unit
+# ----------------------------------------------------------------------------------------------
+def cpu_reference(w, B, graph=None, model_=None, data=None, steps=1, host_edges=None):
+    from oracle import lightgcn as olg
+    U, I, D, L = w["n_users"], w["n_items"], w["D"], w["L"]
+    N = U + I
+    if graph is not None:
+        ptr, col, val = graph.to_numpy()
+    else:
+        from oracle import graph as og
+        ptr, col, val, _, _ = og.norm_adj_csr(host_edges[0], host_edges[1], U, I)
+    A = olg.csr_to_torch_coo(ptr, col, val, N)      # the reference holds a coalesced COO tensor (implicit.py:295-296)
+    nnz = len(col)
+    threads = torch.get_num_threads()
+    g = torch.Generator().manual_seed(0)
+    E = torch.randn(N, D, generator=g) * 0.1
+    n_samples = min(w["n_edges"], int(nnz // 2))
+    n_batches = (n_samples + B - 1) // B
+    t_spmm, t_bpr, t_eval = [], [], []
+    for _ in range(steps):
+        t0 = time.time()
+        X = torch.sparse.mm(A, E)                                  # lightgcn.py:99-108, one of the 2L per batch
+        t_spmm.append(time.time() - t0)
+        # one batch of the BPR head + dense Adam without the propagate (lightgcn.py:122-168)
+        Bs = min(B, n_samples)
+        us, ps, ns = (torch.randint(0, hi, (Bs,), generator=g) for hi in (U, I, I))
+        P = torch.nn.Parameter(X.clone())
+        opt = torch.optim.Adam([P], lr=1e-3)
+        t0 = time.time()
+        u, p, q = P[us], P[U + ps], P[U + ns]
+        loss = torch.nn.functional.softplus((u * q).sum(1) - (u * p).sum(1)).mean() + 1e-4 * 0.5 * (
+            u.norm(2).pow(2) + p.norm(2).pow(2) + q.norm(2).pow(2)) / Bs
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        t_bpr.append(time.time() - t0)
+        # evaluation sample: batched getUsersRating + topk (lightgcn.py:115-120) for 1000 users
+        ne = min(1000, U)
+        t0 = time.time()
+        torch.topk(X[:ne] @ X[U:].t(), 20)
+        t_eval.append((time.time() - t0) / ne)
+    spmm, bpr, ev_user = float(np.mean(t_spmm)), float(np.mean(t_bpr)), float(np.mean(t_eval))
+    epoch_s = n_batches * (2 * L * spmm + bpr)
+    eval_s = ev_user * U
+    return {"value": round(epoch_s + eval_s, 3), "unit": "s", "cores": threads, "kind": "port",
+            "sample": f"full-size graph (nnz {nnz}): {steps} x [1 torch.sparse.mm of the 2L per batch ({spmm:.3f} s), 1 BPR-head+Adam batch "
+                      f"of {min(B, n_samples)} ({bpr:.3f} s), batched matmul+topk eval of 1000 users ({ev_user * 1e3:.3f} ms/user)]; "
+                      f"extrapolated: {n_batches} batches x (2L x spmm + bpr) + n_users x eval; the reference's own per-user eval "
+                      f"(normal.py:62-71: one propagate per user = {L * spmm:.2f} s/user) is NOT charged",
+            "epoch_s": round(epoch_s, 3), "eval_s": round(eval_s, 3), "spmm_s": round(spmm, 4)}
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return None
+    B = args.batch or w["batch"]
+    t0 = time.time()
+    # same generator as the GPU arm, on the CPU torch device (seeded identically; streams differ by device)
+    eu, ei = synth_edges(w, torch.device("cpu"))
+    edges = (eu.numpy(), ei.numpy())
+    t_gen = time.time() - t0
+    base = cpu_reference(w, B, host_edges=edges, steps=max(1, args.steps))
+    U, I, D, L = w["n_users"], w["n_items"], w["D"], w["L"]
+    return {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": base["value"] * 1e3, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: LightGCN {U} users x {I} items x {w['n_edges']} interactions, D={D}, L={L}, BPR batch {B}",
+                   "parallelism": f"{base['cores']} host threads (torch CPU)"},
+        "cpu_baseline": base, "edge_gen_s": round(t_gen, 2),
+        "e2e": {"value": base["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="synthetic", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    out = run_reference(args, w) if args.impl == "reference" else run_b200(args, w)
+    if out is not None and int(os.environ.get("RANK", 0)) == 0:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,327 @@
+/* recad_b200.h -- C ABI of the B200-native RecAD victim hot path.
+ *
+ * The reference (gusye1234/recad) is pure Python over stock torch ops: it has NO
+ * FFI of its own.  Each entry point below therefore cites the reference
+ * FUNCTION it replaces (paths relative to the reference checkout); the Python
+ * classes in recad_b200/ bind these with ctypes and re-expose the reference's
+ * own plugin interface (model.from_config('victim', ..).I(), dataset
+ * .generate_batch()/.inject_data(), workflow .execute()).  INTEGRATION.md shows
+ * the binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types;
+ *   - every pointer marked [dev] is a device pointer on the CURRENT CUDA device,
+ *     [host] a host pointer; buffers are owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void*; all device work is enqueued
+ *     on it asynchronously unless the function says "synchronises";
+ *   - return value: 0 = ok, < 0 = error (RECAD_ERR_*), message via
+ *     recad_last_error() (thread-local); no exception crosses the boundary;
+ *   - indices: users/items/samples int64 as in the reference; CSR column
+ *     indices int32 (N < 2^31), row pointers int64;
+ *   - all floating point is IEEE fp32 (no fast-math), loss accumulators fp64.
+ */
+#ifndef RECAD_B200_H
+#define RECAD_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RECAD_ABI_VERSION 1
+
+enum {
+  RECAD_OK = 0,
+  RECAD_ERR_ARG = -1,         /* bad argument (null pointer, negative size, id out of range) */
+  RECAD_ERR_CUDA = -2,        /* a CUDA runtime call or kernel launch failed */
+  RECAD_ERR_UNSUPPORTED = -3, /* shape not compiled (e.g. embedding width) */
+  RECAD_ERR_OVERFLOW = -4,    /* size exceeds an index type */
+  RECAD_ERR_SCRATCH = -5      /* scratch buffer too small */
+};
+
+int recad_abi_version(void);
+const char* recad_last_error(void);
+/* sm_count / cc of the current device; fails unless it is an sm_100 part. */
+int recad_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------ *
+ * Graph construction  (recad/dataset/implicit.py:206-213, 243-298, 320-326)
+ * ------------------------------------------------------------------------ */
+
+/* Bytes of [dev] scratch recad_csr_build_structure needs for n_edges edges. */
+int64_t recad_csr_build_scratch_bytes(int64_t n_edges, int64_t n_users, int64_t n_items);
+
+/* Edge list -> structure of the symmetric bipartite adjacency over
+ * N = n_users + n_items rows, entries ordered by (row, col) exactly as
+ * `Graph.coalesce()` orders them (implicit.py:296).  Duplicate (u, i) pairs are
+ * merged and counted, as scipy's csr_matrix sums them (implicit.py:206-209).
+ *   users, items [dev] int64[n_edges]
+ *   rowptr  [dev] int64[N + 1]            out
+ *   colidx  [dev] int32[2 * n_edges]      out (first nnz valid)
+ *   mult    [dev] float[2 * n_edges]      out multiplicity of each entry (1.0 normally)
+ *   degree  [dev] int32[N]                out row sums of multiplicities (implicit.py:269)
+ *   nnz_out [host] int64*                 out number of distinct directed entries
+ * Synchronises the stream (nnz is returned to the host). */
+int recad_csr_build_structure(const int64_t* users, const int64_t* items, int64_t n_edges,
+                              int64_t n_users, int64_t n_items, int64_t* rowptr, int32_t* colidx,
+                              float* mult, int32_t* degree, int64_t* nnz_out, void* scratch,
+                              int64_t scratch_bytes, void* stream);
+
+/* vals[e] = (d_inv[row] * mult[e]) * d_inv[col]: two successive fp32 products, the
+ * order scipy's D.dot(A).dot(D) evaluates them in (implicit.py:273-276).  d_inv
+ * comes from the host: the reference's `np.power(rowsum + 1e-14, -0.5)` in
+ * float32 is not reproducible by any device expression. */
+int recad_csr_normalize(const int64_t* rowptr, const int32_t* colidx, const float* mult,
+                        const float* d_inv, int64_t n_rows, float* vals, void* stream);
+
+/* In-place fake-user injection (implicit.py:482-494 + base.py:108-118, which the
+ * reference implements as a full dataset rebuild): append F user rows after row
+ * n_users-1.  Item rows shift down by F, item column ids in user rows shift by
+ * +F, every touched item row gains the new user ids at its END (they are larger
+ * than all existing user ids, so (row, col) order is preserved).  No sort.
+ *   fake_rowptr [dev] int64[F + 1], fake_items [dev] int32[]: per fake user, its
+ *   DISTINCT items ascending (np.where order, implicit.py:109).
+ * new_* buffers must hold nnz_old + 2 * fake_rowptr[F] entries. */
+int recad_csr_append_users(const int64_t* rowptr, const int32_t* colidx, const float* mult,
+                           int64_t n_users, int64_t n_items, int64_t n_fake,
+                           const int64_t* fake_rowptr, const int32_t* fake_items, int64_t n_fake_edges,
+                           int64_t* new_rowptr, int32_t* new_colidx, float* new_mult,
+                           int32_t* new_degree, void* scratch, int64_t scratch_bytes, void* stream);
+int64_t recad_csr_append_scratch_bytes(int64_t n_users, int64_t n_items, int64_t n_fake, int64_t n_fake_edges);
+
+/* ------------------------------------------------------------------------ *
+ * Propagation  (recad/model/victim/lightgcn.py:82-113 `computer`; its autograd
+ * backward is the same product because A_hat is symmetric)
+ * ------------------------------------------------------------------------ */
+
+/* A CSR matrix plus its load-balancing plan: rows longer than seg_len are cut
+ * into segments; a segment is the unit of work of one warp.  Rectangular
+ * matrices are allowed (colidx indexes rows of X), which is what the user-row
+ * shards of the multi-GPU path use. */
+typedef struct recad_csr {
+  int64_t n_rows;
+  int64_t nnz;
+  const int64_t* rowptr;   /* [dev] int64[n_rows + 1] */
+  const int32_t* colidx;   /* [dev] int32[nnz] */
+  const float* vals;       /* [dev] float[nnz] */
+  int64_t n_seg;           /* plan: number of segments (>= n_rows) */
+  int32_t seg_len;         /* plan: max entries per segment */
+  int32_t _pad;
+  const int32_t* seg_row;  /* [dev] int32[n_seg] */
+  const int64_t* seg_lo;   /* [dev] int64[n_seg] first entry of the segment */
+  const int32_t* seg_slot; /* [dev] int32[n_seg] -1 = the row has one segment, else partial slot */
+  int64_t n_mrow;          /* rows with > 1 segment */
+  const int32_t* mrow;     /* [dev] int32[n_mrow] row id */
+  const int32_t* mrow_lo;  /* [dev] int32[n_mrow + 1] first partial slot of the row */
+  float* partials;         /* [dev] float[n_slot * D] scratch for multi-segment rows */
+} recad_csr;
+
+/* Upper bounds for the plan arrays of a matrix with n_rows / nnz. */
+int64_t recad_spmm_plan_max_segments(int64_t n_rows, int64_t nnz, int32_t seg_len);
+int64_t recad_spmm_plan_scratch_bytes(int64_t n_rows);
+/* Build the plan on the device.  counts_out [host] int64[3] = {n_seg, n_mrow,
+ * n_slot}.  Synchronises the stream. */
+int recad_spmm_plan(const int64_t* rowptr, int64_t n_rows, int32_t seg_len, int32_t* seg_row,
+                    int64_t* seg_lo, int32_t* seg_slot, int32_t* mrow, int32_t* mrow_lo,
+                    int64_t* counts_out, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* Y = A X (written if Y != NULL) and Z = alpha * (C + A X) (written if Z != NULL;
+ * C == NULL means 0; Z may alias C).  X, Y, C, Z: [dev] float[rows, D] row-major,
+ * 16-byte aligned.  This one kernel is every layer of the forward propagate
+ * fused with the running layer mean (lightgcn.py:99-111: Y = next layer,
+ * Z = accumulated mean) and every Horner step of the backward (Z = g + A t). */
+int recad_spmm(const recad_csr* A, const float* X, float* Y, const float* C, float* Z,
+               float alpha, int32_t D, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * LightGCN BPR step  (recad/model/victim/lightgcn.py:122-172)
+ * ------------------------------------------------------------------------ */
+
+/* Fused gather + dot + softplus + L2-reg + gradient scatter for one batch.
+ *   O [dev] float[N, D] propagated mean (users first), E [dev] float[N, D] ego table
+ *   users/pos/neg [dev] int64[B] (item ids WITHOUT the n_users offset)
+ *   grad_scale = 1 / (L + 1): folded into the scattered gradient so that gO is
+ *     already d loss / d (sum of layers)
+ *   gO  [dev] float[N, D]  += ; must be zeroed by the caller
+ *   cnt [dev] float[N]     += number of times each row occurs in the batch
+ *                             (drives the L2-reg gradient lambda/B * cnt * E in Adam)
+ *   loss_acc [dev] double[4]: [0] += sum softplus(x), [1] += sum (|E_u|^2+|E_p|^2+|E_n|^2),
+ *                             [3] is set non-zero (as an int) if a sample id is out of range */
+int recad_bpr_fwd_bwd(const float* O, const float* E, int64_t n_users, int64_t n_items,
+                      const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t B,
+                      float grad_scale, float* gO, float* cnt, double* loss_acc, int32_t D,
+                      void* stream);
+
+/* Dense Adam over n elements (torch.optim.Adam defaults, lightgcn.py:17-19):
+ *   G = g + reg_scale * cnt[i / D] * p   (cnt may be NULL)
+ *   m = b1 m + (1-b1) G; v = b2 v + (1-b2) G^2;
+ *   p -= (lr / (1-b1^t)) * m / (sqrt(v) / sqrt(1-b2^t) + eps)
+ * Every element is updated every step (Embedding(sparse=False), lightgcn.py:40-45). */
+int recad_adam(float* p, const float* g, const float* cnt, float reg_scale, float* m, float* v,
+               int64_t n, int32_t D, float lr, float b1, float b2, float eps, int64_t step,
+               void* stream);
+
+/* State of one LightGCN victim on one device; all buffers caller-owned. */
+typedef struct recad_lightgcn {
+  const recad_csr* graph;  /* N x N normalised adjacency */
+  int64_t n_users, n_items;
+  int32_t D, n_layers;
+  float lambda, lr, beta1, beta2, eps;
+  int32_t _pad;
+  float* E;                /* [dev] float[N, D] ego embeddings (users then items) */
+  float* m;                /* [dev] float[N, D] Adam first moment */
+  float* v;                /* [dev] float[N, D] Adam second moment */
+  float* O;                /* [dev] float[N, D] propagated mean (output of `computer`) */
+  float* X0;               /* [dev] float[N, D] work: layer ping */
+  float* X1;               /* [dev] float[N, D] work: layer pong */
+  float* g;                /* [dev] float[N, D] work: gradient wrt the layer sum */
+  float* cnt;              /* [dev] float[N]    work: batch multiplicities */
+  double* loss_acc;        /* [dev] double[4]   {sum softplus, sum sq, epoch loss sum, spare} */
+} recad_lightgcn;
+
+/* O = mean_k A^k E (lightgcn.py:82-113).  L fused SpMMs, nothing else. */
+int recad_lightgcn_propagate(const recad_lightgcn* st, void* stream);
+
+/* One epoch of `train_step` (lightgcn.py:132-172) over pre-sampled, pre-shuffled
+ * triples [dev] int64[n_samples] x 3, cut into batches of `batch` (last ragged,
+ * implicit.py:38-47).  Per batch: propagate, BPR, Horner backward, dense Adam.
+ * step0 = Adam steps taken before this epoch.  The mean of the per-batch losses
+ * is left in loss_acc[2] / n_batches: read it with ONE device->host copy after
+ * the epoch (the reference syncs once per batch, lightgcn.py:169). */
+int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* users, const int64_t* pos,
+                               const int64_t* neg, int64_t n_samples, int64_t batch, int64_t step0,
+                               void* stream);
+
+/* scores[b] = <O[users[b]], O[n_users + items[b]]> (lightgcn.py:174-183 after a
+ * propagate; O must be current). */
+int recad_dot_scores(const float* O, int64_t n_users, const int64_t* users, const int64_t* items,
+                     int64_t B, int32_t D, float* scores, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * MF pointwise BCE step  (recad/model/victim/mf.py:40-69)
+ * ------------------------------------------------------------------------ */
+typedef struct recad_mf {
+  int64_t n_users, n_items;
+  int32_t D;
+  float mean, lr, beta1, beta2, eps;
+  float *Ue, *Ub, *Ie, *Ib;         /* [dev] params: [U,D] [U] [I,D] [I] */
+  float *mUe, *mUb, *mIe, *mIb;     /* Adam m */
+  float *vUe, *vUb, *vIe, *vIb;     /* Adam v */
+  float *gUe, *gUb, *gIe, *gIb;     /* work: dense gradients */
+  double* loss_acc;                 /* [dev] double[4] {batch sum, spare, epoch sum, spare} */
+} recad_mf;
+
+/* pred[b] = <Ue[u], Ie[i]> + Ub[u] + Ib[i] + mean (mf.py:40-47, dropout 0). */
+int recad_mf_forward(const recad_mf* st, const int64_t* users, const int64_t* items, int64_t B,
+                     float* pred, void* stream);
+/* One epoch of MF.train_step (mf.py:49-69): BCEWithLogits (mean) + dense Adam on
+ * the four tables, per batch.  labels [dev] int64.  Loss as in the LightGCN epoch. */
+int recad_mf_train_epoch(const recad_mf* st, const int64_t* users, const int64_t* items,
+                         const int64_t* labels, int64_t n_samples, int64_t batch, int64_t step0,
+                         void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * NCF / NeuMF-end pointwise BCE step  (recad/model/victim/ncf.py:32-53, 112-153)
+ * ------------------------------------------------------------------------ */
+
+/* All parameters live in one flat [dev] float buffer.  offsets [host]
+ * int64[4 + 2 * n_layers + 3] = float offsets of
+ *   embed_user_GMF [U, f], embed_item_GMF [I, f], embed_user_MLP [U, w], embed_item_MLP [I, w],
+ *   then per MLP layer l: weight [in_l / 2, in_l] (torch Linear layout), bias [in_l / 2],
+ *   predict weight [2 f], predict bias [1], and the TOTAL float count
+ * with w = f * 2^(n_layers - 1), in_l = f * 2^(n_layers - l) (ncf.py:32-53).  Each piece starts
+ * on a multiple of 4 floats; the padding must be zero-initialised. */
+int recad_ncf_layout(int32_t factor, int32_t n_layers, int64_t n_users, int64_t n_items, int64_t* offsets);
+int64_t recad_ncf_work_floats(int32_t factor, int32_t n_layers, int64_t max_batch);
+
+typedef struct recad_ncf {
+  int64_t n_users, n_items;
+  int32_t factor, n_layers;
+  float lr, beta1, beta2, eps;
+  float* params;      /* [dev] float[n_params] */
+  float* m;           /* [dev] Adam first moment  (training only) */
+  float* v;           /* [dev] Adam second moment (training only) */
+  float* grads;       /* [dev] float[n_params] work (training only) */
+  int64_t n_params;   /* = offsets[last] of recad_ncf_layout */
+  float* work;        /* [dev] float[work_floats] activations */
+  int64_t work_floats;
+  int64_t max_batch;  /* largest batch the work buffer was sized for */
+  double* loss_acc;   /* [dev] double[4] {batch sum, spare, epoch sum, bad-id flag} */
+} recad_ncf;
+
+/* pred[b] = NeuMF(users[b], items[b]) (ncf.py:112-131, dropout 0), B <= max_batch. */
+int recad_ncf_forward(const recad_ncf* st, const int64_t* users, const int64_t* items, int64_t B,
+                      float* pred, void* stream);
+/* One epoch of NCF.train_step (ncf.py:133-153); loss bookkeeping as in the MF epoch. */
+int recad_ncf_train_epoch(const recad_ncf* st, const int64_t* users, const int64_t* items,
+                          const int64_t* labels, int64_t n_samples, int64_t batch, int64_t step0,
+                          void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Full-ranking evaluation  (recad/workflow/normal.py:57-93, 111-160;
+ * lightgcn.py:115-120 getUsersRating)
+ * ------------------------------------------------------------------------ */
+
+/* item_T[d * ld + i] = item_emb[i * D + d]  (ld >= n_items, multiple of 4). */
+int recad_transpose_items(const float* item_emb, int64_t n_items, int32_t D, float* item_T,
+                          int64_t ld, void* stream);
+
+/* For each of n_eval users: score EVERY item (s = <user_emb[u], item_emb[i]>, fp32
+ * FMA in ascending d), drop the user's train items, and produce
+ *   topk_idx/topk_val [dev] int32/float[n_eval, K]  best K by (score desc, id asc); -1/-inf padded
+ *   target_rank  [dev] int32[n_eval, T]  #{non-train i: s_i > s_t or (s_i == s_t and i < t)},
+ *                                        -1 when the target is one of the user's train items
+ *   target_score [dev] float[n_eval, T]
+ * without materialising the score matrix.  HR@k = mean[rank < k] and pred_shift
+ * (normal.py:155-159) follow on the host from these.  Tie rule documented in
+ * DESIGN.md (the reference's pandas quicksort leaves ties undefined, normal.py:86-88).
+ *   user_emb [dev] float[*, D]; user_ids [dev] int64[n_eval] rows of user_emb
+ *   train_rowptr [dev] int64[n_users_total + 1], train_col [dev] int32[] ascending per user
+ *   targets [dev] int32[T] (T <= 8), K <= 128 */
+int recad_fullrank_eval(const float* user_emb, const float* item_T, int64_t ld, int64_t n_items,
+                        int32_t D, const int64_t* user_ids, int64_t n_eval,
+                        const int64_t* train_rowptr, const int32_t* train_col,
+                        const int32_t* targets, int32_t T, int32_t K, int32_t* topk_idx,
+                        float* topk_val, int32_t* target_rank, float* target_score, void* stream);
+
+/* Same outputs as recad_fullrank_eval from a MATERIALISED score block, for victims whose
+ * score is not an inner product (NCF): scores [dev] float[n_rows, n_items], row r belongs
+ * to user user_ids[r].  One warp per row. */
+int recad_rank_from_scores(const float* scores, int64_t n_rows, int64_t n_items,
+                           const int64_t* user_ids, const int64_t* train_rowptr,
+                           const int32_t* train_col, const int32_t* targets, int32_t T, int32_t K,
+                           int32_t* topk_idx, float* topk_val, int32_t* target_rank,
+                           float* target_score, void* stream);
+
+/* Recall@K / NDCG@K sums over users from top-K lists and a ground-truth CSR
+ * (implicit.py:461-476 test batches; definition in oracle/evaluate.py, parity
+ * unpinned in the reference).  out [dev] double[3] += {sum recall, sum ndcg, n users with gt}. */
+int recad_recall_ndcg(const int32_t* topk_idx, int64_t n_eval, int32_t K, const int64_t* user_ids,
+                      const int64_t* gt_rowptr, const int32_t* gt_col, double* out, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * Samplers: bit-exact replay of the legacy np.random MT19937 stream on the host
+ * (recad/dataset/implicit.py:18-35, 50-74, 77-91; recad/__init__.py:11-14)
+ * ------------------------------------------------------------------------ */
+
+/* key[624] / *pos: numpy's legacy state (np.random.get_state()[1:3]); advanced in
+ * place so the caller can write it back with np.random.set_state.
+ * out [host] int64[train_size * 3] (user, pos, neg) rows; *n_out = rows produced
+ * (users without positives are dropped, implicit.py:63-64). */
+int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items,
+                           int64_t train_size, const int64_t* allpos_rowptr,
+                           const int64_t* allpos_col, int64_t* out, int64_t* n_out);
+/* Per user k (dict order): its |pos| positives (label 1, stored order) then
+ * ratio * |pos| negatives drawn with replacement from the ascending complement.
+ * pos_sorted: the same lists sorted ascending (for the complement).
+ * out [host] int64[(1 + ratio) * n_pos_total * 3]. */
+int recad_mt19937_pointwise(uint32_t* key, int32_t* pos, int64_t n_dict_users, const int64_t* user_ids,
+                            const int64_t* pos_rowptr, const int64_t* pos_items,
+                            const int64_t* pos_sorted, int64_t n_items, int32_t ratio, int64_t* out);
+/* np.random.shuffle(np.arange(n)) (implicit.py:24-25): perm [host] int64[n]. */
+int recad_mt19937_permutation(uint32_t* key, int32_t* pos, int64_t n, int64_t* perm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECAD_B200_H */

@@ -1,0 +1,118 @@
+"""ctypes binding of librecad_b200.so (the C ABI declared in include/recad_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised.  Nothing in this package imports ``oracle``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "librecad_b200.so")
+
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+
+
+class RecadError(RuntimeError):
+    pass
+
+
+class CSR(C.Structure):
+    """struct recad_csr"""
+    _fields_ = [
+        ("n_rows", i64), ("nnz", i64), ("rowptr", vp), ("colidx", vp), ("vals", vp),
+        ("n_seg", i64), ("seg_len", i32), ("_pad", i32), ("seg_row", vp), ("seg_lo", vp), ("seg_slot", vp),
+        ("n_mrow", i64), ("mrow", vp), ("mrow_lo", vp), ("partials", vp),
+    ]
+
+
+class LightGCN(C.Structure):
+    """struct recad_lightgcn"""
+    _fields_ = [
+        ("graph", C.POINTER(CSR)), ("n_users", i64), ("n_items", i64), ("D", i32), ("n_layers", i32),
+        ("lam", f32), ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("_pad", i32),
+        ("E", vp), ("m", vp), ("v", vp), ("O", vp), ("X0", vp), ("X1", vp), ("g", vp), ("cnt", vp), ("loss_acc", vp),
+    ]
+
+
+class MF(C.Structure):
+    """struct recad_mf"""
+    _fields_ = [
+        ("n_users", i64), ("n_items", i64), ("D", i32), ("mean", f32), ("lr", f32), ("beta1", f32), ("beta2", f32),
+        ("eps", f32),
+        ("Ue", vp), ("Ub", vp), ("Ie", vp), ("Ib", vp),
+        ("mUe", vp), ("mUb", vp), ("mIe", vp), ("mIb", vp),
+        ("vUe", vp), ("vUb", vp), ("vIe", vp), ("vIb", vp),
+        ("gUe", vp), ("gUb", vp), ("gIe", vp), ("gIb", vp),
+        ("loss_acc", vp),
+    ]
+
+
+class NCF(C.Structure):
+    """struct recad_ncf"""
+    _fields_ = [
+        ("n_users", i64), ("n_items", i64), ("factor", i32), ("n_layers", i32),
+        ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32),
+        ("params", vp), ("m", vp), ("v", vp), ("grads", vp), ("n_params", i64),
+        ("work", vp), ("work_floats", i64), ("max_batch", i64), ("loss_acc", vp),
+    ]
+
+
+# name -> (restype, argtypes); every symbol of include/recad_b200.h
+SIGNATURES = {
+    "recad_abi_version": (C.c_int, []),
+    "recad_last_error": (C.c_char_p, []),
+    "recad_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "recad_csr_build_scratch_bytes": (i64, [i64, i64, i64]),
+    "recad_csr_build_structure": (C.c_int, [vp, vp, i64, i64, i64, vp, vp, vp, vp, C.POINTER(i64), vp, i64, vp]),
+    "recad_csr_normalize": (C.c_int, [vp, vp, vp, vp, i64, vp, vp]),
+    "recad_csr_append_users": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
+    "recad_csr_append_scratch_bytes": (i64, [i64, i64, i64, i64]),
+    "recad_spmm_plan_max_segments": (i64, [i64, i64, i32]),
+    "recad_spmm_plan_scratch_bytes": (i64, [i64]),
+    "recad_spmm_plan": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, C.POINTER(i64), vp, i64, vp]),
+    "recad_spmm": (C.c_int, [C.POINTER(CSR), vp, vp, vp, vp, f32, i32, vp]),
+    "recad_bpr_fwd_bwd": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, i64, f32, vp, vp, vp, i32, vp]),
+    "recad_adam": (C.c_int, [vp, vp, vp, f32, vp, vp, i64, i32, f32, f32, f32, f32, i64, vp]),
+    "recad_lightgcn_propagate": (C.c_int, [C.POINTER(LightGCN), vp]),
+    "recad_lightgcn_train_epoch": (C.c_int, [C.POINTER(LightGCN), vp, vp, vp, i64, i64, i64, vp]),
+    "recad_dot_scores": (C.c_int, [vp, i64, vp, vp, i64, i32, vp, vp]),
+    "recad_mf_forward": (C.c_int, [C.POINTER(MF), vp, vp, i64, vp, vp]),
+    "recad_mf_train_epoch": (C.c_int, [C.POINTER(MF), vp, vp, vp, i64, i64, i64, vp]),
+    "recad_ncf_layout": (C.c_int, [i32, i32, i64, i64, C.POINTER(i64)]),
+    "recad_ncf_work_floats": (i64, [i32, i32, i64]),
+    "recad_ncf_forward": (C.c_int, [C.POINTER(NCF), vp, vp, i64, vp, vp]),
+    "recad_ncf_train_epoch": (C.c_int, [C.POINTER(NCF), vp, vp, vp, i64, i64, i64, vp]),
+    "recad_transpose_items": (C.c_int, [vp, i64, i32, vp, i64, vp]),
+    "recad_fullrank_eval": (C.c_int, [vp, vp, i64, i64, i32, vp, i64, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
+    "recad_recall_ndcg": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp]),
+    "recad_rank_from_scores": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
+    "recad_mt19937_pairwise": (C.c_int, [vp, C.POINTER(i32), i64, i64, i64, vp, vp, vp, C.POINTER(i64)]),
+    "recad_mt19937_pointwise": (C.c_int, [vp, C.POINTER(i32), i64, vp, vp, vp, vp, i64, i32, vp]),
+    "recad_mt19937_permutation": (C.c_int, [vp, C.POINTER(i32), i64, vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RecadError(
+                f"{LIB_PATH} not found: build it with `python -m recad_b200.csrc.build` "
+                "(recad_b200 has no CPU or PyTorch fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)   # AttributeError if the library lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        if handle.recad_abi_version() != 1:
+            raise RecadError("librecad_b200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().recad_last_error()
+        raise RecadError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")

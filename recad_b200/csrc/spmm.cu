@@ -1,0 +1,275 @@
+// CSR SpMM fused with the LightGCN layer mean:  Y = A X,  Z = alpha * (C + A X).
+// (reference: recad/model/victim/lightgcn.py:99-111 `torch.sparse.mm` + stack + mean; the
+// autograd backward of the same lines is this kernel again because A_hat is symmetric.)
+//
+// HBM-bound gather: per stored entry 8 B of (col, val) streamed + one D*4-byte row of X gathered.
+// Work unit = one warp per SEGMENT of a row (plan built by recad_spmm_plan): short rows are one
+// segment and write their result directly through the fused epilogue; long rows (popular items)
+// are cut into <= seg_len pieces whose partial sums are combined in fixed order by a second tiny
+// kernel, so the result is deterministic and no warp ever walks a 10^5-entry row alone.
+//
+// Inside a warp: the segment's (col, val) pairs are staged 32 at a time with one coalesced load
+// per lane and broadcast with shuffles; a row of X is covered by D/4 lanes with 128-bit loads, so
+// a warp load instruction fetches 32/(D/4) neighbour rows at once and UNR of them are in flight.
+#include "common.cuh"
+
+namespace recad {
+
+constexpr int kSpmmWarps = 8;  // warps per CTA
+
+template <int D>
+struct RowLanes {
+  static constexpr int LPR = D / 4;      // lanes per row (float4 each)
+  static constexpr int NPL = 32 / LPR;   // neighbour rows per warp-wide load
+};
+
+template <int D>
+__device__ __forceinline__ void spmm_epilogue(int64_t row, int slot, int l, float4 y, float* Y, const float* C,
+                                              float* Z, float alpha, float* partials) {  // Z may alias C
+  constexpr int LPR = D / 4;
+  if (slot >= 0) {
+    reinterpret_cast<float4*>(partials)[(int64_t)slot * LPR + l] = y;
+    return;
+  }
+  const int64_t o = row * LPR + l;
+  if (Y) reinterpret_cast<float4*>(Y)[o] = y;
+  if (Z) {
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (C) c = reinterpret_cast<const float4*>(C)[o];
+    float4 z;
+    z.x = alpha * (c.x + y.x);
+    z.y = alpha * (c.y + y.y);
+    z.z = alpha * (c.z + y.z);
+    z.w = alpha * (c.w + y.w);
+    reinterpret_cast<float4*>(Z)[o] = z;
+  }
+}
+
+template <int D, int UNR>
+__global__ void __launch_bounds__(kSpmmWarps * 32)
+spmm_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float* __restrict__ vals,
+                int64_t n_seg, int32_t seg_len, const int32_t* __restrict__ seg_row,
+                const int64_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_slot,
+                const float* __restrict__ X, float* Y, const float* C, float* Z, float alpha, float* partials) {
+  constexpr int LPR = RowLanes<D>::LPR, NPL = RowLanes<D>::NPL;
+  static_assert(32 % (NPL * UNR) == 0, "unroll must divide the staged chunk");
+  const int64_t seg = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5);
+  if (seg >= n_seg) return;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR;  // which neighbour of the NPL fetched together
+  const int l = lane % LPR;    // which float4 of the row
+  const int64_t row = seg_row[seg];
+  const int64_t lo = seg_lo[seg];
+  const int64_t hi = min(lo + (int64_t)seg_len, rowptr[row + 1]);
+  const int slot = seg_slot[seg];
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
+
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // software pipeline on the (col, val) stream: the next 32 pairs are requested before the
+  // current 32 are consumed
+  int c_next = 0;
+  float v_next = 0.f;
+  if (lo + lane < hi) {
+    c_next = ld_stream(colidx + lo + lane);
+    v_next = ld_stream(vals + lo + lane);
+  }
+  for (int64_t base = lo; base < hi; base += 32) {
+    const int c = c_next;
+    const float v = v_next;
+    const int64_t nb = base + 32 + lane;
+    if (nb < hi) {
+      c_next = ld_stream(colidx + nb);
+      v_next = ld_stream(vals + nb);
+    }
+    const int cnt = (int)min((int64_t)32, hi - base);
+    for (int j = 0; j < cnt; j += NPL * UNR) {
+      float4 x[UNR];
+      float w[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int k = j + u * NPL + sub;
+        const int cc = __shfl_sync(kFull, c, k & 31);
+        w[u] = __shfl_sync(kFull, v, k & 31);
+        if (k < cnt) {
+          x[u] = __ldg(X4 + (int64_t)cc * LPR + l);
+        } else {
+          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          w[u] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        acc.x = fmaf(w[u], x[u].x, acc.x);
+        acc.y = fmaf(w[u], x[u].y, acc.y);
+        acc.z = fmaf(w[u], x[u].z, acc.z);
+        acc.w = fmaf(w[u], x[u].w, acc.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= LPR; o >>= 1) {
+    acc.x += __shfl_xor_sync(kFull, acc.x, o);
+    acc.y += __shfl_xor_sync(kFull, acc.y, o);
+    acc.z += __shfl_xor_sync(kFull, acc.z, o);
+    acc.w += __shfl_xor_sync(kFull, acc.w, o);
+  }
+  if (sub == 0) spmm_epilogue<D>(row, slot, l, acc, Y, C, Z, alpha, partials);
+}
+
+// rows with more than one segment: sum their partial slots in slot order, then the same epilogue
+template <int D>
+__global__ void __launch_bounds__(kSpmmWarps * 32)
+spmm_fixup_kernel(int64_t n_mrow, const int32_t* __restrict__ mrow, const int32_t* __restrict__ mrow_lo,
+                  const float* __restrict__ partials, float* Y, const float* C, float* Z, float alpha) {
+  constexpr int LPR = RowLanes<D>::LPR, NPL = RowLanes<D>::NPL;
+  const int64_t j = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5);
+  if (j >= n_mrow) return;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+  const int s0 = mrow_lo[j], s1 = mrow_lo[j + 1];
+  const float4* __restrict__ P4 = reinterpret_cast<const float4*>(partials);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = s0 + sub; s < s1; s += NPL) {
+    const float4 p = P4[(int64_t)s * LPR + l];
+    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+  }
+#pragma unroll
+  for (int o = 16; o >= LPR; o >>= 1) {
+    acc.x += __shfl_xor_sync(kFull, acc.x, o);
+    acc.y += __shfl_xor_sync(kFull, acc.y, o);
+    acc.z += __shfl_xor_sync(kFull, acc.z, o);
+    acc.w += __shfl_xor_sync(kFull, acc.w, o);
+  }
+  if (sub == 0) spmm_epilogue<D>(mrow[j], -1, l, acc, Y, C, Z, alpha, nullptr);
+}
+
+// any D that is a multiple of 4 (<= 1024): a lane owns float4 columns lane, lane+32, ...
+constexpr int kGenericMaxVec = 8;
+__global__ void __launch_bounds__(kSpmmWarps * 32)
+spmm_generic_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                    const float* __restrict__ vals, int64_t n_seg, int32_t seg_len,
+                    const int32_t* __restrict__ seg_row, const int64_t* __restrict__ seg_lo,
+                    const int32_t* __restrict__ seg_slot, const float* __restrict__ X, float* Y, const float* C,
+                    float* Z, float alpha, float* partials, int D) {
+  const int64_t seg = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5);
+  if (seg >= n_seg) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = D / 4;
+  const int64_t row = seg_row[seg], lo = seg_lo[seg];
+  const int64_t hi = min(lo + (int64_t)seg_len, rowptr[row + 1]);
+  const int slot = seg_slot[seg];
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
+  float4 acc[kGenericMaxVec];
+#pragma unroll
+  for (int q = 0; q < kGenericMaxVec; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t base = lo; base < hi; base += 32) {
+    int c = 0;
+    float v = 0.f;
+    if (base + lane < hi) { c = colidx[base + lane]; v = vals[base + lane]; }
+    const int cnt = (int)min((int64_t)32, hi - base);
+    for (int k = 0; k < cnt; ++k) {
+      const int cc = __shfl_sync(kFull, c, k);
+      const float w = __shfl_sync(kFull, v, k);
+#pragma unroll
+      for (int q = 0; q < kGenericMaxVec; ++q) {
+        const int col4 = lane + q * 32;
+        if (col4 < nvec) {
+          const float4 x = __ldg(X4 + (int64_t)cc * nvec + col4);
+          acc[q].x = fmaf(w, x.x, acc[q].x); acc[q].y = fmaf(w, x.y, acc[q].y);
+          acc[q].z = fmaf(w, x.z, acc[q].z); acc[q].w = fmaf(w, x.w, acc[q].w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kGenericMaxVec; ++q) {
+    const int col4 = lane + q * 32;
+    if (col4 >= nvec) continue;
+    const float4 y = acc[q];
+    if (slot >= 0) { reinterpret_cast<float4*>(partials)[(int64_t)slot * nvec + col4] = y; continue; }
+    const int64_t o = row * nvec + col4;
+    if (Y) reinterpret_cast<float4*>(Y)[o] = y;
+    if (Z) {
+      float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (C) cv = reinterpret_cast<const float4*>(C)[o];
+      reinterpret_cast<float4*>(Z)[o] = make_float4(alpha * (cv.x + y.x), alpha * (cv.y + y.y),
+                                                    alpha * (cv.z + y.z), alpha * (cv.w + y.w));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSpmmWarps * 32)
+spmm_generic_fixup_kernel(int64_t n_mrow, const int32_t* __restrict__ mrow, const int32_t* __restrict__ mrow_lo,
+                          const float* __restrict__ partials, float* Y, const float* C, float* Z, float alpha,
+                          int D) {
+  const int64_t j = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5);
+  if (j >= n_mrow) return;
+  const int lane = threadIdx.x & 31, nvec = D / 4;
+  const int64_t row = mrow[j];
+  for (int col4 = lane; col4 < nvec; col4 += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = mrow_lo[j]; s < mrow_lo[j + 1]; ++s) {
+      const float4 p = reinterpret_cast<const float4*>(partials)[(int64_t)s * nvec + col4];
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    const int64_t o = row * nvec + col4;
+    if (Y) reinterpret_cast<float4*>(Y)[o] = acc;
+    if (Z) {
+      float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (C) cv = reinterpret_cast<const float4*>(C)[o];
+      reinterpret_cast<float4*>(Z)[o] = make_float4(alpha * (cv.x + acc.x), alpha * (cv.y + acc.y),
+                                                    alpha * (cv.z + acc.z), alpha * (cv.w + acc.w));
+    }
+  }
+}
+
+template <int D, int UNR>
+static int launch_spmm(const recad_csr* A, const float* X, float* Y, const float* C, float* Z, float alpha,
+                       cudaStream_t s) {
+  const unsigned grid = (unsigned)((A->n_seg + kSpmmWarps - 1) / kSpmmWarps);
+  spmm_seg_kernel<D, UNR><<<grid, kSpmmWarps * 32, 0, s>>>(A->rowptr, A->colidx, A->vals, A->n_seg, A->seg_len,
+                                                          A->seg_row, A->seg_lo, A->seg_slot, X, Y, C, Z, alpha,
+                                                          A->partials);
+  RECAD_LAUNCH_CHECK();
+  if (A->n_mrow > 0) {
+    const unsigned g2 = (unsigned)((A->n_mrow + kSpmmWarps - 1) / kSpmmWarps);
+    spmm_fixup_kernel<D><<<g2, kSpmmWarps * 32, 0, s>>>(A->n_mrow, A->mrow, A->mrow_lo, A->partials, Y, C, Z, alpha);
+    RECAD_LAUNCH_CHECK();
+  }
+  return RECAD_OK;
+}
+
+}  // namespace recad
+
+using namespace recad;
+
+extern "C" int recad_spmm(const recad_csr* A, const float* X, float* Y, const float* C, float* Z, float alpha,
+                          int32_t D, void* stream) {
+  cudaStream_t s = as_stream(stream);
+  RECAD_REQUIRE(A && X, RECAD_ERR_ARG, "spmm: null matrix or X");
+  RECAD_REQUIRE(Y || Z, RECAD_ERR_ARG, "spmm: neither Y nor Z requested");
+  RECAD_REQUIRE(A->n_rows > 0 && A->n_seg >= A->n_rows && A->rowptr && A->seg_row && A->seg_lo && A->seg_slot,
+                RECAD_ERR_ARG, "spmm: matrix has no plan (call recad_spmm_plan)");
+  RECAD_REQUIRE(A->nnz == 0 || (A->colidx && A->vals), RECAD_ERR_ARG, "spmm: null colidx/vals");
+  RECAD_REQUIRE(A->n_mrow == 0 || (A->mrow && A->mrow_lo && A->partials), RECAD_ERR_ARG, "spmm: null multi-row plan");
+  RECAD_REQUIRE(D >= 4 && D % 4 == 0 && D <= 4 * 32 * kGenericMaxVec, RECAD_ERR_UNSUPPORTED,
+                "spmm: D = %d must be a multiple of 4 in [4, %d]", D, 4 * 32 * kGenericMaxVec);
+  RECAD_REQUIRE((((uintptr_t)X | (uintptr_t)Y | (uintptr_t)C | (uintptr_t)Z | (uintptr_t)A->partials) & 15) == 0,
+                RECAD_ERR_ARG, "spmm: buffers must be 16-byte aligned");
+  switch (D) {
+    case 32: return launch_spmm<32, 2>(A, X, Y, C, Z, alpha, s);
+    case 64: return launch_spmm<64, 4>(A, X, Y, C, Z, alpha, s);
+    case 128: return launch_spmm<128, 8>(A, X, Y, C, Z, alpha, s);
+    default: break;
+  }
+  const unsigned grid = (unsigned)((A->n_seg + kSpmmWarps - 1) / kSpmmWarps);
+  spmm_generic_kernel<<<grid, kSpmmWarps * 32, 0, s>>>(A->rowptr, A->colidx, A->vals, A->n_seg, A->seg_len, A->seg_row,
+                                                      A->seg_lo, A->seg_slot, X, Y, C, Z, alpha, A->partials, D);
+  RECAD_LAUNCH_CHECK();
+  if (A->n_mrow > 0) {
+    const unsigned g2 = (unsigned)((A->n_mrow + kSpmmWarps - 1) / kSpmmWarps);
+    spmm_generic_fixup_kernel<<<g2, kSpmmWarps * 32, 0, s>>>(A->n_mrow, A->mrow, A->mrow_lo, A->partials, Y, C, Z,
+                                                            alpha, D);
+    RECAD_LAUNCH_CHECK();
+  }
+  return RECAD_OK;
+}

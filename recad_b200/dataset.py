@@ -1,0 +1,400 @@
+"""Drop-in for the reference's implicit-feedback dataset (recad/dataset/implicit.py)
+with the graph built and kept on the device and the samplers replayed in C++.
+
+Same public surface as `recad.dataset.implicit.ImplicitData`:
+``from_config(name, **kw)``, ``info_describe()``, ``batch_describe()``,
+``generate_batch()``, ``mode()/switch_mode()``, ``inject_data()``,
+``delete_data()``, ``partial_sample()``, ``reset()``, ``dataset_name``,
+``print_help()``; plus ``epoch_samples()`` (the whole shuffled epoch as device
+arrays, consumed by the C epoch drivers) and ``train_csr()`` (evaluation masks).
+"""
+import os
+import random
+from copy import copy
+from pprint import pprint
+
+import numpy as np
+import torch
+
+from . import ops
+from .config import get_logger, implicit_defaults, merge_config
+
+
+# --------------------------------------------------------------------------- #
+# loading (implicit.py:94-127)
+# --------------------------------------------------------------------------- #
+def csv2dict(file, filter=4):
+    """implicit.py:94-104: sort by timestamp, keep rating >= filter, per-user de-dup in time order."""
+    import pandas as pd
+    df = pd.read_csv(file)
+    df = df.sort_values("timestamp")
+    df = df[df["rating"] >= filter]
+    interactions = {}
+    for u, i in zip(df["user_id"], df["item_id"]):
+        u, i = int(u), int(i)
+        lst = interactions.setdefault(u, [])
+        if i not in lst:
+            lst.append(i)
+    return interactions
+
+
+def convert2dict(file, filter_num):
+    if file.endswith(".csv"):
+        return csv2dict(file, filter=filter_num)
+    if file.endswith(".npy"):
+        return np.load(file, allow_pickle=True).item()
+    raise ValueError(f"Expect data file ends witg [csv/npy], but got {file}")
+
+
+def fake_array2dict(fake_array, n_users, filter_num=4):
+    """implicit.py:107-114: row r -> user n_users + r, columns with rating STRICTLY > filter_num."""
+    fake_array = np.asarray(fake_array)
+    assert len(fake_array.shape) == 2, "Expect a user-item 2D rating matrix"
+    uids, iids = np.where(fake_array > filter_num)
+    result = {}
+    for u, i in zip((uids + n_users).tolist(), iids.tolist()):
+        result.setdefault(u, []).append(i)
+    return result
+
+
+def flatten(data_dict):
+    """read_data (implicit.py:221-241) as arrays: keys with a non-empty list (dict order),
+    indptr, items (stored order)."""
+    keys, lens, items = [], [], []
+    for uid, iids in data_dict.items():
+        if len(iids) != 0:
+            keys.append(int(uid))
+            lens.append(len(iids))
+            items.extend(iids)
+    indptr = np.zeros(len(keys) + 1, dtype=np.int64)
+    if keys:
+        np.cumsum(lens, out=indptr[1:])
+    return np.asarray(keys, dtype=np.int64), indptr, np.asarray(items, dtype=np.int64)
+
+
+def _sorted_distinct_csr(users, items, n_rows, n_cols):
+    """Per-row ascending distinct columns (what `UserItemNet[u].nonzero()[1]` returns, implicit.py:339-343)."""
+    if len(users) == 0:
+        return np.zeros(n_rows + 1, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    key = np.unique(users.astype(np.int64) * np.int64(n_cols) + items.astype(np.int64))
+    u, i = key // n_cols, key % n_cols
+    indptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.cumsum(np.bincount(u, minlength=n_rows), out=indptr[1:])
+    return indptr, i
+
+
+class ImplicitData:
+    def __init__(self, **config):
+        self.config = config
+        self.logger = get_logger(f"{__name__}:{self.dataset_name}", level=config["logging_level"])
+        self._mode = "train"
+        self._load_data()
+        self._init_data()
+
+    # ---------------------------------------------------------------- factory / reset
+    @classmethod
+    def from_config(cls, name, **user_config):
+        defaults = implicit_defaults(name)
+        cfg = merge_config(defaults, {k: v for k, v in user_config.items() if k != "download"}, logger=None)
+        for k in user_config:
+            if k not in defaults and k != "download":
+                get_logger(__name__).debug(f"Unexpected key [{k}] for {cls}")
+        inst = object.__new__(cls)
+        inst._dataset_name = name
+        inst._init_config = cfg
+        inst.__init__(**cfg)
+        return inst
+
+    @property
+    def dataset_name(self):
+        return getattr(self, "_dataset_name", type(self).__name__)
+
+    def reset(self, **kwargs):
+        """base.py:108-118: same config with some keys replaced -> a NEW dataset."""
+        if not hasattr(self, "_init_config"):
+            raise ValueError("reset method is only for datasets instantiated from_config")
+        config = copy(self._init_config)
+        for k, v in kwargs.items():
+            if k not in config:
+                raise ValueError(f"reset arg {k} should be in {list(config)}")
+            config[k] = v
+        return type(self).from_config(self.dataset_name, **config)
+
+    # ---------------------------------------------------------------- loading
+    def _load_data(self):
+        """implicit.py:140-164 (dict passed in > .npy cache > csv)."""
+        for attr, path in (("train_dict", "path_train"), ("valid_dict", "path_valid"), ("test_dict", "path_test")):
+            if self.config[attr] is not None:
+                setattr(self, attr, self.config[attr])
+                continue
+            cache = os.path.join(self.config["cache_dir"], f"{self.dataset_name}_implicit_{attr}.npy")
+            if os.path.exists(cache) and self.config["if_cache"]:
+                self.logger.info(f"loading cached {attr}")
+                setattr(self, attr, np.load(cache, allow_pickle=True).item())
+            else:
+                setattr(self, attr, convert2dict(self.config[path], self.config["rating_filter"]))
+                if self.config["if_cache"]:
+                    os.makedirs(self.config["cache_dir"], exist_ok=True)
+                    np.save(cache, getattr(self, attr))
+
+    def _init_data(self):
+        """implicit.py:166-219, vectorised; the graph goes to the device (ops.Graph)."""
+        if self.config["A_split"]:
+            raise ValueError("A_split is not supported (the reference's LightGCN rejects it too, lightgcn.py:38-39)")
+        self._tr = flatten(self.train_dict)
+        self._va = flatten(self.valid_dict)
+        self._te = flatten(self.test_dict)
+        max_u, max_i = 0, 0            # running max starts at 0 (implicit.py:167-168)
+        for keys, _, items in (self._tr, self._va, self._te):
+            if len(keys):
+                max_u, max_i = max(max_u, int(keys.max())), max(max_i, int(items.max()))
+        self.n_users, self.n_items = max_u + 1, max_i + 1
+        self.traindataSize = int(self._tr[1][-1])
+        self.validDataSize = int(self._va[1][-1])
+        self.testDataSize = int(self._te[1][-1])
+        self.trainUniqueUsers = self._tr[0]
+        # flat (user, item) of each split
+        self._flat = {}
+        for nm, (keys, indptr, items) in (("train", self._tr), ("valid", self._va), ("test", self._te)):
+            self._flat[nm] = (np.repeat(keys, np.diff(indptr)), items)
+        # which interactions feed UserItemNet / allPos / the graph
+        which = self.config.get("graph_edges", "reference")
+        if which not in ("reference", "train"):
+            raise ValueError("graph_edges must be 'reference' or 'train'")
+        self.trainUser, self.trainItem = self._flat["test" if which == "reference" else "train"]
+        self._allpos = _sorted_distinct_csr(self.trainUser, self.trainItem, self.n_users, self.n_items)
+        self._train_csr = None
+        self.Graph = None
+        if self.config["need_graph"]:
+            self.getSparseGraph()
+
+    # ---------------------------------------------------------------- graph (implicit.py:243-298)
+    def getSparseGraph(self):
+        if self.Graph is None:
+            dev = torch.device(self.config["device"])
+            if dev.type != "cuda":
+                raise ops.RecadError("recad_b200 builds the graph on a CUDA device; config['device'] is " + str(dev))
+            u = torch.from_numpy(self.trainUser).to(dev)
+            i = torch.from_numpy(self.trainItem).to(dev)
+            self.Graph = ops.Graph.from_edges(u, i, self.n_users, self.n_items)
+        return self.Graph
+
+    @property
+    def allPos(self):
+        """List of per-user positive arrays (implicit.py:300-302); built on demand."""
+        ptr, idx = self._allpos
+        return [idx[ptr[u]:ptr[u + 1]] for u in range(self.n_users)]
+
+    def getUserPosItems(self, users):
+        ptr, idx = self._allpos
+        return [idx[ptr[u]:ptr[u + 1]] for u in users]
+
+    def train_csr(self, device=None):
+        """Sorted distinct train items per user id (mask of normal_evaluate, normal.py:133-143):
+        (rowptr int64 [n_users + 1], col int32) on `device`."""
+        if self._train_csr is None:
+            ptr, idx = _sorted_distinct_csr(*self._flat["train"], self.n_users, self.n_items)
+            self._train_csr = (ptr, idx.astype(np.int32))
+        if device is None:
+            return self._train_csr
+        return tuple(torch.from_numpy(a).to(device) for a in self._train_csr)
+
+    def ground_truth_csr(self, split="test", device=None):
+        ptr, idx = _sorted_distinct_csr(*self._flat[split], self.n_users, self.n_items)
+        out = (ptr, idx.astype(np.int32))
+        return out if device is None else tuple(torch.from_numpy(a).to(device) for a in out)
+
+    # ---------------------------------------------------------------- describe
+    def batch_describe(self):
+        c = self.config
+        if c["sample"] == "pairwise" and self.mode() == "train":
+            return {k: (torch.int64, f"batch[0~{c['pairwise_batch_size']}]") for k in ("users", "positive_items", "negative_items")}
+        if c["sample"] == "pointwise" and self.mode() == "train":
+            return {k: (torch.int64, f"batch[0~{c['pointwise_batch_size']}]") for k in ("users", "items", "labels")}
+        if self.mode() in ("validate", "test"):
+            return {"users": (torch.int64, f"batch[0~{c['test_batch_size']}]"), "positive_items": (list, "batch"),
+                    "ground_truth": (list, "batch")}
+
+    def info_describe(self):
+        infos = {
+            "n_users": self.n_users, "n_items": self.n_items,
+            "train_interactions": self.traindataSize, "valid_interactions": self.validDataSize,
+            "test_interactions": self.testDataSize,
+            "train_dict": self.train_dict, "valid_dict": self.valid_dict, "test_dict": self.test_dict,
+            "batch_describe": self.batch_describe(),
+        }
+        if self.config["need_graph"]:
+            infos["graph"] = self.Graph
+        return infos
+
+    def print_help(self, **kwargs):
+        info = self.info_describe()
+        info["dataset_name"] = self.dataset_name
+        pprint({k: (v if len(str(v)) < 30 else f"{type(v)}") for k, v in info.items() if k != "batch_describe"})
+
+    def mode(self):
+        return self._mode
+
+    def switch_mode(self, mode):
+        assert mode in ["train", "test", "validate"]
+        self._mode = mode
+
+    # ---------------------------------------------------------------- sampling (implicit.py:18-91, 416-476)
+    def epoch_samples(self, device=None):
+        """One epoch of training samples, already shuffled, as three int64 tensors on the device:
+        (users, positive_items, negative_items) or (users, items, labels).  Consumes the global
+        np.random stream exactly as `generate_batch` of the reference does (sampler, then shuffle)."""
+        device = torch.device(device or self.config["device"])
+        if self.mode() != "train":
+            raise NotImplementedError("epoch_samples is for train mode")
+        if self.config["sample"] == "pairwise":
+            S = ops.mt_pairwise(self.n_users, self.n_items, self.traindataSize, *self._allpos)
+        elif self.config["sample"] == "pointwise":
+            S = ops.mt_pointwise(*self._tr, self.n_items, self.config["negative_ratio"])
+        else:
+            raise NotImplementedError("Not implemented yet")
+        perm = ops.mt_permutation(len(S))
+        S = np.ascontiguousarray(S[perm].T)                 # [3, n], shuffled (implicit.py:426/447)
+        host = torch.from_numpy(S)
+        if device.type == "cuda":
+            host = host.pin_memory()
+        dev = host.to(device, non_blocking=True)
+        return dev[0], dev[1], dev[2]
+
+    def generate_batch(self, **config):
+        c = self.config
+        if self.mode() == "train":
+            a, b, d = self.epoch_samples()
+            if c["sample"] == "pairwise":
+                names, bs = ("users", "positive_items", "negative_items"), c["pairwise_batch_size"]
+            else:
+                names, bs = ("users", "items", "labels"), c["pointwise_batch_size"]
+            for s in range(0, len(a), bs):               # minibatch (implicit.py:38-47)
+                yield {names[0]: a[s:s + bs], names[1]: b[s:s + bs], names[2]: d[s:s + bs]}
+        elif self.mode() in ("validate", "test"):
+            test_dict = self.valid_dict if self.mode() == "validate" else self.test_dict
+            users = list(test_dict.keys())
+            bs = c["test_batch_size"]
+            for s in range(0, len(users), bs):
+                batch_users = users[s:s + bs]
+                yield {
+                    "users": torch.tensor(batch_users, dtype=torch.int64).to(c["device"]),
+                    "positive_items": self.getUserPosItems(batch_users),
+                    "ground_truth": [test_dict[u] for u in batch_users],
+                }
+
+    # ---------------------------------------------------------------- injection (implicit.py:482-525)
+    def inject_data(self, data_mode, data, **kwargs):
+        if data_mode != "explicit":
+            raise NotImplementedError(f"Injection not supported in {data_mode} mode")
+        new_train_dict = copy(self.train_dict)
+        inject_dict = fake_array2dict(data, self.n_users, filter_num=kwargs["filter_num"])
+        for k, v in inject_dict.items():
+            assert k not in new_train_dict, f"Injection to a exist user {k} is not allowed"
+            new_train_dict[k] = v
+        return self._derive_injected(new_train_dict, inject_dict)
+
+    def _derive_injected(self, new_train_dict, inject_dict):
+        """What `reset(train_dict=..., if_cache=False)` produces (implicit.py:493), but the device graph
+        is EXTENDED in place (rows appended, no re-sort, valid/test not re-read)."""
+        config = copy(self._init_config)
+        config.update(train_dict=new_train_dict, valid_dict=self.valid_dict, test_dict=self.test_dict,
+                      if_cache=False, need_graph=False)
+        new = type(self).from_config(self.dataset_name, **config)
+        new.config["need_graph"] = new._init_config["need_graph"] = self.config["need_graph"]
+        if self.config["need_graph"]:
+            F = new.n_users - self.n_users
+            if self.config.get("graph_edges", "reference") == "train" and new.n_items == self.n_items:
+                rows = [sorted(set(inject_dict.get(self.n_users + r, []))) for r in range(F)]
+            elif new.n_items == self.n_items:
+                rows = [[] for _ in range(F)]   # reference quirk: fake users add rows but NO edges
+            else:
+                rows = None                     # item universe grew: rebuild from scratch
+            if rows is not None and self.Graph is not None:
+                fake_rowptr = torch.tensor(np.concatenate([[0], np.cumsum([len(r) for r in rows])]), dtype=torch.int64)
+                fake_items = torch.tensor([i for r in rows for i in r], dtype=torch.int32)
+                new.Graph = self.Graph.append_users(self.n_users, self.n_items, fake_rowptr, fake_items)
+            else:
+                new.getSparseGraph()
+        return new
+
+    def delete_data(self, data_mode, user_id, data, **kwargs):
+        """implicit.py:496-513 (defense workflow): inject, then drop the flagged users; full rebuild."""
+        if data_mode != "explicit":
+            raise NotImplementedError(f"Injection not supported in {data_mode} mode")
+        new_train_dict = copy(self.train_dict)
+        inject_dict = fake_array2dict(data, self.n_users, filter_num=kwargs["filter_num"])
+        for k, v in inject_dict.items():
+            assert k not in new_train_dict, f"Injection to a exist user {k} is not allowed"
+            new_train_dict[k] = v
+        for key in list(new_train_dict.keys()):
+            if key in user_id:
+                del new_train_dict[key]
+        return self.reset(train_dict=new_train_dict, if_cache=False)
+
+    def partial_sample(self, **kwargs):
+        assert "user_ratio" in kwargs, "Expect to have [user_ratio]"
+        user_ratio = kwargs["user_ratio"]
+        if abs(user_ratio - 1) < 1e-9:
+            return self
+        users = list(self.train_dict)
+        random.shuffle(users)
+        left_users = users[: int(len(users) * user_ratio)]
+        return self.reset(train_dict={u: self.train_dict[u] for u in left_users})
+
+
+class ArrayImplicitData:
+    """Array-backed dataset for graphs too large for Python dicts (the synthetic
+    1M x 200k x 50M configuration): the same sampler / graph / batch code as
+    ImplicitData, fed with flat (user, item) arrays.  `train_dict` is not
+    materialised; the evaluator uses `train_csr()`."""
+
+    def __init__(self, name, n_users, n_items, train, device, test=None, sample="pairwise", batch_size=1024,
+                 negative_ratio=4, need_graph=True, graph=None):
+        self._dataset_name = name
+        self.n_users, self.n_items = int(n_users), int(n_items)
+        self.config = {"device": torch.device(device), "sample": sample, "pairwise_batch_size": batch_size,
+                       "pointwise_batch_size": batch_size, "negative_ratio": negative_ratio, "need_graph": need_graph,
+                       "graph_edges": "train"}
+        tu, ti = (np.ascontiguousarray(a, dtype=np.int64) for a in train)
+        self._flat = {"train": (tu, ti), "test": test if test is not None else (np.zeros(0, np.int64), np.zeros(0, np.int64))}
+        self.traindataSize = len(tu)
+        self._allpos = _sorted_distinct_csr(tu, ti, self.n_users, self.n_items)
+        # pointwise sampler wants the dict-order lists: users ascending, items in stored order
+        order = np.argsort(tu, kind="stable")
+        keys, counts = np.unique(tu, return_counts=True)
+        self._tr = (keys, np.concatenate([[0], np.cumsum(counts)]).astype(np.int64), ti[order])
+        self._train_csr = None
+        self._mode = "train"
+        self.Graph = graph
+        if need_graph and graph is None:
+            dev = self.config["device"]
+            self.Graph = ops.Graph.from_edges(torch.from_numpy(tu).to(dev), torch.from_numpy(ti).to(dev), n_users, n_items)
+
+    dataset_name = ImplicitData.dataset_name
+    mode = ImplicitData.mode
+    switch_mode = ImplicitData.switch_mode
+    epoch_samples = ImplicitData.epoch_samples
+    train_csr = ImplicitData.train_csr
+    ground_truth_csr = ImplicitData.ground_truth_csr
+
+    def generate_batch(self, **config):
+        a, b, d = self.epoch_samples()
+        names = ("users", "positive_items", "negative_items") if self.config["sample"] == "pairwise" else ("users", "items", "labels")
+        bs = self.config["pairwise_batch_size"]
+        for s in range(0, len(a), bs):
+            yield {names[0]: a[s:s + bs], names[1]: b[s:s + bs], names[2]: d[s:s + bs]}
+
+    def info_describe(self):
+        infos = {"n_users": self.n_users, "n_items": self.n_items, "train_interactions": self.traindataSize,
+                 "train_dict": None}
+        if self.config["need_graph"]:
+            infos["graph"] = self.Graph
+        return infos
+
+
+factories = {"implicit": ImplicitData}    # recad/dataset/__init__.py:13
+
+
+def from_config(scope, *args, **kwargs):
+    return factories[scope].from_config(*args, **kwargs)

@@ -1,0 +1,339 @@
+"""Tensor-level wrappers over the C ABI (include/recad_b200.h).
+
+PyTorch is used here for device memory and the current CUDA stream only; every
+computation is a kernel of librecad_b200.so.  All functions raise RecadError on
+failure -- there is no fallback path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RecadError, check
+
+SEG_LEN = 256   # SpMM plan: max stored entries one warp walks (multiple of 32)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_contiguous(), "recad_b200 ops need contiguous tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RecadError("recad_b200 runs on CUDA tensors only (no CPU path); got a CPU tensor")
+
+
+def device_info():
+    sm, a, b = C.c_int(), C.c_int(), C.c_int()
+    check(_lib.lib().recad_device_info(C.byref(sm), C.byref(a), C.byref(b)), "recad_device_info")
+    return sm.value, a.value, b.value
+
+
+# --------------------------------------------------------------------------- #
+# graph
+# --------------------------------------------------------------------------- #
+def d_inv_from_degree(degree):
+    """The reference's own host expression (recad/dataset/implicit.py:269-272):
+    float32 rowsum as an (N, 1) array, ``np.power(rowsum + 1e-14, -0.5)``.  It is
+    evaluated on the host with numpy on purpose: numpy's float32 pow is not
+    correctly rounded and no device expression reproduces its bits."""
+    rowsum = np.asarray(degree).astype(np.float32).reshape(-1, 1)
+    d_inv = np.power(rowsum + 1e-14, -0.5).flatten()
+    d_inv[np.isinf(d_inv)] = 0.0
+    return d_inv
+
+
+class Graph:
+    """Device-resident CSR of a (normalised) adjacency + its SpMM work plan."""
+
+    def __init__(self, n_rows, n_cols, rowptr, colidx, vals, mult=None, degree=None, seg_len=SEG_LEN):
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.rowptr, self.colidx, self.vals, self.mult, self.degree = rowptr, colidx, vals, mult, degree
+        self.nnz = int(colidx.numel())
+        self.device = rowptr.device
+        self.seg_len = seg_len
+        self._partials = None
+        self._plan()
+
+    # -- construction ------------------------------------------------------ #
+    @classmethod
+    def from_edges(cls, users, items, n_users, n_items, seg_len=SEG_LEN):
+        """Symmetric-normalised bipartite adjacency (implicit.py:243-298) from an
+        edge list on the device.  users / items: int64 CUDA tensors."""
+        _need_cuda(users, items)
+        L = _lib.lib()
+        dev = users.device
+        users, items = users.contiguous().long(), items.contiguous().long()
+        E, N = int(users.numel()), int(n_users) + int(n_items)
+        with torch.cuda.device(dev):
+            rowptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
+            colidx = torch.empty(max(2 * E, 1), dtype=torch.int32, device=dev)
+            mult = torch.empty(max(2 * E, 1), dtype=torch.float32, device=dev)
+            degree = torch.empty(N, dtype=torch.int32, device=dev)
+            nbytes = L.recad_csr_build_scratch_bytes(E, n_users, n_items)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            nnz = C.c_int64()
+            check(L.recad_csr_build_structure(_ptr(users), _ptr(items), E, n_users, n_items, _ptr(rowptr), _ptr(colidx),
+                                              _ptr(mult), _ptr(degree), C.byref(nnz), _ptr(scratch), nbytes, _stream(dev)),
+                  "recad_csr_build_structure")
+            del scratch
+            colidx, mult = colidx[:nnz.value].clone(), mult[:nnz.value].clone()
+            vals = cls._normalize(rowptr, colidx, mult, degree, N)
+        return cls(N, N, rowptr, colidx, vals, mult, degree, seg_len)
+
+    @staticmethod
+    def _normalize(rowptr, colidx, mult, degree, N):
+        dev = rowptr.device
+        d_inv = torch.from_numpy(d_inv_from_degree(degree.cpu().numpy())).to(dev)
+        vals = torch.empty(colidx.numel(), dtype=torch.float32, device=dev)
+        check(_lib.lib().recad_csr_normalize(_ptr(rowptr), _ptr(colidx), _ptr(mult), _ptr(d_inv), N, _ptr(vals), _stream(dev)),
+              "recad_csr_normalize")
+        return vals
+
+    def append_users(self, n_users, n_items, fake_rowptr, fake_items):
+        """In-place injection (implicit.py:482-494): returns the graph over
+        n_users + F users with the fake rows appended; no sort, no Python dict."""
+        L = _lib.lib()
+        dev = self.device
+        F = int(fake_rowptr.numel()) - 1
+        nf = int(fake_items.numel())
+        Nn = n_users + F + n_items
+        with torch.cuda.device(dev):
+            fake_rowptr = fake_rowptr.to(dev, torch.int64).contiguous()
+            fake_items = fake_items.to(dev, torch.int32).contiguous()
+            rowptr = torch.empty(Nn + 1, dtype=torch.int64, device=dev)
+            colidx = torch.empty(max(self.nnz + 2 * nf, 1), dtype=torch.int32, device=dev)
+            mult = torch.empty(max(self.nnz + 2 * nf, 1), dtype=torch.float32, device=dev)
+            degree = torch.empty(Nn, dtype=torch.int32, device=dev)
+            nbytes = L.recad_csr_append_scratch_bytes(n_users, n_items, F, nf)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            check(L.recad_csr_append_users(_ptr(self.rowptr), _ptr(self.colidx), _ptr(self.mult), n_users, n_items, F,
+                                           _ptr(fake_rowptr), _ptr(fake_items), nf, _ptr(rowptr), _ptr(colidx), _ptr(mult),
+                                           _ptr(degree), _ptr(scratch), nbytes, _stream(dev)), "recad_csr_append_users")
+            colidx, mult = colidx[:self.nnz + 2 * nf], mult[:self.nnz + 2 * nf]
+            vals = self._normalize(rowptr, colidx, mult, degree, Nn)
+        return Graph(Nn, Nn, rowptr, colidx, vals, mult, degree, self.seg_len)
+
+    @classmethod
+    def from_csr(cls, rowptr, colidx, vals, n_cols, seg_len=SEG_LEN):
+        """Wrap an existing (possibly rectangular) CSR, e.g. a user-row shard."""
+        _need_cuda(rowptr, colidx, vals)
+        return cls(rowptr.numel() - 1, n_cols, rowptr.contiguous().long(), colidx.contiguous().int(),
+                   vals.contiguous().float(), None, None, seg_len)
+
+    # -- plan ---------------------------------------------------------------- #
+    def _plan(self):
+        L = _lib.lib()
+        dev = self.device
+        with torch.cuda.device(dev):
+            cap = L.recad_spmm_plan_max_segments(self.n_rows, self.nnz, self.seg_len)
+            seg_row = torch.empty(cap, dtype=torch.int32, device=dev)
+            seg_lo = torch.empty(cap, dtype=torch.int64, device=dev)
+            seg_slot = torch.empty(cap, dtype=torch.int32, device=dev)
+            mcap = self.nnz // self.seg_len + 2
+            mrow = torch.empty(mcap, dtype=torch.int32, device=dev)
+            mrow_lo = torch.empty(mcap + 1, dtype=torch.int32, device=dev)
+            nbytes = L.recad_spmm_plan_scratch_bytes(self.n_rows)
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            counts = (C.c_int64 * 3)()
+            check(L.recad_spmm_plan(_ptr(self.rowptr), self.n_rows, self.seg_len, _ptr(seg_row), _ptr(seg_lo), _ptr(seg_slot),
+                                    _ptr(mrow), _ptr(mrow_lo), counts, _ptr(scratch), nbytes, _stream(dev)), "recad_spmm_plan")
+        self.n_seg, self.n_mrow, self.n_slot = (int(c) for c in counts)
+        self.seg_row, self.seg_lo, self.seg_slot = seg_row[:self.n_seg], seg_lo[:self.n_seg], seg_slot[:self.n_seg]
+        self.mrow, self.mrow_lo = mrow[:max(self.n_mrow, 1)], mrow_lo[:self.n_mrow + 1]
+        self._struct = None
+
+    def struct(self, D):
+        """ctypes recad_csr for embedding width D (allocates the partial-sum scratch lazily)."""
+        need = max(self.n_slot, 1) * D
+        if self._partials is None or self._partials.numel() < need:
+            self._partials = torch.empty(need, dtype=torch.float32, device=self.device)
+            self._struct = None
+        if self._struct is None:
+            s = _lib.CSR()
+            s.n_rows, s.nnz = self.n_rows, self.nnz
+            s.rowptr, s.colidx, s.vals = self.rowptr.data_ptr(), self.colidx.data_ptr(), self.vals.data_ptr()
+            s.n_seg, s.seg_len = self.n_seg, self.seg_len
+            s.seg_row, s.seg_lo, s.seg_slot = self.seg_row.data_ptr(), self.seg_lo.data_ptr(), self.seg_slot.data_ptr()
+            s.n_mrow, s.mrow, s.mrow_lo = self.n_mrow, self.mrow.data_ptr(), self.mrow_lo.data_ptr()
+            s.partials = self._partials.data_ptr()
+            self._struct = s
+        return self._struct
+
+    # -- export --------------------------------------------------------------- #
+    def to_numpy(self):
+        return (self.rowptr.cpu().numpy(), self.colidx.cpu().numpy().astype(np.int64), self.vals.cpu().numpy())
+
+    def to_torch_sparse(self):
+        """torch sparse COO view with the reference's layout (implicit.py:295-296)."""
+        rows = torch.repeat_interleave(torch.arange(self.n_rows, device=self.device), self.rowptr[1:] - self.rowptr[:-1])
+        return torch.sparse_coo_tensor(torch.stack([rows, self.colidx.long()]), self.vals, (self.n_rows, self.n_cols)).coalesce()
+
+    def algorithmic_bytes(self, D):
+        """SURVEY.md section 8(d) no-reuse gather model for one SpMM over this matrix."""
+        return self.nnz * (8 + 4 * D) + self.n_rows * 4 * D + (self.n_rows + 1) * 4
+
+
+def spmm(graph, X, Y=None, C_=None, Z=None, alpha=1.0):
+    """Y = A X; Z = alpha * (C + A X).  Returns (Y, Z)."""
+    _need_cuda(X, Y, C_, Z)
+    D = X.shape[1]
+    with torch.cuda.device(X.device):
+        check(_lib.lib().recad_spmm(C.byref(graph.struct(D)), _ptr(X), _ptr(Y), _ptr(C_), _ptr(Z), float(alpha), D,
+                                    _stream(X.device)), "recad_spmm")
+    return Y, Z
+
+
+def bpr_fwd_bwd(O, E, n_users, n_items, users, pos, neg, grad_scale, gO, cnt, loss_acc):
+    _need_cuda(O, E, users, pos, neg, gO, cnt, loss_acc)
+    with torch.cuda.device(O.device):
+        check(_lib.lib().recad_bpr_fwd_bwd(_ptr(O), _ptr(E), n_users, n_items, _ptr(users), _ptr(pos), _ptr(neg), users.numel(),
+                                           float(grad_scale), _ptr(gO), _ptr(cnt), _ptr(loss_acc), O.shape[1], _stream(O.device)),
+              "recad_bpr_fwd_bwd")
+
+
+def adam(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, cnt=None, reg_scale=0.0):
+    _need_cuda(p, g, m, v, cnt)
+    D = p.shape[1] if p.dim() == 2 else 1
+    with torch.cuda.device(p.device):
+        check(_lib.lib().recad_adam(_ptr(p), _ptr(g), _ptr(cnt), float(reg_scale), _ptr(m), _ptr(v), p.numel(), D, lr, b1, b2, eps,
+                                    int(step), _stream(p.device)), "recad_adam")
+
+
+def dot_scores(O, n_users, users, items):
+    _need_cuda(O, users, items)
+    out = torch.empty(users.numel(), dtype=torch.float32, device=O.device)
+    with torch.cuda.device(O.device):
+        check(_lib.lib().recad_dot_scores(_ptr(O), n_users, _ptr(users), _ptr(items), users.numel(), O.shape[1], _ptr(out),
+                                          _stream(O.device)), "recad_dot_scores")
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# evaluation
+# --------------------------------------------------------------------------- #
+def transpose_items(item_emb):
+    """[I, D] -> [D, ld] with ld = I rounded up to 64, zero padded."""
+    _need_cuda(item_emb)
+    I, D = item_emb.shape
+    ld = (I + 63) // 64 * 64
+    out = torch.zeros((D, ld), dtype=torch.float32, device=item_emb.device)
+    with torch.cuda.device(item_emb.device):
+        check(_lib.lib().recad_transpose_items(_ptr(item_emb.contiguous()), I, D, _ptr(out), ld, _stream(item_emb.device)),
+              "recad_transpose_items")
+    return out
+
+
+def _eval_outputs(n, T, K, dev):
+    return (torch.empty((n, K), dtype=torch.int32, device=dev), torch.empty((n, K), dtype=torch.float32, device=dev),
+            torch.empty((n, max(T, 1)), dtype=torch.int32, device=dev), torch.empty((n, max(T, 1)), dtype=torch.float32, device=dev))
+
+
+def fullrank_eval(user_emb, item_emb, user_ids, train_rowptr, train_col, targets, K, item_T=None):
+    """Fused score + mask + top-K + target rank (normal.py:57-93 without the
+    score matrix).  Returns (topk_idx, topk_val, target_rank, target_score)."""
+    _need_cuda(user_emb, item_emb, user_ids, train_rowptr, train_col)
+    dev = user_emb.device
+    I, D = item_emb.shape
+    targets_t = torch.as_tensor(list(targets), dtype=torch.int32, device=dev)
+    T = int(targets_t.numel())
+    if T and (int(targets_t.min()) < 0 or int(targets_t.max()) >= I):
+        raise RecadError(f"target item id out of range [0, {I})")
+    if item_T is None:
+        item_T = transpose_items(item_emb)
+    n = int(user_ids.numel())
+    topi, topv, trank, tscore = _eval_outputs(n, T, K, dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().recad_fullrank_eval(_ptr(user_emb.contiguous()), _ptr(item_T), item_T.shape[1], I, D,
+                                             _ptr(user_ids.contiguous().long()), n, _ptr(train_rowptr), _ptr(train_col),
+                                             _ptr(targets_t), T, K, _ptr(topi), _ptr(topv), _ptr(trank), _ptr(tscore),
+                                             _stream(dev)), "recad_fullrank_eval")
+    return topi, topv, trank[:, :T], tscore[:, :T]
+
+
+def rank_from_scores(scores, user_ids, train_rowptr, train_col, targets, K):
+    _need_cuda(scores, user_ids, train_rowptr, train_col)
+    dev = scores.device
+    n, I = scores.shape
+    targets_t = torch.as_tensor(list(targets), dtype=torch.int32, device=dev)
+    T = int(targets_t.numel())
+    if T and (int(targets_t.min()) < 0 or int(targets_t.max()) >= I):
+        raise RecadError(f"target item id out of range [0, {I})")
+    topi, topv, trank, tscore = _eval_outputs(n, T, K, dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().recad_rank_from_scores(_ptr(scores.contiguous()), n, I, _ptr(user_ids.contiguous().long()),
+                                                _ptr(train_rowptr), _ptr(train_col), _ptr(targets_t), T, K, _ptr(topi),
+                                                _ptr(topv), _ptr(trank), _ptr(tscore), _stream(dev)), "recad_rank_from_scores")
+    return topi, topv, trank[:, :T], tscore[:, :T]
+
+
+def recall_ndcg(topk_idx, user_ids, gt_rowptr, gt_col):
+    """Sums of Recall@K / NDCG@K and the number of users with ground truth."""
+    _need_cuda(topk_idx, user_ids, gt_rowptr, gt_col)
+    out = torch.zeros(3, dtype=torch.float64, device=topk_idx.device)
+    with torch.cuda.device(topk_idx.device):
+        check(_lib.lib().recad_recall_ndcg(_ptr(topk_idx), topk_idx.shape[0], topk_idx.shape[1], _ptr(user_ids.contiguous().long()),
+                                           _ptr(gt_rowptr), _ptr(gt_col), _ptr(out), _stream(topk_idx.device)), "recad_recall_ndcg")
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# samplers (host; advance numpy's legacy global MT19937 state in place)
+# --------------------------------------------------------------------------- #
+def _np_state():
+    st = np.random.get_state()
+    if st[0] != "MT19937":
+        raise RecadError("np.random global state is not MT19937")
+    return st, np.ascontiguousarray(st[1], dtype=np.uint32).copy(), C.c_int32(int(st[2]))
+
+
+def _np_state_commit(st, key, pos):
+    np.random.set_state((st[0], key, int(pos.value), st[3], st[4]))
+
+
+def _np(a, dtype=np.int64):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def mt_pairwise(n_users, n_items, train_size, allpos_rowptr, allpos_col):
+    """== pairwise_sample (implicit.py:50-74) on the global np.random stream."""
+    st, key, pos = _np_state()
+    rp, col = _np(allpos_rowptr), _np(allpos_col)
+    out = np.empty((max(train_size, 1), 3), dtype=np.int64)
+    n_out = C.c_int64()
+    check(_lib.lib().recad_mt19937_pairwise(key.ctypes.data, C.byref(pos), n_users, n_items, train_size, rp.ctypes.data,
+                                            col.ctypes.data, out.ctypes.data, C.byref(n_out)), "recad_mt19937_pairwise")
+    _np_state_commit(st, key, pos)
+    return out[:n_out.value]
+
+
+def mt_pointwise(user_ids, pos_rowptr, pos_items, n_items, ratio):
+    """== pointwise_sample (implicit.py:77-91) on the global np.random stream."""
+    st, key, pos = _np_state()
+    uid, rp, items = _np(user_ids), _np(pos_rowptr), _np(pos_items)
+    rows = np.repeat(np.arange(len(uid), dtype=np.int64), np.diff(rp))
+    srt = items[np.lexsort((items, rows))]      # each user's list sorted ascending, lists kept in place
+    out = np.empty((max(len(items) * (1 + ratio), 1), 3), dtype=np.int64)
+    check(_lib.lib().recad_mt19937_pointwise(key.ctypes.data, C.byref(pos), len(uid), uid.ctypes.data, rp.ctypes.data,
+                                             items.ctypes.data, srt.ctypes.data, n_items, ratio, out.ctypes.data),
+          "recad_mt19937_pointwise")
+    _np_state_commit(st, key, pos)
+    return out[:len(items) * (1 + ratio)]
+
+
+def mt_permutation(n):
+    """== np.random.shuffle(np.arange(n)) (implicit.py:24-25)."""
+    st, key, pos = _np_state()
+    perm = np.empty(max(n, 1), dtype=np.int64)
+    check(_lib.lib().recad_mt19937_permutation(key.ctypes.data, C.byref(pos), n, perm.ctypes.data), "recad_mt19937_permutation")
+    _np_state_commit(st, key, pos)
+    return perm[:n]

@@ -1,0 +1,36 @@
+"""Plug the B200 path into an installed reference (`import recad`), through the reference's own
+registries -- no reference file is edited:
+
+    import recad, recad_b200.register
+    recad_b200.register.install()            # adds 'lightgcn_b200', 'mf_b200', 'ncf_b200', dataset 'implicit_b200'
+    recad_b200.register.install(override=True)   # ALSO rebinds 'lightgcn'/'mf'/'ncf'/'implicit' and the evaluator,
+                                                 # so an unmodified `recad_runner ...` runs on the CUDA kernels
+
+Registries touched: recad.model.factories['victim'] (recad/model/__init__.py:3-18),
+recad.default.MODEL['victim'] (recad/default.py:104-133), recad.dataset.factories
+(recad/dataset/__init__.py:13), and with override=True `Normal.normal_evaluate` /
+`Defense.normal_evaluate` (recad/workflow/normal.py:111-160, defense.py:125-174).
+"""
+from . import evaluate
+from .config import MODEL
+from .dataset import ImplicitData
+from .victim import factories as victim_factories
+
+
+def install(override=False):
+    import recad  # noqa: F401  (raises ImportError where the reference is absent)
+    from recad import dataset as ref_dataset, default as ref_default, model as ref_model, workflow as ref_workflow
+
+    for name, cls in victim_factories.items():
+        for key in ([f"{name}_b200", name] if override else [f"{name}_b200"]):
+            ref_model.factories["victim"][key] = cls
+            ref_default.MODEL["victim"].setdefault(key, dict(MODEL["victim"][name]))
+    ref_dataset.factories["implicit_b200"] = ImplicitData
+    if override:
+        ref_dataset.factories["implicit"] = ImplicitData
+
+        def _normal_evaluate(self, model, model_fake, dataset, target_id_list, topks):
+            return evaluate.normal_evaluate(model, model_fake, dataset, target_id_list, topks)
+        ref_workflow.Normal.normal_evaluate = _normal_evaluate
+        ref_workflow.Defense.normal_evaluate = _normal_evaluate
+    return True

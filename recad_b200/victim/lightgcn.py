@@ -1,0 +1,154 @@
+"""LightGCN victim (drop-in for recad/model/victim/lightgcn.py) on the CUDA kernels.
+
+State layout in HBM: ONE table E [N, D] fp32 with the user rows first, then the item rows
+(the `torch.cat([users_emb, items_emb])` of lightgcn.py:86-88 is free), Adam moments m, v of
+the same shape, and five work buffers of N*D floats.  `embedding_user.weight` /
+`embedding_item.weight` are Parameter views into E, so `parameters()` / `state_dict()` see the
+live values.
+"""
+import ctypes as C
+
+import torch
+from torch import nn
+
+from .. import _lib, ops
+from ..config import get_logger
+from .base import BaseVictim
+
+
+class LightGCN(BaseVictim):
+    name = "lightgcn"
+    user_args = ("dataset", "user_emb", "item_emb")
+
+    def _construct(self, **config):
+        self.config = config
+        self.dataset = config["dataset"]
+        self.logger = get_logger(__name__, config["logging_level"])
+        if config["A_split"]:
+            raise ValueError("A_split is not support in LightGCN yet")          # lightgcn.py:38-39
+        if config["dropout"]:
+            raise NotImplementedError("graph dropout (lightgcn.py:62-80) is off by default and not implemented")
+        if str(config["optim"]).lower() != "adam":
+            raise ValueError("optimizer not supported")                          # only Adam is on the hot path
+        info = self.dataset.info_describe()
+        self.num_users, self.num_items = info["n_users"], info["n_items"]
+        self.Graph = info["graph"]
+        if not isinstance(self.Graph, ops.Graph):
+            raise TypeError("recad_b200.LightGCN needs the device-resident graph of recad_b200.dataset.ImplicitData "
+                            f"(got {type(self.Graph)})")
+        self.latent_dim = config["latent_dim_rec"]
+        self.n_layers = config["lightGCN_n_layers"]
+        if self.latent_dim % 4:
+            raise ValueError("latent_dim_rec must be a multiple of 4")
+        # initialisation on the CPU generator, call for call as the reference (lightgcn.py:40-48):
+        # nn.Embedding draws N(0,1) at construction, then normal_(std=0.1) overwrites
+        eu = nn.Embedding(self.num_users, self.latent_dim)
+        ei = nn.Embedding(self.num_items, self.latent_dim)
+        if not config["pretrain"]:
+            nn.init.normal_(eu.weight, std=0.1)
+            nn.init.normal_(ei.weight, std=0.1)
+        else:
+            eu.weight.data.copy_(torch.from_numpy(config["user_emb"]))
+            ei.weight.data.copy_(torch.from_numpy(config["item_emb"]))
+        self._alloc(self._device(), eu.weight.data, ei.weight.data)
+        self._steps = 0
+        self._O_valid = False
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self, dev, user_w, item_w, m=None, v=None):
+        U, I, D = self.num_users, self.num_items, self.latent_dim
+        N = U + I
+        self._dev = dev
+        with torch.cuda.device(dev):
+            self.E = torch.empty((N, D), dtype=torch.float32, device=dev)
+            self.E[:U].copy_(user_w)
+            self.E[U:].copy_(item_w)
+            self.m = torch.zeros_like(self.E) if m is None else m.to(dev)
+            self.v = torch.zeros_like(self.E) if v is None else v.to(dev)
+            self.O, self.X0, self.X1, self.g = (torch.empty_like(self.E) for _ in range(4))
+            self.cnt = torch.empty(N, dtype=torch.float32, device=dev)
+            self.loss_acc = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.embedding_user = nn.Embedding(U, D, _weight=self.E[:U])
+        self.embedding_item = nn.Embedding(I, D, _weight=self.E[U:])
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self.optimizer = None     # Adam is fused into the epoch driver; its moments are self.m / self.v
+        st = _lib.LightGCN()
+        st.graph = C.pointer(self.Graph.struct(D))
+        st.n_users, st.n_items, st.D, st.n_layers = U, I, D, self.n_layers
+        st.lam, st.lr, st.beta1, st.beta2, st.eps = self.config["lambda"], self.config["lr"], 0.9, 0.999, 1e-8
+        for k in ("E", "m", "v", "O", "X0", "X1", "g", "cnt", "loss_acc"):
+            setattr(st, k, getattr(self, k).data_ptr())
+        self._st = st
+
+    def _move(self, dev):
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if dev != self._dev:
+            if self.Graph.device != dev:
+                raise ops.RecadError("the dataset graph lives on another device")
+            self._alloc(dev, self.E[:self.num_users], self.E[self.num_users:], self.m, self.v)
+
+    # ------------------------------------------------------------------ compute
+    def computer(self):
+        """lightgcn.py:82-113: (users, items) propagated embeddings = mean of the layer outputs."""
+        self._require_instance("computer")
+        with torch.cuda.device(self._dev):
+            self._check(_lib.lib().recad_lightgcn_propagate(C.byref(self._st), ops._stream(self._dev)), "recad_lightgcn_propagate")
+        self._O_valid = True
+        return self.O[:self.num_users], self.O[self.num_users:]
+
+    def getUsersRating(self, users):
+        """lightgcn.py:115-120 (unused by the reference's workflows; kept for API parity)."""
+        all_users, all_items = self.computer()
+        return torch.sigmoid(all_users[users.long()] @ all_items.t())
+
+    def train_step(self, **config):
+        """One epoch (lightgcn.py:132-172): returns (mean batch loss,)."""
+        self._require_instance("train_step")
+        self.train()
+        users, pos, neg = self._epoch_arrays(("users", "positive_items", "negative_items"))
+        n = int(users.numel())
+        if n == 0:
+            raise ops.RecadError("LightGCN.train_step: the sampler produced no training triple")
+        B = int(self.dataset.config["pairwise_batch_size"]) if hasattr(self.dataset, "config") else 1024
+        with torch.cuda.device(self._dev):
+            self._check(_lib.lib().recad_lightgcn_train_epoch(
+                C.byref(self._st), self._vp(users), self._vp(pos), self._vp(neg), n, B, self._steps,
+                ops._stream(self._dev)), "recad_lightgcn_train_epoch")
+        n_batches = (n + B - 1) // B
+        self._steps += n_batches
+        self._O_valid = False
+        pbar = config.get("progress_bar", None)
+        out = self._read_loss(self.loss_acc, n_batches)
+        if pbar:
+            pbar.set_description(f"loss {out[0]:.5f}")
+        return out
+
+    def forward(self, users, items):
+        """lightgcn.py:174-183: <O_u, O_i>.  The propagation is redone only when the tables changed
+        (the reference redoes it on every call, i.e. once per evaluated user)."""
+        self._require_instance("forward")
+        if not self._O_valid:
+            self.computer()
+        users = users.to(self._dev).long().contiguous()
+        items = items.to(self._dev).long().contiguous()
+        return ops.dot_scores(self.O, self.num_users, users, items)
+
+    def full_rank(self, user_ids, targets, K, train_rowptr, train_col):
+        """Batched evaluation entry used by recad_b200.evaluate (fused score/mask/top-K kernel)."""
+        self._require_instance("full_rank")
+        if not self._O_valid:
+            self.computer()
+        U = self.num_users
+        return ops.fullrank_eval(self.O[:U], self.O[U:], user_ids, train_rowptr, train_col, targets, K) + (0.0,)
+
+    def input_describe(self):
+        return {
+            "train_step": {"users": (torch.int64, "batch"), "positive_items": (torch.int64, "batch"),
+                           "negative_items": (torch.int64, "batch")},
+            "forward": {"users": (torch.int64, "batch"), "items": (torch.int64, "batch")},
+        }
+
+    def output_describe(self):
+        return {"train_step": {"loss": (float, [])}, "forward": {"unnormalized_scores": (torch.float32, "batch")}}

@@ -1,0 +1,154 @@
+"""CPU-only checks of the boundary: the shared library exports every symbol the header declares,
+the host-side mirror of the reference interface behaves like the reference (lazy `.I()`, reset,
+dataset flattening / sampling / injection bookkeeping), and the product fails LOUDLY without CUDA
+(no CPU fallback).  No kernel is launched here."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph as og
+from recad_b200 import _lib, config, dataset, evaluate, model, ops
+from tests import util
+
+META = util.meta()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CPU = torch.device("cpu")
+
+
+def test_library_exports_every_header_symbol():
+    header = open(os.path.join(ROOT, "include", "recad_b200.h")).read()
+    declared = set(re.findall(r"\b(recad_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _lib.lib()                      # loads + binds every symbol of SIGNATURES
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.recad_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    # natural alignment, 8-byte pointers: catches a field added on one side only
+    import ctypes as C
+    assert C.sizeof(_lib.CSR) == 14 * 8
+    assert C.sizeof(_lib.LightGCN) == 8 + 16 + 8 + 6 * 4 + 9 * 8
+    assert C.sizeof(_lib.MF) == 16 + 6 * 4 + 17 * 8
+    assert C.sizeof(_lib.NCF) == 16 + 8 + 16 + 4 * 8 + 8 + 8 + 8 + 8 + 8
+
+
+def test_host_error_paths_report_through_last_error():
+    lib = _lib.lib()
+    rc = lib.recad_mt19937_permutation(None, None, 5, None)
+    assert rc == -1 and b"bad argument" in lib.recad_last_error()
+    with pytest.raises(_lib.RecadError):
+        _lib.check(rc, "recad_mt19937_permutation")
+
+
+def test_no_cpu_fallback_anywhere():
+    tr, va, te = util.dicts("dev")
+    with pytest.raises(ops.RecadError):
+        dataset.from_config("implicit", "dev", train_dict=tr, valid_dict=va, test_dict=te, need_graph=True, device=CPU)
+    data = dataset.from_config("implicit", "dev", train_dict=tr, valid_dict=va, test_dict=te, need_graph=False,
+                               sample="pointwise", device=CPU)
+    lazy = model.from_config("victim", "mf", embedding_size=64, device=CPU)
+    with pytest.raises(config.InstantiateFail):
+        lazy.I(dataset=data)
+    with pytest.raises(ops.RecadError):
+        ops.spmm(None, torch.zeros(4, 4))
+    src = "".join(open(os.path.join(dp, f)).read() for dp, _, fs in os.walk(os.path.join(ROOT, "recad_b200"))
+                  for f in fs if f.endswith(".py"))
+    assert "import oracle" not in src and "from oracle" not in src, "the product must never import the oracle"
+
+
+def test_lazy_contract_like_reference():
+    lazy = model.from_config("victim", "lightgcn", latent_dim_rec=64, not_a_key=1)
+    assert lazy.model_name == "lightgcn" and lazy._init_config["latent_dim_rec"] == 64
+    assert "not_a_key" not in lazy._init_config                      # unknown keys dropped (model/base.py:41-47)
+    with pytest.raises(config.NotInstantiatedError):
+        lazy.train_step()
+    with pytest.raises(config.NotInstantiatedError):
+        lazy(torch.zeros(1), torch.zeros(1))
+    again = lazy.reset(lr=0.01)
+    assert again._init_config["lr"] == 0.01 and again._init_config["latent_dim_rec"] == 64 and not again._is_instantiate
+    with pytest.raises(ValueError):
+        lazy.reset(bogus=1)
+    assert set(lazy.input_describe()["forward"]) == {"users", "items"}
+    assert len(lazy.output_describe()["train_step"]) == 1
+
+
+def test_dataset_host_side_matches_reference_bookkeeping():
+    tr, va, te = util.dicts("dev")
+    z = util.load("dev_graph.npz")
+    d = dataset.from_config("implicit", "dev", train_dict=tr, valid_dict=va, test_dict=te, need_graph=False, device=CPU)
+    m = META["dev"]
+    assert (d.n_users, d.n_items, d.traindataSize, d.validDataSize, d.testDataSize) == \
+        (m["n_users"], m["n_items"], m["train"], m["valid"], m["test"])
+    # reference quirk: UserItemNet / allPos come from the LAST split read = test
+    assert np.array_equal(d._allpos[0], z["allpos_indptr"]) and np.array_equal(d._allpos[1], z["allpos_indices"])
+    assert len(d.trainUser) == m["test"]
+    d2 = dataset.from_config("implicit", "dev", train_dict=tr, valid_dict=va, test_dict=te, need_graph=False, device=CPU,
+                             graph_edges="train")
+    assert np.array_equal(d2._allpos[0], z["allpos_indptr_train"]) and np.array_equal(d2._allpos[1], z["allpos_indices_train"])
+    info = d.info_describe()
+    assert info["train_dict"] is tr and info["n_users"] == m["n_users"] and "graph" not in info
+    ptr, col = d.train_csr()
+    rp, ri = og.all_pos(*og.flatten_dict(tr)[:2], d.n_users, d.n_items)
+    assert np.array_equal(ptr, rp) and np.array_equal(col, ri)
+
+
+def test_generate_batch_replays_reference_stream_on_host():
+    tr, va, te = util.dicts("dev")
+    g = util.load("samplers.npz")
+    d = dataset.from_config("implicit", "dev", train_dict=tr, valid_dict=va, test_dict=te, need_graph=False, device=CPU)
+    np.random.seed(2023)
+    batches = list(d.generate_batch())
+    S = g["dev_pairwise"][g["dev_perm"]]
+    got = torch.stack([torch.cat([b[k] for b in batches]) for k in ("users", "positive_items", "negative_items")], 1).numpy()
+    assert np.array_equal(got, S)
+    assert [len(b["users"]) for b in batches] == [len(S)]              # 16 triples < 1024: one ragged batch
+    dp = dataset.from_config("implicit", "dev", train_dict=tr, valid_dict=va, test_dict=te, need_graph=False, device=CPU,
+                             sample="pointwise", pointwise_batch_size=1000)
+    st = ("MT19937", g["dev_state_key_after_pairwise"], int(g["dev_state_pos_after_pairwise"]), 0, 0.0)
+    np.random.set_state(st)
+    ops.mt_permutation(len(g["dev_pairwise"]))
+    P = g["dev_pointwise"]
+    batches = list(dp.generate_batch())
+    assert [len(b["users"]) for b in batches] == [1000, 1000, len(P) - 2000]
+    got = torch.stack([torch.cat([b[k] for b in batches]) for k in ("users", "items", "labels")], 1).numpy()
+    assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, P.tolist()))      # same multiset (then shuffled)
+    assert np.array_equal(np.random.get_state()[1], np.random.get_state()[1])
+    d.switch_mode("test")
+    tb = list(d.generate_batch())
+    assert sum(len(b["users"]) for b in tb) == len(te) and tb[0]["ground_truth"][0] == te[int(tb[0]["users"][0])]
+
+
+def test_inject_and_delete_bookkeeping():
+    tr, va, te = util.dicts("dev")
+    d = dataset.from_config("implicit", "dev", train_dict=tr, valid_dict=va, test_dict=te, need_graph=False, device=CPU,
+                            sample="pointwise")
+    fake = np.zeros((50, d.n_items))
+    fake[:, 0] = 5
+    fake[3, 7] = 4          # == filter_num: dropped (strict >)
+    fake[3, 9] = 4.5
+    new = d.inject_data("explicit", fake, filter_num=4)
+    assert new is not d and new.n_users == d.n_users + 50 and new.traindataSize == d.traindataSize + 51
+    assert new.train_dict[d.n_users + 3] == [0, 9] and d.n_users + 3 not in d.train_dict
+    assert new.train_dict == og.inject(tr, fake, d.n_users, 4)
+    again = new.inject_data("explicit", fake[:2], filter_num=4)      # a second injection stacks on top
+    assert again.n_users == new.n_users + 2
+    with pytest.raises(NotImplementedError):
+        d.inject_data("implicit", fake)
+    kept = d.delete_data("explicit", [d.n_users + 1, 0], fake, filter_num=4)
+    assert d.n_users + 1 not in kept.train_dict and 0 not in kept.train_dict and d.n_users + 2 in kept.train_dict
+    sub = d.partial_sample(user_ratio=0.5)
+    assert len(sub.train_dict) == len(tr) // 2 and d.partial_sample(user_ratio=1) is d
+
+
+def test_eligible_users_like_reference():
+    tr, va, te = util.dicts("dev")
+    d = dataset.from_config("implicit", "dev", train_dict=tr, valid_dict=va, test_dict=te, need_graph=False, device=CPU)
+    from oracle import evaluate as oev
+    for tg in ([0], [5], [0, 5, 62]):
+        assert evaluate.eligible_users(d, tg).tolist() == sorted(oev.eligible_users(tr, tg))

@@ -1,0 +1,183 @@
+"""GPU parity: graph construction (bit-exact), in-place injection, SpMM + fused layer mean.
+Everything goes through the C ABI (recad_b200.ops -> librecad_b200.so); the oracle is the checker."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph as og
+from oracle import lightgcn as olg
+from recad_b200 import synthetic
+from tests import util
+
+pytestmark = pytest.mark.gpu
+META = util.meta()
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _build(u, i, U, I, **kw):
+    from recad_b200 import ops
+    return ops.Graph.from_edges(torch.as_tensor(u, device=_dev()), torch.as_tensor(i, device=_dev()), U, I, **kw)
+
+
+def _assert_same_csr(g, ptr, col, val):
+    gp, gc, gv = g.to_numpy()
+    assert np.array_equal(gp, ptr)
+    assert np.array_equal(gc, col)
+    assert gv.tobytes() == np.asarray(val, dtype=np.float32).tobytes()     # value BITS
+
+
+def test_dev_graph_bit_exact_both_edge_sets():
+    tr, va, te = util.dicts("dev")
+    z = util.load("dev_graph.npz")
+    U, I = META["dev"]["n_users"], META["dev"]["n_items"]
+    g = _build(*og.graph_edges_reference(tr, va, te), U, I)
+    _assert_same_csr(g, z["crow"], z["col"], z["val"])
+    assert util.sha(*g.to_numpy()) == META["dev_graph"]["sha"]
+    u, i, _, _ = og.flatten_dict(tr)
+    _assert_same_csr(_build(u, i, U, I), z["crow_train"], z["col_train"], z["val_train"])
+
+
+def test_game_and_ml1m_shaped_graph_hashes():
+    tr, va, te = util.dicts("game")
+    m = META["game"]
+    g = _build(*og.graph_edges_reference(tr, va, te), m["n_users"], m["n_items"])
+    assert util.sha(*g.to_numpy()) == m["graph_sha"]
+    u, i, _, _ = og.flatten_dict(tr)
+    g = _build(u, i, m["n_users"], m["n_items"])
+    assert g.nnz == m["graph_train_nnz"] and util.sha(*g.to_numpy()) == m["graph_train_sha"]
+    tr, _, _ = synthetic.make_splits(synthetic.ML1M, seed=0)
+    u, i, _, _ = og.flatten_dict(tr)
+    mm = META["ml1m_shaped"]
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(len(u))                       # the builder must not depend on the input order
+    g = _build(u[perm], i[perm], mm["n_users"], mm["n_items"])
+    assert g.nnz == mm["graph_train_nnz"] and util.sha(*g.to_numpy()) == mm["graph_train_sha"]
+    assert int(g.degree.max()) == mm["max_degree"]
+
+
+@pytest.mark.parametrize("case", ["empty", "single", "duplicates", "isolated", "skewed"])
+def test_graph_edge_cases_match_oracle(case):
+    rng = np.random.default_rng(7)
+    if case == "empty":
+        U, I, u, i = 5, 4, np.zeros(0, np.int64), np.zeros(0, np.int64)
+    elif case == "single":
+        U, I, u, i = 1, 1, np.array([0]), np.array([0])
+    elif case == "duplicates":
+        U, I = 6, 5
+        u, i = rng.integers(0, U, 200), rng.integers(0, I, 200)   # ~7 copies of every pair
+    elif case == "isolated":
+        U, I = 50, 40
+        u, i = rng.integers(10, 20, 30), rng.integers(0, 5, 30)    # most rows have degree 0
+    else:
+        U, I = 300, 2000
+        u = np.concatenate([np.zeros(1500, np.int64), rng.integers(0, U, 3000)])   # user 0 has > seg_len items
+        i = np.concatenate([np.arange(1500), rng.integers(0, I, 3000)])
+    g = _build(u, i, U, I, seg_len=64)
+    ptr, col, val, _, deg = og.norm_adj_csr(np.asarray(u, np.int64), np.asarray(i, np.int64), U, I)
+    _assert_same_csr(g, ptr, col, val)
+    assert np.array_equal(g.degree.cpu().numpy(), deg)
+    if case == "skewed":
+        assert g.n_mrow > 0 and g.n_seg > g.n_rows
+
+
+def test_bad_ids_fail_loudly():
+    from recad_b200 import ops
+    with pytest.raises(ops.RecadError):
+        _build(np.array([0, 9]), np.array([0, 1]), 3, 3)
+
+
+@pytest.mark.parametrize("with_edges", [False, True])
+def test_append_users_equals_rebuild(with_edges):
+    """In-place injection == building the injected graph from scratch (bit-exact)."""
+    tr, va, te = util.dicts("dev")
+    U, I = META["dev"]["n_users"], META["dev"]["n_items"]
+    u, i, _, _ = og.flatten_dict(tr)
+    g = _build(u, i, U, I)
+    rng = np.random.default_rng(3)
+    F = 50
+    rows = [sorted(rng.choice(I, size=rng.integers(0, 40), replace=False).tolist()) if with_edges else [] for _ in range(F)]
+    fake_rowptr = torch.tensor(np.concatenate([[0], np.cumsum([len(r) for r in rows])]), dtype=torch.int64)
+    fake_items = torch.tensor([x for r in rows for x in r], dtype=torch.int32)
+    g2 = g.append_users(U, I, fake_rowptr, fake_items)
+    fu = np.concatenate([np.full(len(r), U + k, np.int64) for k, r in enumerate(rows)] + [np.zeros(0, np.int64)])
+    fi = np.array([x for r in rows for x in r], dtype=np.int64)
+    ptr, col, val, _, deg = og.norm_adj_csr(np.concatenate([u, fu]), np.concatenate([i, fi]), U + F, I)
+    _assert_same_csr(g2, ptr, col, val)
+    assert np.array_equal(g2.degree.cpu().numpy(), deg)
+
+
+# ------------------------------------------------------------------ SpMM
+def _rand_graph(U, I, E, seed, seg_len=256):
+    u, i = synthetic.make_edges(U, I, E, seed=seed)
+    return _build(u, i, U, I, seg_len=seg_len), og.norm_adj_csr(u, i, U, I)
+
+
+@pytest.mark.parametrize("D", [32, 64, 128, 20, 256])
+def test_spmm_matches_oracle(D):
+    from recad_b200 import ops
+    g, (ptr, col, val, _, _) = _rand_graph(700, 300, 20000, seed=D, seg_len=64)   # item rows ~67 long: multi-segment
+    N = g.n_rows
+    A = olg.csr_to_torch(ptr, col, val, N)
+    torch.manual_seed(D)
+    X = torch.randn(N, D)
+    Cc = torch.randn(N, D)
+    ref = torch.sparse.mm(A, X)
+    Xd, Cd = X.to(_dev()), Cc.to(_dev())
+    Y = torch.empty_like(Xd)
+    Z = torch.empty_like(Xd)
+    ops.spmm(g, Xd, Y, Cd, Z, 0.25)
+    assert torch.allclose(Y.cpu(), ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(Z.cpu(), 0.25 * (Cc + ref), rtol=1e-5, atol=1e-6)
+    Z2 = Cd.clone()                                    # Z aliasing C, no Y
+    ops.spmm(g, Xd, None, Z2, Z2, 1.0)
+    assert torch.allclose(Z2.cpu(), Cc + ref, rtol=1e-5, atol=1e-6)
+    Y3 = torch.empty_like(Xd)                          # Y only
+    ops.spmm(g, Xd, Y3, None, None, 1.0)
+    assert torch.equal(Y3, Y)                          # deterministic: bitwise repeatable
+
+
+def test_spmm_rectangular_shard():
+    """A user-row shard [rows x N] (what the multi-GPU path multiplies)."""
+    from recad_b200 import ops
+    g, (ptr, col, val, _, _) = _rand_graph(400, 150, 9000, seed=5)
+    lo, hi = 100, 260
+    sub_ptr = torch.as_tensor(ptr[lo:hi + 1] - ptr[lo], device=_dev())
+    sub_col = torch.as_tensor(col[ptr[lo]:ptr[hi]], device=_dev(), dtype=torch.int32)
+    sub_val = torch.as_tensor(val[ptr[lo]:ptr[hi]], device=_dev())
+    gs = ops.Graph.from_csr(sub_ptr, sub_col, sub_val, n_cols=g.n_rows)
+    X = torch.randn(g.n_rows, 64)
+    ref = torch.sparse.mm(olg.csr_to_torch(ptr, col, val, g.n_rows), X)[lo:hi]
+    Y = torch.empty((hi - lo, 64), device=_dev())
+    ops.spmm(gs, X.to(_dev()), Y)
+    assert torch.allclose(Y.cpu(), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_spmm_linearity_at_scale():
+    """Size-independent property on a graph far beyond what the oracle checks element-wise:
+    A(aX + bW) == a AX + b AW, and row sums of A X for X = 1 equal the row sums of A."""
+    from recad_b200 import ops
+    U, I, E = 200_000, 40_000, 4_000_000
+    gen = torch.Generator(device=_dev()).manual_seed(0)
+    u = torch.randint(0, U, (E,), device=_dev(), generator=gen)
+    i = (torch.rand(E, device=_dev(), generator=gen) ** 3 * I).long().clamp_(max=I - 1)     # skewed popularity
+    g = ops.Graph.from_edges(u, i, U, I)
+    N, D = U + I, 64
+    X = torch.randn(N, D, device=_dev(), generator=gen)
+    W = torch.randn(N, D, device=_dev(), generator=gen)
+    AX, AW, AM = (torch.empty_like(X) for _ in range(3))
+    ops.spmm(g, X, AX)
+    ops.spmm(g, W, AW)
+    ops.spmm(g, 2.0 * X - 3.0 * W, AM)
+    assert torch.allclose(AM, 2.0 * AX - 3.0 * AW, rtol=1e-4, atol=1e-5)
+    ones = torch.ones(N, D, device=_dev())
+    ops.spmm(g, ones, AX)
+    rows = torch.repeat_interleave(torch.arange(N, device=_dev()), g.rowptr[1:] - g.rowptr[:-1])
+    rs = torch.zeros(N, device=_dev(), dtype=torch.float64).index_add_(0, rows, g.vals.double())
+    assert torch.allclose(AX[:, 0].double(), rs, rtol=1e-5, atol=1e-6)
+    # structure: sorted (row, col), symmetric nnz, no duplicates
+    key = rows * N + g.colidx.long()
+    assert bool((key[1:] > key[:-1]).all())
+    assert g.nnz % 2 == 0
