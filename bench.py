@@ -141,8 +141,10 @@ def run_b200(args, w):
     graph = ops.Graph.from_edges(eu, ei, U, I)
     torch.cuda.synchronize()
     t_graph = time.time() - t0
-    data = dataset.ArrayImplicitData(args.workload, U, I, (eu.cpu().numpy(), ei.cpu().numpy()), dev, batch_size=B, graph=graph)
     del eu, ei
+    gtest = torch.Generator().manual_seed(1)          # one held-out item per user: ground truth of Recall/NDCG@20
+    test = (np.arange(U, dtype=np.int64), torch.randint(0, I, (U,), generator=gtest).numpy())
+    data = dataset.ArrayImplicitData(args.workload, U, I, None, dev, batch_size=B, graph=graph, test=test, prefetch=False)
     torch.manual_seed(2023)
     m = model.from_config("victim", "lightgcn", latent_dim_rec=D, lightGCN_n_layers=L, device=dev).I(dataset=data)
     rp, rc = data.train_csr(dev)
@@ -154,22 +156,23 @@ def run_b200(args, w):
     sets = [data.epoch_samples(dev) for _ in range(2)]
     torch.cuda.synchronize()
     t_sampler = (time.time() - t0) / 2
-    n = int(sets[0][0].numel())
+    n = int(sets[0][0].shape[0])
     n_batches = (n + B - 1) // B
+    gt_ptr, gt_col = data.ground_truth_csr("test", dev)
     import ctypes as C
     from recad_b200 import _lib
     lib = _lib.lib()
 
     def epoch(samples):
-        us, ps, ns = samples
-        _lib.check(lib.recad_lightgcn_train_epoch(C.byref(m._st), m._vp(us), m._vp(ps), m._vp(ns), int(us.numel()), B, m._steps,
+        rows, perm = samples
+        _lib.check(lib.recad_lightgcn_train_epoch(C.byref(m._st), m._vp(rows), m._vp(perm), int(rows.shape[0]), B, m._steps,
                                                   ops._stream(dev)), "recad_lightgcn_train_epoch")
-        m._steps += (int(us.numel()) + B - 1) // B
+        m._steps += (int(rows.shape[0]) + B - 1) // B
         m._O_valid = False
 
     def full_eval():
         topi, topv, rank_, score, _ = m.full_rank(users_all, target, 20, rp, rc)
-        return topi, rank_
+        return ops.recall_ndcg(topi, users_all, gt_ptr, gt_col), rank_
 
     for k in range(args.warmup):
         epoch(sets[k % 2])
@@ -208,16 +211,23 @@ def run_b200(args, w):
     achieved = alg / (spmm_ms * 1e-3) / 1e9
 
     # end to end through the public API: host sampler + pinned H2D + epoch + loss D2H, then evaluation + metric D2H
-    e2e = []
-    for k in range(max(1, min(args.steps, 2))):
+    # (the next epoch's samples are drawn on a background thread while the GPU works: dataset._EpochPipe)
+    data.config["prefetch"] = True
+    data._pipe.prefetch = True
+    e2e, metrics = [], None
+    for k in range(1 + max(1, args.steps)):            # first pass primes the prefetch pipeline and is not counted
         torch.cuda.synchronize()
         t0 = time.time()
-        m.train_step()
-        res = evaluate.recall_ndcg(m, data, K=20, split="train", users=users_all)
+        loss_e2e = m.train_step()[0]
+        sums, rank_ = full_eval()
+        sums = sums.cpu().numpy()
+        hr20 = float((rank_[:, 0] < 20).float().mean().item())
         torch.cuda.synchronize()
-        e2e.append(time.time() - t0)
-    h2d = n * 3 * 8
-    d2h = 4 * 8 + 3 * 8
+        if k:
+            e2e.append(time.time() - t0)
+        metrics = {"loss": loss_e2e, "recall@20": sums[0] / max(sums[2], 1), "ndcg@20": sums[1] / max(sums[2], 1), "HR@20(target 0)": hr20}
+    h2d = n * 4 * 8            # samples [n, 3] + perm [n], int64
+    d2h = 4 * 8 + 3 * 8 + 4
 
     out = {
         "metric": METRIC, "value": round(step_ms / 1e3, 6), "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -235,7 +245,9 @@ def run_b200(args, w):
                      "ms_per_launch": round(spmm_ms, 4), "algorithmic_bytes": alg, "peak_source": pk_src,
                      "model": "no-reuse gather: nnz*(8+4D) + 3*N*4D + (N+1)*4"},
         "e2e": {"value": round(float(np.mean(e2e)), 6), "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "includes": "C++ MT19937 sampler + shuffle on host, pinned H2D of the samples, epoch, loss D2H, full-rank eval, metric D2H"},
+                "includes": "train_step(): exact C++ MT19937 sampler + shuffle on host (next epoch prefetched on a thread), pinned H2D of "
+                            "samples + permutation, epoch, loss D2H; then full-rank eval of all users, Recall/NDCG/HR D2H",
+                "metrics_last_step": metrics},
         "gpu_launches": args.steps * (n_batches * (2 * L * (2 if graph.n_mrow else 1) + 2) + 3),
         "clocks": clocks.summary(),
     }

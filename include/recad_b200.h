@@ -139,7 +139,8 @@ int recad_spmm(const recad_csr* A, const float* X, float* Y, const float* C, flo
 
 /* Fused gather + dot + softplus + L2-reg + gradient scatter for one batch.
  *   O [dev] float[N, D] propagated mean (users first), E [dev] float[N, D] ego table
- *   users/pos/neg [dev] int64[B] (item ids WITHOUT the n_users offset)
+ *   samples [dev] int64[*, 3] rows (user, pos, neg) (item ids WITHOUT the n_users offset);
+ *   perm [dev] int64[B] row index of each of the B samples of this batch (NULL = rows 0..B-1)
  *   grad_scale = 1 / (L + 1): folded into the scattered gradient so that gO is
  *     already d loss / d (sum of layers)
  *   gO  [dev] float[N, D]  += ; must be zeroed by the caller
@@ -148,7 +149,7 @@ int recad_spmm(const recad_csr* A, const float* X, float* Y, const float* C, flo
  *   loss_acc [dev] double[4]: [0] += sum softplus(x), [1] += sum (|E_u|^2+|E_p|^2+|E_n|^2),
  *                             [3] is set non-zero (as an int) if a sample id is out of range */
 int recad_bpr_fwd_bwd(const float* O, const float* E, int64_t n_users, int64_t n_items,
-                      const int64_t* users, const int64_t* pos, const int64_t* neg, int64_t B,
+                      const int64_t* samples, const int64_t* perm, int64_t B,
                       float grad_scale, float* gO, float* cnt, double* loss_acc, int32_t D,
                       void* stream);
 
@@ -182,15 +183,17 @@ typedef struct recad_lightgcn {
 /* O = mean_k A^k E (lightgcn.py:82-113).  L fused SpMMs, nothing else. */
 int recad_lightgcn_propagate(const recad_lightgcn* st, void* stream);
 
-/* One epoch of `train_step` (lightgcn.py:132-172) over pre-sampled, pre-shuffled
- * triples [dev] int64[n_samples] x 3, cut into batches of `batch` (last ragged,
- * implicit.py:38-47).  Per batch: propagate, BPR, Horner backward, dense Adam.
+/* One epoch of `train_step` (lightgcn.py:132-172) over pre-sampled triples
+ * samples [dev] int64[n_samples, 3] = (user, pos, neg) rows in SAMPLER order, visited in the
+ * order perm [dev] int64[n_samples] (the epoch shuffle of implicit.py:18-35; NULL = identity):
+ * batch b is rows perm[b*batch .. (b+1)*batch) (last ragged, implicit.py:38-47).  The shuffle
+ * is an index indirection inside the kernels, the sample array is never rewritten.
+ * Per batch: propagate, BPR, Horner backward, dense Adam.
  * step0 = Adam steps taken before this epoch.  The mean of the per-batch losses
  * is left in loss_acc[2] / n_batches: read it with ONE device->host copy after
  * the epoch (the reference syncs once per batch, lightgcn.py:169). */
-int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* users, const int64_t* pos,
-                               const int64_t* neg, int64_t n_samples, int64_t batch, int64_t step0,
-                               void* stream);
+int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* samples, const int64_t* perm,
+                               int64_t n_samples, int64_t batch, int64_t step0, void* stream);
 
 /* scores[b] = <O[users[b]], O[n_users + items[b]]> (lightgcn.py:174-183 after a
  * propagate; O must be current). */
@@ -215,10 +218,10 @@ typedef struct recad_mf {
 int recad_mf_forward(const recad_mf* st, const int64_t* users, const int64_t* items, int64_t B,
                      float* pred, void* stream);
 /* One epoch of MF.train_step (mf.py:49-69): BCEWithLogits (mean) + dense Adam on
- * the four tables, per batch.  labels [dev] int64.  Loss as in the LightGCN epoch. */
-int recad_mf_train_epoch(const recad_mf* st, const int64_t* users, const int64_t* items,
-                         const int64_t* labels, int64_t n_samples, int64_t batch, int64_t step0,
-                         void* stream);
+ * the four tables, per batch.  samples [dev] int64[n, 3] = (user, item, label) rows, perm as in
+ * recad_lightgcn_train_epoch.  Loss as in the LightGCN epoch. */
+int recad_mf_train_epoch(const recad_mf* st, const int64_t* samples, const int64_t* perm,
+                         int64_t n_samples, int64_t batch, int64_t step0, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * NCF / NeuMF-end pointwise BCE step  (recad/model/victim/ncf.py:32-53, 112-153)
@@ -253,9 +256,8 @@ typedef struct recad_ncf {
 int recad_ncf_forward(const recad_ncf* st, const int64_t* users, const int64_t* items, int64_t B,
                       float* pred, void* stream);
 /* One epoch of NCF.train_step (ncf.py:133-153); loss bookkeeping as in the MF epoch. */
-int recad_ncf_train_epoch(const recad_ncf* st, const int64_t* users, const int64_t* items,
-                          const int64_t* labels, int64_t n_samples, int64_t batch, int64_t step0,
-                          void* stream);
+int recad_ncf_train_epoch(const recad_ncf* st, const int64_t* samples, const int64_t* perm,
+                          int64_t n_samples, int64_t batch, int64_t step0, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * Full-ranking evaluation  (recad/workflow/normal.py:57-93, 111-160;
@@ -310,7 +312,7 @@ int recad_recall_ndcg(const int32_t* topk_idx, int64_t n_eval, int32_t K, const 
  * (users without positives are dropped, implicit.py:63-64). */
 int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items,
                            int64_t train_size, const int64_t* allpos_rowptr,
-                           const int64_t* allpos_col, int64_t* out, int64_t* n_out);
+                           const int32_t* allpos_col, int64_t* out, int64_t* n_out);
 /* Per user k (dict order): its |pos| positives (label 1, stored order) then
  * ratio * |pos| negatives drawn with replacement from the ascending complement.
  * pos_sorted: the same lists sorted ascending (for the complement).

@@ -71,17 +71,17 @@ SIGNATURES = {
     "recad_spmm_plan_scratch_bytes": (i64, [i64]),
     "recad_spmm_plan": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, C.POINTER(i64), vp, i64, vp]),
     "recad_spmm": (C.c_int, [C.POINTER(CSR), vp, vp, vp, vp, f32, i32, vp]),
-    "recad_bpr_fwd_bwd": (C.c_int, [vp, vp, i64, i64, vp, vp, vp, i64, f32, vp, vp, vp, i32, vp]),
+    "recad_bpr_fwd_bwd": (C.c_int, [vp, vp, i64, i64, vp, vp, i64, f32, vp, vp, vp, i32, vp]),
     "recad_adam": (C.c_int, [vp, vp, vp, f32, vp, vp, i64, i32, f32, f32, f32, f32, i64, vp]),
     "recad_lightgcn_propagate": (C.c_int, [C.POINTER(LightGCN), vp]),
-    "recad_lightgcn_train_epoch": (C.c_int, [C.POINTER(LightGCN), vp, vp, vp, i64, i64, i64, vp]),
+    "recad_lightgcn_train_epoch": (C.c_int, [C.POINTER(LightGCN), vp, vp, i64, i64, i64, vp]),
     "recad_dot_scores": (C.c_int, [vp, i64, vp, vp, i64, i32, vp, vp]),
     "recad_mf_forward": (C.c_int, [C.POINTER(MF), vp, vp, i64, vp, vp]),
-    "recad_mf_train_epoch": (C.c_int, [C.POINTER(MF), vp, vp, vp, i64, i64, i64, vp]),
+    "recad_mf_train_epoch": (C.c_int, [C.POINTER(MF), vp, vp, i64, i64, i64, vp]),
     "recad_ncf_layout": (C.c_int, [i32, i32, i64, i64, C.POINTER(i64)]),
     "recad_ncf_work_floats": (i64, [i32, i32, i64]),
     "recad_ncf_forward": (C.c_int, [C.POINTER(NCF), vp, vp, i64, vp, vp]),
-    "recad_ncf_train_epoch": (C.c_int, [C.POINTER(NCF), vp, vp, vp, i64, i64, i64, vp]),
+    "recad_ncf_train_epoch": (C.c_int, [C.POINTER(NCF), vp, vp, i64, i64, i64, vp]),
     "recad_transpose_items": (C.c_int, [vp, i64, i32, vp, i64, vp]),
     "recad_fullrank_eval": (C.c_int, [vp, vp, i64, i64, i32, vp, i64, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
     "recad_recall_ndcg": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp]),

@@ -16,7 +16,7 @@ namespace recad {
 template <int LPR, int VPL>
 __global__ void __launch_bounds__(256)
 bpr_kernel(const float* __restrict__ O, const float* __restrict__ E, int64_t n_users, int64_t n_items,
-           const int64_t* __restrict__ users, const int64_t* __restrict__ pos, const int64_t* __restrict__ neg,
+           const int64_t* __restrict__ samples, const int64_t* __restrict__ perm,
            int64_t B, float grad_scale, float* __restrict__ gO, float* __restrict__ cnt,
            double* __restrict__ loss_acc, int nvec, int* __restrict__ bad) {
   constexpr int GPW = 32 / LPR;  // sample groups per warp
@@ -35,7 +35,8 @@ bpr_kernel(const float* __restrict__ O, const float* __restrict__ E, int64_t n_u
     const bool valid = b < B;
     int64_t u = 0, p = 0, n = 0;
     if (valid) {
-      u = users[b]; p = pos[b]; n = neg[b];
+      const int64_t row = perm ? perm[b] : b;      // the epoch shuffle is this indirection
+      u = samples[3 * row]; p = samples[3 * row + 1]; n = samples[3 * row + 2];
       if (u < 0 || u >= n_users || p < 0 || p >= n_items || n < 0 || n >= n_items) {
         if (l == 0) atomicOr(bad, 1);
         u = 0; p = 0; n = 0;
@@ -180,27 +181,27 @@ int launch_adam(float* p, const float* g, const float* cnt, float reg_scale, flo
 }
 
 template <int LPR, int VPL>
-static int launch_bpr_t(const float* O, const float* E, int64_t U, int64_t I, const int64_t* users, const int64_t* pos,
-                        const int64_t* neg, int64_t B, float gs, float* gO, float* cnt, double* loss, int nvec,
+static int launch_bpr_t(const float* O, const float* E, int64_t U, int64_t I, const int64_t* samples,
+                        const int64_t* perm, int64_t B, float gs, float* gO, float* cnt, double* loss, int nvec,
                         int* bad, cudaStream_t s) {
   const int64_t groups_per_block = 256 / LPR;
   const int64_t want = (B + groups_per_block - 1) / groups_per_block;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 32));
-  bpr_kernel<LPR, VPL><<<grid, 256, 0, s>>>(O, E, U, I, users, pos, neg, B, gs, gO, cnt, loss, nvec, bad);
+  bpr_kernel<LPR, VPL><<<grid, 256, 0, s>>>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad);
   RECAD_LAUNCH_CHECK();
   return RECAD_OK;
 }
 
-int launch_bpr(const float* O, const float* E, int64_t U, int64_t I, const int64_t* users, const int64_t* pos,
-               const int64_t* neg, int64_t B, float gs, float* gO, float* cnt, double* loss, int D, int* bad,
+int launch_bpr(const float* O, const float* E, int64_t U, int64_t I, const int64_t* samples, const int64_t* perm,
+               int64_t B, float gs, float* gO, float* cnt, double* loss, int D, int* bad,
                cudaStream_t s) {
   const int nvec = D / 4;
-  if (nvec <= 8) return launch_bpr_t<8, 1>(O, E, U, I, users, pos, neg, B, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 16) return launch_bpr_t<16, 1>(O, E, U, I, users, pos, neg, B, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 32) return launch_bpr_t<32, 1>(O, E, U, I, users, pos, neg, B, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 64) return launch_bpr_t<32, 2>(O, E, U, I, users, pos, neg, B, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 128) return launch_bpr_t<32, 4>(O, E, U, I, users, pos, neg, B, gs, gO, cnt, loss, nvec, bad, s);
-  return launch_bpr_t<32, 8>(O, E, U, I, users, pos, neg, B, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 8) return launch_bpr_t<8, 1>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 16) return launch_bpr_t<16, 1>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 32) return launch_bpr_t<32, 1>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 64) return launch_bpr_t<32, 2>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 128) return launch_bpr_t<32, 4>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
+  return launch_bpr_t<32, 8>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
 }
 
 __global__ void dot_scores_kernel(const float* __restrict__ O, int64_t n_users, const int64_t* __restrict__ users,
@@ -236,13 +237,13 @@ using namespace recad;
 
 extern "C" {
 
-int recad_bpr_fwd_bwd(const float* O, const float* E, int64_t n_users, int64_t n_items, const int64_t* users,
-                      const int64_t* pos, const int64_t* neg, int64_t B, float grad_scale, float* gO, float* cnt,
+int recad_bpr_fwd_bwd(const float* O, const float* E, int64_t n_users, int64_t n_items, const int64_t* samples,
+                      const int64_t* perm, int64_t B, float grad_scale, float* gO, float* cnt,
                       double* loss_acc, int32_t D, void* stream) {
-  RECAD_REQUIRE(O && E && users && pos && neg && gO && cnt && loss_acc, RECAD_ERR_ARG, "bpr: null pointer");
+  RECAD_REQUIRE(O && E && samples && gO && cnt && loss_acc, RECAD_ERR_ARG, "bpr: null pointer");
   RECAD_REQUIRE(B > 0 && D >= 4 && D % 4 == 0 && D <= 1024, RECAD_ERR_UNSUPPORTED, "bpr: bad B or D");
   // loss_acc[3] doubles as the out-of-range flag (stays 0.0 when all ids are valid)
-  return launch_bpr(O, E, n_users, n_items, users, pos, neg, B, grad_scale, gO, cnt, loss_acc, D,
+  return launch_bpr(O, E, n_users, n_items, samples, perm, B, grad_scale, gO, cnt, loss_acc, D,
                     reinterpret_cast<int*>(loss_acc + 3), as_stream(stream));
 }
 
@@ -275,14 +276,13 @@ int recad_lightgcn_propagate(const recad_lightgcn* st, void* stream) {
   return RECAD_OK;
 }
 
-int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* users, const int64_t* pos, const int64_t* neg,
+int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* samples, const int64_t* perm,
                                int64_t n_samples, int64_t batch, int64_t step0, void* stream) {
   int rc = check_lightgcn(st);
   if (rc) return rc;
   RECAD_REQUIRE(st->m && st->v && st->g && st->cnt && st->loss_acc && st->X0 && st->X1, RECAD_ERR_ARG,
                 "lightgcn_train_epoch: null training buffer");
-  RECAD_REQUIRE(users && pos && neg && n_samples > 0 && batch > 0 && step0 >= 0, RECAD_ERR_ARG,
-                "lightgcn_train_epoch: bad samples");
+  RECAD_REQUIRE(samples && n_samples > 0 && batch > 0 && step0 >= 0, RECAD_ERR_ARG, "lightgcn_train_epoch: bad samples");
   cudaStream_t s = as_stream(stream);
   const int64_t N = st->n_users + st->n_items;
   const int L = st->n_layers, D = st->D;
@@ -295,7 +295,7 @@ int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* users, c
     if (rc) return rc;
     RECAD_CUDA_CHECK(cudaMemsetAsync(st->g, 0, N * D * sizeof(float), s));
     RECAD_CUDA_CHECK(cudaMemsetAsync(st->cnt, 0, N * sizeof(float), s));
-    rc = launch_bpr(st->O, st->E, st->n_users, st->n_items, users + b0, pos + b0, neg + b0, B,
+    rc = launch_bpr(st->O, st->E, st->n_users, st->n_items, perm ? samples : samples + 3 * b0, perm ? perm + b0 : nullptr, B,
                     1.0f / (float)(L + 1), st->g, st->cnt, st->loss_acc, D, reinterpret_cast<int*>(st->loss_acc + 3), s);
     if (rc) return rc;
     // Horner: t <- g + A t, L times, so that t = (I + A + ... + A^L) g

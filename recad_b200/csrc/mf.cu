@@ -14,8 +14,8 @@ template <int LPR, int VPL, bool kTrain>
 __global__ void __launch_bounds__(256)
 mf_kernel(const float* __restrict__ Ue, const float* __restrict__ Ub, const float* __restrict__ Ie,
           const float* __restrict__ Ib, float mean, int64_t n_users, int64_t n_items,
-          const int64_t* __restrict__ users, const int64_t* __restrict__ items, const int64_t* __restrict__ labels,
-          int64_t B, int nvec, float* __restrict__ pred, float* __restrict__ gUe, float* __restrict__ gUb,
+          const int64_t* __restrict__ users, const int64_t* __restrict__ items, const int64_t* __restrict__ samples,
+          const int64_t* __restrict__ perm, int64_t B, int nvec, float* __restrict__ pred, float* __restrict__ gUe, float* __restrict__ gUb,
           float* __restrict__ gIe, float* __restrict__ gIb, double* __restrict__ loss_acc, int* __restrict__ bad) {
   const int lane = threadIdx.x & 31, l = lane % LPR;
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
@@ -28,9 +28,14 @@ mf_kernel(const float* __restrict__ Ue, const float* __restrict__ Ub, const floa
   for (int64_t it = 0; it < iters; ++it) {
     const int64_t b = it * n_groups + group;
     const bool valid = b < B;
-    int64_t u = 0, i = 0;
+    int64_t u = 0, i = 0, label = 0;
     if (valid) {
-      u = users[b]; i = items[b];
+      if (kTrain) {   // (user, item, label) rows, visited through the epoch permutation
+        const int64_t row = perm ? perm[b] : b;
+        u = samples[3 * row]; i = samples[3 * row + 1]; label = samples[3 * row + 2];
+      } else {
+        u = users[b]; i = items[b];
+      }
       if (u < 0 || u >= n_users || i < 0 || i >= n_items) {
         if (l == 0 && bad) atomicOr(bad, 1);
         u = 0; i = 0;
@@ -57,7 +62,7 @@ mf_kernel(const float* __restrict__ Ue, const float* __restrict__ Ub, const floa
       if (l == 0) pred[b] = x;
       continue;
     }
-    const float y = (float)labels[b];
+    const float y = (float)label;
     // BCEWithLogits: (1 - y) x - log_sigmoid(x),  log_sigmoid(x) = min(x, 0) - log1p(exp(-|x|))
     if (l == 0) loss_sum += (1.f - y) * x - (fminf(x, 0.f) - log1pf(expf(-fabsf(x))));
     const float g = (1.f / (1.f + expf(-x)) - y) * inv_B;
@@ -88,8 +93,8 @@ mf_kernel(const float* __restrict__ Ue, const float* __restrict__ Ub, const floa
 }
 
 template <bool kTrain>
-static int launch_mf(const recad_mf* st, const int64_t* users, const int64_t* items, const int64_t* labels, int64_t B,
-                     float* pred, cudaStream_t s) {
+static int launch_mf(const recad_mf* st, const int64_t* users, const int64_t* items, const int64_t* samples,
+                     const int64_t* perm, int64_t B, float* pred, cudaStream_t s) {
   const int nvec = st->D / 4;
   int* bad = st->loss_acc ? reinterpret_cast<int*>(st->loss_acc + 3) : nullptr;
 #define RECAD_MF_LAUNCH(LPR, VPL)                                                                              \
@@ -97,7 +102,7 @@ static int launch_mf(const recad_mf* st, const int64_t* users, const int64_t* it
     const int64_t gpb = 256 / LPR;                                                                             \
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((B + gpb - 1) / gpb, (int64_t)sm_count() * 32)); \
     mf_kernel<LPR, VPL, kTrain><<<grid, 256, 0, s>>>(st->Ue, st->Ub, st->Ie, st->Ib, st->mean, st->n_users,     \
-                                                     st->n_items, users, items, labels, B, nvec, pred, st->gUe, \
+                                                     st->n_items, users, items, samples, perm, B, nvec, pred, st->gUe, \
                                                      st->gUb, st->gIe, st->gIb, st->loss_acc, bad);            \
   }
   if (nvec <= 8) RECAD_MF_LAUNCH(8, 1)
@@ -133,15 +138,14 @@ int recad_mf_forward(const recad_mf* st, const int64_t* users, const int64_t* it
   int rc = check_mf(st, false);
   if (rc) return rc;
   RECAD_REQUIRE(users && items && pred && B > 0, RECAD_ERR_ARG, "mf_forward: bad argument");
-  return launch_mf<false>(st, users, items, nullptr, B, pred, as_stream(stream));
+  return launch_mf<false>(st, users, items, nullptr, nullptr, B, pred, as_stream(stream));
 }
 
-int recad_mf_train_epoch(const recad_mf* st, const int64_t* users, const int64_t* items, const int64_t* labels,
-                         int64_t n_samples, int64_t batch, int64_t step0, void* stream) {
+int recad_mf_train_epoch(const recad_mf* st, const int64_t* samples, const int64_t* perm, int64_t n_samples,
+                         int64_t batch, int64_t step0, void* stream) {
   int rc = check_mf(st, true);
   if (rc) return rc;
-  RECAD_REQUIRE(users && items && labels && n_samples > 0 && batch > 0 && step0 >= 0, RECAD_ERR_ARG,
-                "mf_train_epoch: bad samples");
+  RECAD_REQUIRE(samples && n_samples > 0 && batch > 0 && step0 >= 0, RECAD_ERR_ARG, "mf_train_epoch: bad samples");
   cudaStream_t s = as_stream(stream);
   const int64_t U = st->n_users, I = st->n_items, D = st->D;
   // order Ue, Ie, Ub, Ib: both embedding tables stay 16-byte aligned when laid out back to back
@@ -167,7 +171,7 @@ int recad_mf_train_epoch(const recad_mf* st, const int64_t* users, const int64_t
     } else {
       for (int k = 0; k < 4; ++k) RECAD_CUDA_CHECK(cudaMemsetAsync(G[k], 0, sz[k] * sizeof(float), s));
     }
-    rc = launch_mf<true>(st, users + b0, items + b0, labels + b0, B, nullptr, s);
+    rc = launch_mf<true>(st, nullptr, nullptr, perm ? samples : samples + 3 * b0, perm ? perm + b0 : nullptr, B, nullptr, s);
     if (rc) return rc;
     const AdamScalars a = adam_scalars(st->lr, st->beta1, st->beta2, st->eps, step);
     // fold: epoch_sum += batch_sum / B   (half_lambda = 0: no regulariser in MF)

@@ -59,7 +59,7 @@ struct MT {
 extern "C" {
 
 int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items, int64_t train_size,
-                           const int64_t* allpos_rowptr, const int64_t* allpos_col, int64_t* out, int64_t* n_out) {
+                           const int64_t* allpos_rowptr, const int32_t* allpos_col, int64_t* out, int64_t* n_out) {
   if (!key || !pos || !allpos_rowptr || !out || !n_out || n_users <= 0 || n_items <= 0 || train_size < 0 ||
       n_users > 0xffffffffLL || n_items > 0xffffffffLL) {
     recad::set_error("mt19937_pairwise: bad argument");
@@ -70,7 +70,17 @@ int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t
   int64_t* users = new int64_t[train_size > 0 ? train_size : 1];
   for (int64_t k = 0; k < train_size; ++k) users[k] = (int64_t)mt.masked((uint64_t)n_users - 1);
   int64_t w = 0;
+  // The users are known up front, so the two dependent random accesses per sample (row pointer,
+  // then the row's items) are software-prefetched: the loop is otherwise DRAM-latency bound.
+  constexpr int64_t kAheadPtr = 24, kAheadRow = 12;
   for (int64_t k = 0; k < train_size; ++k) {
+    if (k + kAheadPtr < train_size) __builtin_prefetch(allpos_rowptr + users[k + kAheadPtr]);
+    if (k + kAheadRow < train_size) {
+      const int64_t u1 = users[k + kAheadRow];
+      const int64_t a = allpos_rowptr[u1], b = allpos_rowptr[u1 + 1];
+      for (int64_t q = a; q < b && q < a + 192; q += 16) __builtin_prefetch(allpos_col + q);
+      if (b > a + 192) __builtin_prefetch(allpos_col + (a + b) / 2);
+    }
     const int64_t u = users[k];
     const int64_t lo = allpos_rowptr[u], hi = allpos_rowptr[u + 1];
     if (hi == lo) continue;  // implicit.py:63-64
@@ -82,7 +92,7 @@ int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t
     }
     const int64_t p = allpos_col[lo + (int64_t)mt.masked((uint64_t)(hi - lo) - 1)];
     int64_t neg;
-    do { neg = (int64_t)mt.masked((uint64_t)n_items - 1); } while (std::binary_search(allpos_col + lo, allpos_col + hi, neg));
+    do { neg = (int64_t)mt.masked((uint64_t)n_items - 1); } while (std::binary_search(allpos_col + lo, allpos_col + hi, (int32_t)neg));
     out[3 * w] = u; out[3 * w + 1] = p; out[3 * w + 2] = neg;
     ++w;
   }
@@ -144,8 +154,23 @@ int recad_mt19937_permutation(uint32_t* key, int32_t* pos, int64_t n, int64_t* p
   }
   MT mt{key, *pos};
   for (int64_t i = 0; i < n; ++i) perm[i] = i;
+  // j = random_interval(i) depends on i only, not on the data: draw kAhead swaps ahead (same stream
+  // order) and prefetch perm[j], which is otherwise one DRAM miss per element
+  constexpr int kAhead = 32;
+  int64_t ring[kAhead];
+  int64_t drawn = n - 1;  // next i whose j has not been drawn yet
+  for (int q = 0; q < kAhead && drawn > 0; ++q, --drawn) {
+    ring[(n - 1 - drawn) % kAhead] = (int64_t)mt.masked((uint64_t)drawn);
+    __builtin_prefetch(perm + ring[(n - 1 - drawn) % kAhead], 1);
+  }
   for (int64_t i = n - 1; i > 0; --i) {
-    const int64_t j = (int64_t)mt.masked((uint64_t)i);
+    const int slot = (int)((n - 1 - i) % kAhead);
+    const int64_t j = ring[slot];
+    if (drawn > 0) {
+      ring[slot] = (int64_t)mt.masked((uint64_t)drawn);
+      __builtin_prefetch(perm + ring[slot], 1);
+      --drawn;
+    }
     std::swap(perm[i], perm[j]);
   }
   *pos = mt.pos;

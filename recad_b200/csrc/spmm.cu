@@ -11,6 +11,10 @@
 // Inside a warp: the segment's (col, val) pairs are staged 32 at a time with one coalesced load
 // per lane and broadcast with shuffles; a row of X is covered by D/4 lanes with 128-bit loads, so
 // a warp load instruction fetches 32/(D/4) neighbour rows at once and UNR of them are in flight.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace recad {
@@ -45,19 +49,22 @@ __device__ __forceinline__ void spmm_epilogue(int64_t row, int slot, int l, floa
   }
 }
 
-template <int D, int UNR>
-__global__ void __launch_bounds__(kSpmmWarps * 32)
+template <int D, int UNR, int MINB, bool kStreamX>
+__global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
 spmm_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                 int64_t n_seg, int32_t seg_len, const int32_t* __restrict__ seg_row,
                 const int64_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_slot,
                 const float* __restrict__ X, float* Y, const float* C, float* Z, float alpha, float* partials) {
   constexpr int LPR = RowLanes<D>::LPR, NPL = RowLanes<D>::NPL;
   static_assert(32 % (NPL * UNR) == 0, "unroll must divide the staged chunk");
-  const int64_t seg = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5);
-  if (seg >= n_seg) return;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR;  // which neighbour of the NPL fetched together
   const int l = lane % LPR;    // which float4 of the row
+  // persistent launch: the grid is sized to the resident-CTA capacity of the chip and every warp
+  // strides over the segment list, so occupancy stays full until the list is exhausted (a warp
+  // per segment leaves a CTA's slots idle while its longest row finishes)
+  const int64_t n_warps = (int64_t)gridDim.x * kSpmmWarps;
+  for (int64_t seg = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5); seg < n_seg; seg += n_warps) {
   const int64_t row = seg_row[seg];
   const int64_t lo = seg_lo[seg];
   const int64_t hi = min(lo + (int64_t)seg_len, rowptr[row + 1]);
@@ -91,7 +98,7 @@ spmm_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
         const int cc = __shfl_sync(kFull, c, k & 31);
         w[u] = __shfl_sync(kFull, v, k & 31);
         if (k < cnt) {
-          x[u] = __ldg(X4 + (int64_t)cc * LPR + l);
+          x[u] = kStreamX ? ld_stream4(X4 + (int64_t)cc * LPR + l) : __ldg(X4 + (int64_t)cc * LPR + l);
         } else {
           x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           w[u] = 0.f;
@@ -114,6 +121,7 @@ spmm_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
     acc.w += __shfl_xor_sync(kFull, acc.w, o);
   }
   if (sub == 0) spmm_epilogue<D>(row, slot, l, acc, Y, C, Z, alpha, partials);
+  }
 }
 
 // rows with more than one segment: sum their partial slots in slot order, then the same epilogue
@@ -222,14 +230,46 @@ spmm_generic_fixup_kernel(int64_t n_mrow, const int32_t* __restrict__ mrow, cons
   }
 }
 
+// tuning knob (RECAD_SPMM_VARIANT): bit0 = persistent grid, bit1 = cap registers for 6 CTAs/SM,
+// bit2 = stream X past L1.  The default is the variant measured fastest on B200 (profiles/).
+static int spmm_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RECAD_SPMM_VARIANT");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+template <int D, int UNR, int MINB, bool kStreamX>
+static int launch_spmm_v(const recad_csr* A, const float* X, float* Y, const float* C, float* Z, float alpha,
+                         bool persistent, cudaStream_t s) {
+  auto kern = spmm_seg_kernel<D, UNR, MINB, kStreamX>;
+  int64_t grid = (A->n_seg + kSpmmWarps - 1) / kSpmmWarps;
+  if (persistent) {
+    static int per_sm = 0;
+    if (!per_sm) RECAD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSpmmWarps * 32, 0));
+    grid = std::min<int64_t>(grid, (int64_t)sm_count() * std::max(per_sm, 1));
+  }
+  kern<<<(unsigned)grid, kSpmmWarps * 32, 0, s>>>(A->rowptr, A->colidx, A->vals, A->n_seg, A->seg_len, A->seg_row,
+                                                 A->seg_lo, A->seg_slot, X, Y, C, Z, alpha, A->partials);
+  RECAD_LAUNCH_CHECK();
+  return RECAD_OK;
+}
+
 template <int D, int UNR>
 static int launch_spmm(const recad_csr* A, const float* X, float* Y, const float* C, float* Z, float alpha,
                        cudaStream_t s) {
-  const unsigned grid = (unsigned)((A->n_seg + kSpmmWarps - 1) / kSpmmWarps);
-  spmm_seg_kernel<D, UNR><<<grid, kSpmmWarps * 32, 0, s>>>(A->rowptr, A->colidx, A->vals, A->n_seg, A->seg_len,
-                                                          A->seg_row, A->seg_lo, A->seg_slot, X, Y, C, Z, alpha,
-                                                          A->partials);
-  RECAD_LAUNCH_CHECK();
+  const int v = spmm_variant();
+  const bool pers = v & 1;
+  int rc;
+  switch ((v >> 1) & 3) {
+    case 0: rc = launch_spmm_v<D, UNR, 1, false>(A, X, Y, C, Z, alpha, pers, s); break;
+    case 1: rc = launch_spmm_v<D, UNR, 6, false>(A, X, Y, C, Z, alpha, pers, s); break;
+    case 2: rc = launch_spmm_v<D, UNR, 1, true>(A, X, Y, C, Z, alpha, pers, s); break;
+    default: rc = launch_spmm_v<D, UNR, 6, true>(A, X, Y, C, Z, alpha, pers, s); break;
+  }
+  if (rc) return rc;
   if (A->n_mrow > 0) {
     const unsigned g2 = (unsigned)((A->n_mrow + kSpmmWarps - 1) / kSpmmWarps);
     spmm_fixup_kernel<D><<<g2, kSpmmWarps * 32, 0, s>>>(A->n_mrow, A->mrow, A->mrow_lo, A->partials, Y, C, Z, alpha);
@@ -257,7 +297,7 @@ extern "C" int recad_spmm(const recad_csr* A, const float* X, float* Y, const fl
                 RECAD_ERR_ARG, "spmm: buffers must be 16-byte aligned");
   switch (D) {
     case 32: return launch_spmm<32, 2>(A, X, Y, C, Z, alpha, s);
-    case 64: return launch_spmm<64, 4>(A, X, Y, C, Z, alpha, s);
+    case 64: return (spmm_variant() & 8) ? launch_spmm<64, 8>(A, X, Y, C, Z, alpha, s) : launch_spmm<64, 4>(A, X, Y, C, Z, alpha, s);
     case 128: return launch_spmm<128, 8>(A, X, Y, C, Z, alpha, s);
     default: break;
   }

@@ -83,6 +83,78 @@ def _sorted_distinct_csr(users, items, n_rows, n_cols):
     return indptr, i
 
 
+class _EpochPipe:
+    """Host side of an epoch: draw (samples, perm) with the exact MT19937 replay into PINNED buffers and
+    ship them to the device with one asynchronous copy each.
+
+    Speculative prefetch: the sampler is a sequential state machine on numpy's global stream (seconds for
+    50 M samples), so while the GPU trains epoch e a background thread draws epoch e+1 from a COPY of
+    the state epoch e ended with.  At the next call the prefetch is used only if np.random's state still
+    equals that starting state (nobody else consumed the stream, the case inside normal_train's epoch
+    loop, normal.py:95-109); then the global state is advanced to where the prefetch ended.  Otherwise it is
+    discarded and the epoch is drawn synchronously -- the stream seen by every consumer is identical to
+    the reference's in both cases."""
+
+    def __init__(self, data):
+        import threading
+        self.data = data
+        self.threading = threading
+        self.bufs = [None, None]
+        self.turn = 0
+        self.pending = None      # (thread, start_key, start_pos, result dict)
+        self.prefetch = bool(data.config.get("prefetch", data.traindataSize >= (1 << 21)))
+
+    def _buffers(self, slot, cuda):
+        n = self.data.traindataSize * (1 if self.data.config["sample"] == "pairwise" else 1 + self.data.config["negative_ratio"])
+        if self.bufs[slot] is None or self.bufs[slot][0].shape[0] < n:
+            s, p = torch.empty((max(n, 1), 3), dtype=torch.int64), torch.empty(max(n, 1), dtype=torch.int64)
+            if cuda:
+                s, p = s.pin_memory(), p.pin_memory()
+            self.bufs[slot] = (s, p)
+        return self.bufs[slot]
+
+    def _draw(self, key, pos, slot, cuda):
+        s, p = self._buffers(slot, cuda)
+        S, perm = self.data._draw_epoch(key, pos, (s.numpy(), p.numpy()))
+        return s[:len(S)], p[:len(perm)]
+
+    def next(self, device):
+        cuda = device.type == "cuda"
+        st = np.random.get_state()
+        if st[0] != "MT19937":
+            raise ops.RecadError("np.random global state is not MT19937")
+        got = None
+        if self.pending is not None:
+            thread, k0, p0, res = self.pending
+            thread.join()
+            self.pending = None
+            if p0 == int(st[2]) and np.array_equal(k0, st[1]) and "out" in res:
+                got = res["out"]
+                key, pos = res["key"], res["pos"]
+        if got is None:
+            key, pos = np.ascontiguousarray(st[1], dtype=np.uint32).copy(), [int(st[2])]
+            got = self._draw(key, pos, self.turn, cuda)
+        np.random.set_state((st[0], key, int(pos[0]), st[3], st[4]))
+        self.turn ^= 1
+        if cuda:
+            s_dev = got[0].to(device, non_blocking=True)
+            p_dev = got[1].to(device, non_blocking=True)
+        else:                                   # host "device" (CPU-only tests): detach from the reusable buffers
+            s_dev, p_dev = got[0].clone(), got[1].clone()
+        if self.prefetch:
+            k2, p2, res = key.copy(), [int(pos[0])], {}
+            slot = self.turn
+
+            def work():
+                kk, pp = k2.copy(), [p2[0]]
+                res["out"] = self._draw(kk, pp, slot, cuda)
+                res["key"], res["pos"] = kk, pp
+            t = self.threading.Thread(target=work, daemon=True)
+            t.start()
+            self.pending = (t, k2, p2[0], res)
+        return s_dev, p_dev
+
+
 class ImplicitData:
     def __init__(self, **config):
         self.config = config
@@ -162,7 +234,8 @@ class ImplicitData:
         if which not in ("reference", "train"):
             raise ValueError("graph_edges must be 'reference' or 'train'")
         self.trainUser, self.trainItem = self._flat["test" if which == "reference" else "train"]
-        self._allpos = _sorted_distinct_csr(self.trainUser, self.trainItem, self.n_users, self.n_items)
+        ptr, idx = _sorted_distinct_csr(self.trainUser, self.trainItem, self.n_users, self.n_items)
+        self._allpos = (ptr, idx.astype(np.int32))
         self._train_csr = None
         self.Graph = None
         if self.config["need_graph"]:
@@ -241,36 +314,42 @@ class ImplicitData:
 
     # ---------------------------------------------------------------- sampling (implicit.py:18-91, 416-476)
     def epoch_samples(self, device=None):
-        """One epoch of training samples, already shuffled, as three int64 tensors on the device:
-        (users, positive_items, negative_items) or (users, items, labels).  Consumes the global
-        np.random stream exactly as `generate_batch` of the reference does (sampler, then shuffle)."""
-        device = torch.device(device or self.config["device"])
+        """One epoch of training rows for the C epoch drivers: (samples, perm) on the device.
+        samples int64 [n, 3] = (user, pos, neg) or (user, item, label) in SAMPLER order; perm int64 [n] =
+        the epoch shuffle (implicit.py:18-35), applied by the kernels as an index indirection.
+        Consumes the global np.random stream exactly as `generate_batch` of the reference does (sampler,
+        then shuffle).  With config['prefetch'] the NEXT epoch is drawn on a background thread while the
+        GPU trains (see _EpochPipe)."""
         if self.mode() != "train":
             raise NotImplementedError("epoch_samples is for train mode")
+        if getattr(self, "_pipe", None) is None:
+            self._pipe = _EpochPipe(self)
+        return self._pipe.next(torch.device(device or self.config["device"]))
+
+    def _draw_epoch(self, key, pos, buf=None):
+        """Sampler + shuffle from an EXPLICIT MT19937 state (key, pos are advanced in place)."""
         if self.config["sample"] == "pairwise":
-            S = ops.mt_pairwise(self.n_users, self.n_items, self.traindataSize, *self._allpos)
+            S = ops.mt_pairwise_raw(key, pos, self.n_users, self.n_items, self.traindataSize, *self._allpos,
+                                    out=None if buf is None else buf[0])
         elif self.config["sample"] == "pointwise":
-            S = ops.mt_pointwise(*self._tr, self.n_items, self.config["negative_ratio"])
+            S = ops.mt_pointwise_raw(key, pos, *self._tr, self.n_items, self.config["negative_ratio"],
+                                     out=None if buf is None else buf[0])
         else:
             raise NotImplementedError("Not implemented yet")
-        perm = ops.mt_permutation(len(S))
-        S = np.ascontiguousarray(S[perm].T)                 # [3, n], shuffled (implicit.py:426/447)
-        host = torch.from_numpy(S)
-        if device.type == "cuda":
-            host = host.pin_memory()
-        dev = host.to(device, non_blocking=True)
-        return dev[0], dev[1], dev[2]
+        perm = ops.mt_permutation_raw(key, pos, len(S), out=None if buf is None else buf[1])
+        return S, perm
 
     def generate_batch(self, **config):
         c = self.config
         if self.mode() == "train":
-            a, b, d = self.epoch_samples()
+            samples, perm = self.epoch_samples()
+            S = samples[perm]                              # compatibility path only: materialise the shuffle
             if c["sample"] == "pairwise":
                 names, bs = ("users", "positive_items", "negative_items"), c["pairwise_batch_size"]
             else:
                 names, bs = ("users", "items", "labels"), c["pointwise_batch_size"]
-            for s in range(0, len(a), bs):               # minibatch (implicit.py:38-47)
-                yield {names[0]: a[s:s + bs], names[1]: b[s:s + bs], names[2]: d[s:s + bs]}
+            for s in range(0, len(S), bs):                 # minibatch (implicit.py:38-47)
+                yield {names[0]: S[s:s + bs, 0], names[1]: S[s:s + bs, 1], names[2]: S[s:s + bs, 2]}
         elif self.mode() in ("validate", "test"):
             test_dict = self.valid_dict if self.mode() == "validate" else self.test_dict
             users = list(test_dict.keys())
@@ -344,46 +423,67 @@ class ImplicitData:
 
 
 class ArrayImplicitData:
-    """Array-backed dataset for graphs too large for Python dicts (the synthetic
-    1M x 200k x 50M configuration): the same sampler / graph / batch code as
-    ImplicitData, fed with flat (user, item) arrays.  `train_dict` is not
-    materialised; the evaluator uses `train_csr()`."""
+    """Array-backed dataset for graphs too large for Python dicts (the synthetic 1M x 200k x 50M
+    configuration): the same sampler / epoch pipe / graph code as ImplicitData, but everything is derived
+    from the DEVICE graph -- the user rows of the symmetric CSR already are every user's sorted distinct
+    positives (allPos / the evaluation mask), so no host-side sort of the interactions is ever done.
+    `train_dict` is not materialised; the evaluator uses `train_csr()`.
+
+    train: (users, items) CUDA int64 tensors of distinct pairs, or None when `graph` is given.
+    test:  optional (users, items) host arrays of held-out pairs (ground truth for Recall/NDCG)."""
 
     def __init__(self, name, n_users, n_items, train, device, test=None, sample="pairwise", batch_size=1024,
-                 negative_ratio=4, need_graph=True, graph=None):
+                 negative_ratio=4, need_graph=True, graph=None, prefetch=None):
         self._dataset_name = name
         self.n_users, self.n_items = int(n_users), int(n_items)
-        self.config = {"device": torch.device(device), "sample": sample, "pairwise_batch_size": batch_size,
+        dev = torch.device(device)
+        self.config = {"device": dev, "sample": sample, "pairwise_batch_size": batch_size,
                        "pointwise_batch_size": batch_size, "negative_ratio": negative_ratio, "need_graph": need_graph,
                        "graph_edges": "train"}
-        tu, ti = (np.ascontiguousarray(a, dtype=np.int64) for a in train)
-        self._flat = {"train": (tu, ti), "test": test if test is not None else (np.zeros(0, np.int64), np.zeros(0, np.int64))}
-        self.traindataSize = len(tu)
-        self._allpos = _sorted_distinct_csr(tu, ti, self.n_users, self.n_items)
-        # pointwise sampler wants the dict-order lists: users ascending, items in stored order
-        order = np.argsort(tu, kind="stable")
-        keys, counts = np.unique(tu, return_counts=True)
-        self._tr = (keys, np.concatenate([[0], np.cumsum(counts)]).astype(np.int64), ti[order])
-        self._train_csr = None
-        self._mode = "train"
+        if prefetch is not None:
+            self.config["prefetch"] = prefetch
+        if graph is None:
+            tu, ti = (torch.as_tensor(a).to(dev).long() for a in train)
+            graph = ops.Graph.from_edges(tu, ti, n_users, n_items)
         self.Graph = graph
-        if need_graph and graph is None:
-            dev = self.config["device"]
-            self.Graph = ops.Graph.from_edges(torch.from_numpy(tu).to(dev), torch.from_numpy(ti).to(dev), n_users, n_items)
+        U = self.n_users
+        rowptr_u = graph.rowptr[:U + 1].contiguous()
+        n_train = int(rowptr_u[-1])
+        col_u = (graph.colidx[:n_train] - U).contiguous()                 # int32 item ids, ascending per user
+        self._train_csr_dev = (rowptr_u, col_u)
+        self._allpos = (rowptr_u.cpu().numpy(), col_u.cpu().numpy())      # host copy for the C++ sampler
+        self._train_csr = self._allpos
+        self.traindataSize = n_train
+        # pointwise sampler: dict order = users ascending, each list ascending
+        lens = np.diff(self._allpos[0])
+        keys = np.flatnonzero(lens > 0).astype(np.int64)
+        self._tr = (keys, np.concatenate([[0], np.cumsum(lens[keys])]).astype(np.int64), self._allpos[1].astype(np.int64)) \
+            if sample == "pointwise" else None
+        self._test = test
+        self._gt = {}
+        self._mode = "train"
 
     dataset_name = ImplicitData.dataset_name
     mode = ImplicitData.mode
     switch_mode = ImplicitData.switch_mode
     epoch_samples = ImplicitData.epoch_samples
-    train_csr = ImplicitData.train_csr
-    ground_truth_csr = ImplicitData.ground_truth_csr
+    _draw_epoch = ImplicitData._draw_epoch
+    generate_batch = ImplicitData.generate_batch
 
-    def generate_batch(self, **config):
-        a, b, d = self.epoch_samples()
-        names = ("users", "positive_items", "negative_items") if self.config["sample"] == "pairwise" else ("users", "items", "labels")
-        bs = self.config["pairwise_batch_size"]
-        for s in range(0, len(a), bs):
-            yield {names[0]: a[s:s + bs], names[1]: b[s:s + bs], names[2]: d[s:s + bs]}
+    def train_csr(self, device=None):
+        if device is None:
+            return self._train_csr
+        return tuple(t.to(device) for t in self._train_csr_dev)
+
+    def ground_truth_csr(self, split="test", device=None):
+        if split not in self._gt:
+            if split != "test" or self._test is None:
+                raise ValueError(f"ArrayImplicitData has no '{split}' ground truth")
+            ptr, idx = _sorted_distinct_csr(np.asarray(self._test[0], np.int64), np.asarray(self._test[1], np.int64),
+                                            self.n_users, self.n_items)
+            self._gt[split] = (ptr, idx.astype(np.int32))
+        out = self._gt[split]
+        return out if device is None else tuple(torch.from_numpy(a).to(device) for a in out)
 
     def info_describe(self):
         infos = {"n_users": self.n_users, "n_items": self.n_items, "train_interactions": self.traindataSize,

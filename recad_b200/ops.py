@@ -193,10 +193,12 @@ def spmm(graph, X, Y=None, C_=None, Z=None, alpha=1.0):
     return Y, Z
 
 
-def bpr_fwd_bwd(O, E, n_users, n_items, users, pos, neg, grad_scale, gO, cnt, loss_acc):
-    _need_cuda(O, E, users, pos, neg, gO, cnt, loss_acc)
+def bpr_fwd_bwd(O, E, n_users, n_items, samples, perm, grad_scale, gO, cnt, loss_acc):
+    """samples: int64 [n, 3] (user, pos, neg); perm: int64 [B] rows of this batch or None (= all rows in order)."""
+    _need_cuda(O, E, samples, perm, gO, cnt, loss_acc)
+    B = perm.numel() if perm is not None else samples.shape[0]
     with torch.cuda.device(O.device):
-        check(_lib.lib().recad_bpr_fwd_bwd(_ptr(O), _ptr(E), n_users, n_items, _ptr(users), _ptr(pos), _ptr(neg), users.numel(),
+        check(_lib.lib().recad_bpr_fwd_bwd(_ptr(O), _ptr(E), n_users, n_items, _ptr(samples), _ptr(perm), B,
                                            float(grad_scale), _ptr(gO), _ptr(cnt), _ptr(loss_acc), O.shape[1], _stream(O.device)),
               "recad_bpr_fwd_bwd")
 
@@ -293,47 +295,75 @@ def _np_state():
     st = np.random.get_state()
     if st[0] != "MT19937":
         raise RecadError("np.random global state is not MT19937")
-    return st, np.ascontiguousarray(st[1], dtype=np.uint32).copy(), C.c_int32(int(st[2]))
+    return st, np.ascontiguousarray(st[1], dtype=np.uint32).copy(), [int(st[2])]
 
 
 def _np_state_commit(st, key, pos):
-    np.random.set_state((st[0], key, int(pos.value), st[3], st[4]))
+    np.random.set_state((st[0], key, int(pos[0]), st[3], st[4]))
 
 
 def _np(a, dtype=np.int64):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
-def mt_pairwise(n_users, n_items, train_size, allpos_rowptr, allpos_col):
-    """== pairwise_sample (implicit.py:50-74) on the global np.random stream."""
-    st, key, pos = _np_state()
-    rp, col = _np(allpos_rowptr), _np(allpos_col)
-    out = np.empty((max(train_size, 1), 3), dtype=np.int64)
-    n_out = C.c_int64()
-    check(_lib.lib().recad_mt19937_pairwise(key.ctypes.data, C.byref(pos), n_users, n_items, train_size, rp.ctypes.data,
+# *_raw: explicit MT19937 state -- key: uint32[624] (advanced in place), pos: one-element list.
+# The ctypes calls release the GIL, so a raw sampler can run on a background thread.
+def mt_pairwise_raw(key, pos, n_users, n_items, train_size, allpos_rowptr, allpos_col, out=None):
+    rp, col = _np(allpos_rowptr), _np(allpos_col, np.int32)
+    if out is None:
+        out = np.empty((max(train_size, 1), 3), dtype=np.int64)
+    assert out.dtype == np.int64 and out.flags.c_contiguous and out.shape[0] >= train_size
+    n_out, cpos = C.c_int64(), C.c_int32(pos[0])
+    check(_lib.lib().recad_mt19937_pairwise(key.ctypes.data, C.byref(cpos), n_users, n_items, train_size, rp.ctypes.data,
                                             col.ctypes.data, out.ctypes.data, C.byref(n_out)), "recad_mt19937_pairwise")
-    _np_state_commit(st, key, pos)
+    pos[0] = cpos.value
     return out[:n_out.value]
 
 
-def mt_pointwise(user_ids, pos_rowptr, pos_items, n_items, ratio):
-    """== pointwise_sample (implicit.py:77-91) on the global np.random stream."""
-    st, key, pos = _np_state()
+def mt_pointwise_raw(key, pos, user_ids, pos_rowptr, pos_items, n_items, ratio, out=None):
     uid, rp, items = _np(user_ids), _np(pos_rowptr), _np(pos_items)
     rows = np.repeat(np.arange(len(uid), dtype=np.int64), np.diff(rp))
     srt = items[np.lexsort((items, rows))]      # each user's list sorted ascending, lists kept in place
-    out = np.empty((max(len(items) * (1 + ratio), 1), 3), dtype=np.int64)
-    check(_lib.lib().recad_mt19937_pointwise(key.ctypes.data, C.byref(pos), len(uid), uid.ctypes.data, rp.ctypes.data,
+    n = len(items) * (1 + ratio)
+    if out is None:
+        out = np.empty((max(n, 1), 3), dtype=np.int64)
+    assert out.dtype == np.int64 and out.flags.c_contiguous and out.shape[0] >= n
+    cpos = C.c_int32(pos[0])
+    check(_lib.lib().recad_mt19937_pointwise(key.ctypes.data, C.byref(cpos), len(uid), uid.ctypes.data, rp.ctypes.data,
                                              items.ctypes.data, srt.ctypes.data, n_items, ratio, out.ctypes.data),
           "recad_mt19937_pointwise")
+    pos[0] = cpos.value
+    return out[:n]
+
+
+def mt_permutation_raw(key, pos, n, out=None):
+    perm = np.empty(max(n, 1), dtype=np.int64) if out is None else out
+    assert perm.dtype == np.int64 and perm.flags.c_contiguous and perm.shape[0] >= n
+    cpos = C.c_int32(pos[0])
+    check(_lib.lib().recad_mt19937_permutation(key.ctypes.data, C.byref(cpos), n, perm.ctypes.data), "recad_mt19937_permutation")
+    pos[0] = cpos.value
+    return perm[:n]
+
+
+def mt_pairwise(n_users, n_items, train_size, allpos_rowptr, allpos_col, out=None):
+    """== pairwise_sample (implicit.py:50-74) on the global np.random stream."""
+    st, key, pos = _np_state()
+    S = mt_pairwise_raw(key, pos, n_users, n_items, train_size, allpos_rowptr, allpos_col, out)
     _np_state_commit(st, key, pos)
-    return out[:len(items) * (1 + ratio)]
+    return S
 
 
-def mt_permutation(n):
+def mt_pointwise(user_ids, pos_rowptr, pos_items, n_items, ratio, out=None):
+    """== pointwise_sample (implicit.py:77-91) on the global np.random stream."""
+    st, key, pos = _np_state()
+    S = mt_pointwise_raw(key, pos, user_ids, pos_rowptr, pos_items, n_items, ratio, out)
+    _np_state_commit(st, key, pos)
+    return S
+
+
+def mt_permutation(n, out=None):
     """== np.random.shuffle(np.arange(n)) (implicit.py:24-25)."""
     st, key, pos = _np_state()
-    perm = np.empty(max(n, 1), dtype=np.int64)
-    check(_lib.lib().recad_mt19937_permutation(key.ctypes.data, C.byref(pos), n, perm.ctypes.data), "recad_mt19937_permutation")
+    perm = mt_permutation_raw(key, pos, n, out)
     _np_state_commit(st, key, pos)
-    return perm[:n]
+    return perm

@@ -62,8 +62,9 @@ class BaseVictim(LazyMixin, torch.nn.Module):
         return self
 
     def _epoch_arrays(self, names):
-        """The epoch's shuffled samples as device tensors: the dataset's fast path if it has one, else
-        drain the reference-style batch generator (any BaseData)."""
+        """The epoch's training rows for the C epoch driver: (samples int64 [n, 3], perm int64 [n] or None)
+        on the device.  recad_b200 datasets hand over sampler-order rows + the shuffle permutation; for any
+        other BaseData the reference-style batch generator is drained (its rows are already shuffled)."""
         ds = self.dataset
         if hasattr(ds, "epoch_samples"):
             return ds.epoch_samples(self._dev)
@@ -71,7 +72,9 @@ class BaseVictim(LazyMixin, torch.nn.Module):
         for batch in ds.generate_batch():
             for c, n in zip(cols, names):
                 c.append(batch[n].to(self._dev).long())
-        return tuple(torch.cat(c) for c in cols)
+        if not cols[0]:
+            return torch.zeros((0, 3), dtype=torch.int64, device=self._dev), None
+        return torch.stack([torch.cat(c) for c in cols], 1).contiguous(), None
 
     def _read_loss(self, loss_acc, n_batches):
         """One device->host copy per epoch (the reference syncs every batch, lightgcn.py:169)."""

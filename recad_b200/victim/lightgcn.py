@@ -107,14 +107,14 @@ class LightGCN(BaseVictim):
         """One epoch (lightgcn.py:132-172): returns (mean batch loss,)."""
         self._require_instance("train_step")
         self.train()
-        users, pos, neg = self._epoch_arrays(("users", "positive_items", "negative_items"))
-        n = int(users.numel())
+        samples, perm = self._epoch_arrays(("users", "positive_items", "negative_items"))
+        n = int(samples.shape[0])
         if n == 0:
             raise ops.RecadError("LightGCN.train_step: the sampler produced no training triple")
         B = int(self.dataset.config["pairwise_batch_size"]) if hasattr(self.dataset, "config") else 1024
         with torch.cuda.device(self._dev):
             self._check(_lib.lib().recad_lightgcn_train_epoch(
-                C.byref(self._st), self._vp(users), self._vp(pos), self._vp(neg), n, B, self._steps,
+                C.byref(self._st), self._vp(samples), self._vp(perm), n, B, self._steps,
                 ops._stream(self._dev)), "recad_lightgcn_train_epoch")
         n_batches = (n + B - 1) // B
         self._steps += n_batches

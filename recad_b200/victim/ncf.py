@@ -143,13 +143,13 @@ class NCF(BaseVictim):
         """One epoch (ncf.py:133-153): returns (mean batch loss,)."""
         self._require_instance("train_step")
         self.train()
-        users, items, labels = self._epoch_arrays(("users", "items", "labels"))
-        n = int(users.numel())
+        samples, perm = self._epoch_arrays(("users", "items", "labels"))
+        n = int(samples.shape[0])
         if n == 0:
             raise ops.RecadError("NCF.train_step: the sampler produced no training row")
         B = int(self.dataset.config["pointwise_batch_size"]) if hasattr(self.dataset, "config") else 1024
         with torch.cuda.device(self._dev):
-            self._check(_lib.lib().recad_ncf_train_epoch(C.byref(self._st), self._vp(users), self._vp(items), self._vp(labels),
+            self._check(_lib.lib().recad_ncf_train_epoch(C.byref(self._st), self._vp(samples), self._vp(perm),
                                                          n, B, self._steps, ops._stream(self._dev)), "recad_ncf_train_epoch")
         n_batches = (n + B - 1) // B
         self._steps += n_batches
