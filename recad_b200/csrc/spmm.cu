@@ -236,7 +236,7 @@ static int spmm_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("RECAD_SPMM_VARIANT");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 3;
   }
   return v;
 }
