@@ -286,6 +286,21 @@ int recad_fullrank_eval(const float* user_emb, const float* item_T, int64_t ld, 
                         const int32_t* targets, int32_t T, int32_t K, int32_t* topk_idx,
                         float* topk_val, int32_t* target_rank, float* target_score, void* stream);
 
+/* The same evaluation on the tensor cores: tcgen05.mma kind::tf32 with fp32 accumulators in TMEM, operand
+ * tiles fed by TMA, every operand split x = tf32(x) + tf32(x - tf32(x)) and three MMAs per tile ("3xTF32":
+ * |score error| ~ 2^-21 |u||i|, so ranks can differ from recad_fullrank_eval only between near-tied items).
+ * item_emb is the ROW-major [n_items, D] table (no transpose needed), D <= 64, K <= 32.
+ * item_bias [dev] float[n_items] or NULL is added to every score (MF's b_i; b_u and the mean do not
+ * change a user's ranking and are added to target_score by the caller).
+ * scratch [dev] float[recad_fullrank_tc_scratch_floats(n_eval, n_items)], 256-byte aligned. */
+int64_t recad_fullrank_tc_scratch_floats(int64_t n_eval, int64_t n_items);
+int recad_fullrank_eval_tc(const float* user_emb, const float* item_emb, int64_t n_items, int32_t D,
+                           const int64_t* user_ids, int64_t n_eval, const int64_t* train_rowptr,
+                           const int32_t* train_col, const int32_t* targets, int32_t T, int32_t K,
+                           const float* item_bias, int32_t* topk_idx, float* topk_val,
+                           int32_t* target_rank, float* target_score, float* scratch,
+                           int64_t scratch_floats, void* stream);
+
 /* Same outputs as recad_fullrank_eval from a MATERIALISED score block, for victims whose
  * score is not an inner product (NCF): scores [dev] float[n_rows, n_items], row r belongs
  * to user user_ids[r].  One warp per row. */

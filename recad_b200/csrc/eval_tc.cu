@@ -1,0 +1,432 @@
+// Full-ranking evaluation on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+// (reference: recad/workflow/normal.py:57-93 / 111-160; the score tile is lightgcn.py:115-120's
+//  U_b . I^T, never materialised.)
+//
+// Scores are fp32-accurate: every operand x is split on the device into x_hi = tf32(x) and
+// x_lo = tf32(x - x_hi), and a tile is three kind::tf32 MMAs accumulated in fp32 in TMEM:
+//       S = A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T            (|error| ~ 2^-21 |a||b|, "3xTF32")
+//
+// One CTA = 128 users (one TMEM lane each) x ALL items, streamed as 128-item tiles:
+//   warp 0    : TMA producer   -- user tile once, then item tiles (hi + lo, 64 KB) into a 2-stage ring
+//   warp 1    : MMA issuer     -- one thread issues 24 tcgen05.mma (3 passes x 2 k-blocks x 4 k-steps of 8)
+//                                 per tile into one of 4 TMEM accumulators (128 lanes x 128 columns)
+//   warps 2-5 : epilogue       -- tcgen05.ld the user's row (32 columns at a time) and, in registers, apply the
+//                                 train-item mask, the target-rank counters and a threshold-filtered top-K
+//                                 insertion (shared memory is touched only when a score beats the K-th best)
+// The producer / MMA / epilogue run concurrently on mbarrier pipelines (smem full/empty, TMEM full/empty).
+// The targets' scores come from the SAME arithmetic: a first 16-column MMA over the gathered target rows.
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace recad {
+
+constexpr int kTcM = 128;        // users per CTA = TMEM lanes
+constexpr int kTcN = 128;        // items per tile = TMEM columns per accumulator
+constexpr int kTcK = 64;         // padded embedding width
+constexpr int kTcKB = kTcK / 32; // 128-byte k-blocks (32 fp32)
+constexpr int kTcStages = 2;
+constexpr int kTcAcc = 4;
+constexpr int kTcThreads = 192;
+constexpr int kTcTgtN = 16;
+constexpr int kTcMaxT = 8;
+constexpr uint32_t kKbBytes = kTcM * 128;                    // one k-block of a 128-row operand tile: 16 KB
+constexpr uint32_t kOperandBytes = kTcKB * kKbBytes;         // 32 KB (hi or lo)
+constexpr uint32_t kStageBytes = 2 * kOperandBytes;          // hi + lo: 64 KB
+constexpr uint32_t kSmemA = 2 * kOperandBytes;               // 64 KB
+constexpr uint32_t kSmemTiles = kSmemA + kTcStages * kStageBytes;   // 192 KB
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);       // start address
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
+  d |= (uint64_t)1 << 46;                             // descriptor version
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor: D = F32, A = B = TF32, both K-major, dense
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct TcMaps {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo, t_hi, t_lo;
+};
+
+// ---------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kTcThreads, 1)
+fullrank_tc_kernel(const __grid_constant__ TcMaps maps, int64_t n_items, const int64_t* __restrict__ user_ids,
+                   int64_t n_eval, const int64_t* __restrict__ train_rowptr, const int32_t* __restrict__ train_col,
+                   const int32_t* __restrict__ targets, int T, int K, const float* __restrict__ item_bias,
+                   int32_t* __restrict__ topk_idx, float* __restrict__ topk_val, int32_t* __restrict__ target_rank,
+                   float* __restrict__ target_score) {
+  extern __shared__ unsigned char smem_raw[];
+  // 128-byte-swizzled operand tiles need a 1024-byte aligned base (the launch reserves the slack)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // [A_hi | A_lo | stage0: B_hi B_lo | stage1: B_hi B_lo | top-K values | top-K ids | barriers | tmem ptr]
+  float* topv = reinterpret_cast<float*>(smem + kSmemTiles);
+  int32_t* topi = reinterpret_cast<int32_t*>(topv + (size_t)K * kTcM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(topi + (size_t)K * kTcM);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t sA = smem_u32(smem), sB = sA + kSmemA;
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t bar_a_full = bar0;
+  auto bar_b_full = [&](int s) { return bar0 + 8 * (1 + s); };
+  auto bar_b_empty = [&](int s) { return bar0 + 8 * (1 + kTcStages + s); };
+  auto bar_acc_full = [&](int a) { return bar0 + 8 * (1 + 2 * kTcStages + a); };
+  auto bar_acc_empty = [&](int a) { return bar0 + 8 * (1 + 2 * kTcStages + kTcAcc + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (n_items + kTcN - 1) / kTcN;
+  const int64_t row0 = (int64_t)blockIdx.x * kTcM;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a_full, 1);
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(bar_b_full(s), 1); mbar_init(bar_b_empty(s), 1); }
+    for (int a = 0; a < kTcAcc; ++a) { mbar_init(bar_acc_full(a), 1); mbar_init(bar_acc_empty(a), kTcM); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(bar_a_full, kSmemA);
+      for (int kb = 0; kb < kTcKB; ++kb) {
+        tma_load_2d(sA + kb * kKbBytes, &maps.a_hi, kb * 32, (int)row0, bar_a_full);
+        tma_load_2d(sA + kOperandBytes + kb * kKbBytes, &maps.a_lo, kb * 32, (int)row0, bar_a_full);
+      }
+      for (int64_t j = 0; j <= n_tiles; ++j) {      // j = 0 is the 16-row target tile, j >= 1 item tile j-1
+        const int s = (int)(j % kTcStages);
+        const uint32_t use = (uint32_t)(j / kTcStages);
+        mbar_wait(bar_b_empty(s), (use & 1) ^ 1);
+        const uint32_t dst = sB + s * kStageBytes;
+        if (j == 0) {
+          mbar_expect_tx(bar_b_full(s), 2 * kTcKB * kTcTgtN * 128);
+          for (int kb = 0; kb < kTcKB; ++kb) {
+            tma_load_2d(dst + kb * kKbBytes, &maps.t_hi, kb * 32, 0, bar_b_full(s));
+            tma_load_2d(dst + kOperandBytes + kb * kKbBytes, &maps.t_lo, kb * 32, 0, bar_b_full(s));
+          }
+        } else {
+          mbar_expect_tx(bar_b_full(s), kStageBytes);
+          const int r = (int)((j - 1) * kTcN);
+          for (int kb = 0; kb < kTcKB; ++kb) {
+            tma_load_2d(dst + kb * kKbBytes, &maps.b_hi, kb * 32, r, bar_b_full(s));
+            tma_load_2d(dst + kOperandBytes + kb * kKbBytes, &maps.b_lo, kb * 32, r, bar_b_full(s));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      mbar_wait(bar_a_full, 0);
+      for (int64_t j = 0; j <= n_tiles; ++j) {
+        const int s = (int)(j % kTcStages), a = (int)(j % kTcAcc);
+        mbar_wait(bar_b_full(s), (uint32_t)(j / kTcStages) & 1);
+        mbar_wait(bar_acc_empty(a), ((uint32_t)(j / kTcAcc) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t idesc = j == 0 ? umma_idesc(kTcM, kTcTgtN) : umma_idesc(kTcM, kTcN);
+        const uint32_t d = tmem_base + a * kTcN;
+        const uint32_t bst = sB + s * kStageBytes;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {      // hi*hi, lo*hi, hi*lo
+          const uint32_t ao = sA + (pass == 1 ? kOperandBytes : 0);
+          const uint32_t bo = bst + (pass == 2 ? kOperandBytes : 0);
+#pragma unroll
+          for (int kb = 0; kb < kTcKB; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc_mma_tf32(d, umma_desc(ao + kb * kKbBytes + k * 32), umma_desc(bo + kb * kKbBytes + k * 32), idesc, acc);
+              acc = 1;
+            }
+        }
+        tc_commit(bar_b_empty(s));      // the smem stage is free once these MMAs have read it
+        tc_commit(bar_acc_full(a));     // ... and the accumulator is complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: thread = user row
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int64_t g = row0 + r;
+    const bool active = g < n_eval;
+    const int64_t uid = active ? user_ids[g] : 0;
+    for (int k = 0; k < K; ++k) { topv[k * kTcM + r] = -INFINITY; topi[k * kTcM + r] = -1; }
+    float tau = -INFINITY;
+    int64_t cur = 0, end = 0;
+    if (active) { cur = train_rowptr[uid]; end = train_rowptr[uid + 1]; }
+    float st[kTcMaxT];
+    int tg[kTcMaxT], rk[kTcMaxT];
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    // j = 0: the targets' scores, same arithmetic as every other score
+    mbar_wait(bar_acc_full(0), 0);
+    tc_fence_after();
+    {
+      uint32_t v[16];
+      tmem_ld16(lane_addr, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int t = 0; t < kTcMaxT; ++t) {
+        st[t] = 0.f; tg[t] = -1; rk[t] = 0;
+        if (t < T) {
+          tg[t] = targets[t];
+          st[t] = __uint_as_float(v[t]) + (item_bias ? __ldg(item_bias + tg[t]) : 0.f);
+          int64_t lo = cur, hi = end;
+          while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (train_col[mid] < tg[t]) lo = mid + 1; else hi = mid; }
+          if (lo < end && train_col[lo] == tg[t]) rk[t] = -1;
+        }
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(bar_acc_empty(0));
+
+    for (int64_t j = 1; j <= n_tiles; ++j) {
+      const int a = (int)(j % kTcAcc);
+      const int64_t j0 = (j - 1) * kTcN;
+      // train-item mask of this tile for this user (sorted list, walking pointer)
+      uint32_t mask[4] = {0u, 0u, 0u, 0u};
+      while (cur < end) {
+        const int c = train_col[cur];
+        if (c >= j0 + kTcN) break;
+        if (c >= j0) mask[(c - j0) >> 5] |= 1u << ((c - j0) & 31);
+        ++cur;
+      }
+      mbar_wait(bar_acc_full(a), (uint32_t)(j / kTcAcc) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + a * kTcN + c * 32, v);
+        tmem_ld_wait();
+        const int64_t base = j0 + c * 32;
+        const int lim = (int)min((int64_t)32, n_items - base);
+        if (active && lim > 0) {
+          const uint32_t m = mask[c];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (e >= lim || ((m >> e) & 1u)) continue;
+            const int item = (int)(base + e);
+            float s = __uint_as_float(v[e]);
+            if (item_bias) s += __ldg(item_bias + item);
+#pragma unroll
+            for (int t = 0; t < kTcMaxT; ++t)
+              if (t < T && rk[t] >= 0 && item != tg[t] && (s > st[t] || (s == st[t] && item < tg[t]))) ++rk[t];
+            if (s > tau) {
+              int p = K - 1;
+              while (p > 0 && topv[(p - 1) * kTcM + r] < s) {
+                topv[p * kTcM + r] = topv[(p - 1) * kTcM + r];
+                topi[p * kTcM + r] = topi[(p - 1) * kTcM + r];
+                --p;
+              }
+              topv[p * kTcM + r] = s;
+              topi[p * kTcM + r] = item;
+              tau = topv[(K - 1) * kTcM + r];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty(a));
+    }
+    if (active) {
+      for (int k = 0; k < K; ++k) { topk_idx[g * K + k] = topi[k * kTcM + r]; topk_val[g * K + k] = topv[k * kTcM + r]; }
+      for (int t = 0; t < T; ++t) { target_rank[g * T + t] = rk[t]; target_score[g * T + t] = st[t]; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// x -> (tf32(x), tf32(x - tf32(x))), rows gathered through idx, zero padded to [n_pad, 64]
+__global__ void split_tf32_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, const int32_t* __restrict__ idx32,
+                                  int64_t n_rows, int64_t n_pad, int D, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_pad * kTcK) return;
+  const int64_t r = e / kTcK;
+  const int d = (int)(e % kTcK);
+  float x = 0.f;
+  if (r < n_rows && d < D) {
+    const int64_t sr = idx ? idx[r] : (idx32 ? (int64_t)idx32[r] : r);
+    x = src[sr * D + d];
+  }
+  uint32_t hb, lb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+  const float h = __uint_as_float(hb);
+  const float rem = x - h;                   // exact in fp32
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+  hi[e] = h;
+  lo[e] = __uint_as_float(lb);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    RECAD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    RECAD_REQUIRE(p && q == cudaDriverEntryPointSuccess, RECAD_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)kTcK, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)kTcK * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RECAD_REQUIRE(r == CUDA_SUCCESS, RECAD_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return RECAD_OK;
+}
+
+}  // namespace recad
+
+using namespace recad;
+
+extern "C" {
+
+int64_t recad_fullrank_tc_scratch_floats(int64_t n_eval, int64_t n_items) {
+  const int64_t np = (n_eval + kTcM - 1) / kTcM * kTcM, ip = (n_items + kTcN - 1) / kTcN * kTcN;
+  return 2 * kTcK * (np + ip + kTcTgtN) + 64;
+}
+
+int recad_fullrank_eval_tc(const float* user_emb, const float* item_emb, int64_t n_items, int32_t D,
+                           const int64_t* user_ids, int64_t n_eval, const int64_t* train_rowptr,
+                           const int32_t* train_col, const int32_t* targets, int32_t T, int32_t K,
+                           const float* item_bias, int32_t* topk_idx, float* topk_val, int32_t* target_rank,
+                           float* target_score, float* scratch, int64_t scratch_floats, void* stream) {
+  cudaStream_t s = as_stream(stream);
+  RECAD_REQUIRE(user_emb && item_emb && user_ids && train_rowptr && topk_idx && topk_val && scratch, RECAD_ERR_ARG,
+                "fullrank_tc: null pointer");
+  RECAD_REQUIRE(n_eval > 0 && n_items > 0 && n_items < (int64_t(1) << 31) - kTcN, RECAD_ERR_ARG, "fullrank_tc: bad sizes");
+  RECAD_REQUIRE(D >= 1 && D <= kTcK, RECAD_ERR_UNSUPPORTED, "fullrank_tc: D = %d > %d (use recad_fullrank_eval)", D, kTcK);
+  RECAD_REQUIRE(K >= 1 && K <= 32, RECAD_ERR_UNSUPPORTED, "fullrank_tc: K = %d > 32 (use recad_fullrank_eval)", K);
+  RECAD_REQUIRE(T >= 0 && T <= kTcMaxT && (T == 0 || (targets && target_rank && target_score)), RECAD_ERR_ARG,
+                "fullrank_tc: 0 <= T <= %d targets", kTcMaxT);
+  RECAD_REQUIRE(scratch_floats >= recad_fullrank_tc_scratch_floats(n_eval, n_items), RECAD_ERR_SCRATCH,
+                "fullrank_tc: scratch too small");
+  RECAD_REQUIRE(((uintptr_t)scratch & 255) == 0, RECAD_ERR_ARG, "fullrank_tc: scratch must be 256-byte aligned");
+  const int64_t np = (n_eval + kTcM - 1) / kTcM * kTcM, ip = (n_items + kTcN - 1) / kTcN * kTcN;
+  float* a_hi = scratch;
+  float* a_lo = a_hi + np * kTcK;
+  float* b_hi = a_lo + np * kTcK;
+  float* b_lo = b_hi + ip * kTcK;
+  float* t_hi = b_lo + ip * kTcK;
+  float* t_lo = t_hi + kTcTgtN * kTcK;
+  const int TB = 256;
+  split_tf32_kernel<<<(unsigned)((np * kTcK + TB - 1) / TB), TB, 0, s>>>(user_emb, user_ids, nullptr, n_eval, np, D, a_hi, a_lo);
+  RECAD_LAUNCH_CHECK();
+  split_tf32_kernel<<<(unsigned)((ip * kTcK + TB - 1) / TB), TB, 0, s>>>(item_emb, nullptr, nullptr, n_items, ip, D, b_hi, b_lo);
+  RECAD_LAUNCH_CHECK();
+  split_tf32_kernel<<<(unsigned)((kTcTgtN * kTcK + TB - 1) / TB), TB, 0, s>>>(item_emb, nullptr, targets, T, kTcTgtN, D, t_hi, t_lo);
+  RECAD_LAUNCH_CHECK();
+  TcMaps maps;
+  int rc;
+  if ((rc = make_map(&maps.a_hi, a_hi, np, kTcM))) return rc;
+  if ((rc = make_map(&maps.a_lo, a_lo, np, kTcM))) return rc;
+  if ((rc = make_map(&maps.b_hi, b_hi, ip, kTcN))) return rc;
+  if ((rc = make_map(&maps.b_lo, b_lo, ip, kTcN))) return rc;
+  if ((rc = make_map(&maps.t_hi, t_hi, kTcTgtN, kTcTgtN))) return rc;
+  if ((rc = make_map(&maps.t_lo, t_lo, kTcTgtN, kTcTgtN))) return rc;
+  const size_t smem_bytes = 1024 + kSmemTiles + (size_t)K * kTcM * 8 + 16 * 8 + 16;
+  RECAD_REQUIRE(smem_bytes <= 227 * 1024, RECAD_ERR_UNSUPPORTED, "fullrank_tc: shared memory %zu B", smem_bytes);
+  static bool attr = false;
+  if (!attr) {
+    RECAD_CUDA_CHECK(cudaFuncSetAttribute(fullrank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  fullrank_tc_kernel<<<(unsigned)(np / kTcM), kTcThreads, smem_bytes, s>>>(maps, n_items, user_ids, n_eval, train_rowptr, train_col,
+                                                                         targets, T, K, item_bias, topk_idx, topk_val,
+                                                                         target_rank, target_score);
+  RECAD_LAUNCH_CHECK();
+  return RECAD_OK;
+}
+
+}  // extern "C"

@@ -5,6 +5,7 @@ computation is a kernel of librecad_b200.so.  All functions raise RecadError on
 failure -- there is no fallback path.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -240,20 +241,44 @@ def _eval_outputs(n, T, K, dev):
             torch.empty((n, max(T, 1)), dtype=torch.int32, device=dev), torch.empty((n, max(T, 1)), dtype=torch.float32, device=dev))
 
 
-def fullrank_eval(user_emb, item_emb, user_ids, train_rowptr, train_col, targets, K, item_T=None):
-    """Fused score + mask + top-K + target rank (normal.py:57-93 without the
-    score matrix).  Returns (topk_idx, topk_val, target_rank, target_score)."""
-    _need_cuda(user_emb, item_emb, user_ids, train_rowptr, train_col)
+EVAL_PRECISION = os.environ.get("RECAD_EVAL_PRECISION", "tf32x3")   # "tf32x3" (tensor cores) | "exact" (fp32 FMA chain)
+
+
+def fullrank_eval(user_emb, item_emb, user_ids, train_rowptr, train_col, targets, K, item_T=None, item_bias=None,
+                  precision=None):
+    """Fused score + mask + top-K + target rank (normal.py:57-93 without the score matrix).
+    score(u, i) = <user_emb[u], item_emb[i]> (+ item_bias[i]).  Returns (topk_idx, topk_val, target_rank,
+    target_score).  precision "tf32x3": tcgen05 tensor-core kernel (needs D <= 64, K <= 32; fp32-accurate scores,
+    ranks may differ from "exact" between near-tied items only); "exact": CUDA-core kernel whose scores are the
+    bit-exact ascending-d FMA chain."""
+    _need_cuda(user_emb, item_emb, user_ids, train_rowptr, train_col, item_bias)
     dev = user_emb.device
     I, D = item_emb.shape
     targets_t = torch.as_tensor(list(targets), dtype=torch.int32, device=dev)
     T = int(targets_t.numel())
     if T and (int(targets_t.min()) < 0 or int(targets_t.max()) >= I):
         raise RecadError(f"target item id out of range [0, {I})")
-    if item_T is None:
-        item_T = transpose_items(item_emb)
     n = int(user_ids.numel())
     topi, topv, trank, tscore = _eval_outputs(n, T, K, dev)
+    precision = precision or EVAL_PRECISION
+    if precision not in ("tf32x3", "exact"):
+        raise RecadError(f"unknown evaluation precision {precision!r}")
+    if precision == "tf32x3" and D <= 64 and K <= 32:
+        L = _lib.lib()
+        nfl = L.recad_fullrank_tc_scratch_floats(n, I)
+        with torch.cuda.device(dev):
+            scratch = torch.empty(nfl, dtype=torch.float32, device=dev)
+            check(L.recad_fullrank_eval_tc(_ptr(user_emb.contiguous()), _ptr(item_emb.contiguous()), I, D,
+                                           _ptr(user_ids.contiguous().long()), n, _ptr(train_rowptr), _ptr(train_col),
+                                           _ptr(targets_t), T, K, _ptr(item_bias), _ptr(topi), _ptr(topv), _ptr(trank),
+                                           _ptr(tscore), _ptr(scratch), nfl, _stream(dev)), "recad_fullrank_eval_tc")
+        return topi, topv, trank[:, :T], tscore[:, :T]
+    if item_bias is not None:        # exact kernel: the bias rides along as one more embedding dimension
+        user_emb = torch.cat([user_emb, torch.ones((user_emb.shape[0], 1), device=dev)], 1)
+        item_emb = torch.cat([item_emb, item_bias.view(-1, 1)], 1)
+        D, item_T = D + 1, None
+    if item_T is None:
+        item_T = transpose_items(item_emb)
     with torch.cuda.device(dev):
         check(_lib.lib().recad_fullrank_eval(_ptr(user_emb.contiguous()), _ptr(item_T), item_T.shape[1], I, D,
                                              _ptr(user_ids.contiguous().long()), n, _ptr(train_rowptr), _ptr(train_col),

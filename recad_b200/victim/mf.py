@@ -110,13 +110,14 @@ class MF(BaseVictim):
         return out
 
     def full_rank(self, user_ids, targets, K, train_rowptr, train_col):
-        """<[U, b_u, 1], [V, 1, b_i]> ranks exactly like the MF score (the constant mean shifts nothing):
-        the biases ride along as two extra embedding dimensions of the fused full-rank kernel."""
+        """score = <U_u, V_i> + b_i (+ b_u + mean, constant per user): the item bias is added inside the
+        fused full-rank kernel, the per-user constants afterwards."""
         self._require_instance("full_rank")
-        U, I, dev = self.num_users, self.num_items, self._dev
-        ue = torch.cat([self.user_emb.weight, self.user_bias.weight, torch.ones((U, 1), device=dev)], 1).contiguous()
-        ie = torch.cat([self.item_emb.weight, torch.ones((I, 1), device=dev), self.item_bias.weight], 1).contiguous()
-        return ops.fullrank_eval(ue, ie, user_ids, train_rowptr, train_col, targets, K) + (self.mean_value,)
+        topi, topv, rank, score = ops.fullrank_eval(self.user_emb.weight, self.item_emb.weight, user_ids, train_rowptr,
+                                                    train_col, targets, K, item_bias=self.item_bias.weight.view(-1))
+        # b_u and the mean shift every score of a user equally: they never change a rank, only the reported score
+        score = score + self.user_bias.weight.view(-1)[user_ids].unsqueeze(1)
+        return topi, topv, rank, score, self.mean_value
 
     def input_describe(self):
         return {

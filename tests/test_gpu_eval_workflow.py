@@ -35,12 +35,61 @@ def test_fullrank_kernel_matches_oracle(D, K, T):
     targets[0] = train[0][0] if train[0] else targets[0]      # exercise "target is a train item" -> rank -1
     topi, topv, trank, tscore = ops.fullrank_eval(
         torch.as_tensor(ue, device=DEV), torch.as_tensor(ie, device=DEV), torch.as_tensor(users, device=DEV),
-        torch.as_tensor(ptr, device=DEV), torch.as_tensor(idx.astype(np.int32), device=DEV), targets, K)
+        torch.as_tensor(ptr, device=DEV), torch.as_tensor(idx.astype(np.int32), device=DEV), targets, K, precision="exact")
     rtopi, rtopv, rrank, rscore = oev.full_rank_batched(ue, ie, users, ptr, idx, targets, K)
     assert np.array_equal(tscore.cpu().numpy(), rscore)           # same fma sequence => same bits
     assert np.array_equal(trank.cpu().numpy(), rrank)
     assert np.array_equal(topi.cpu().numpy(), rtopi)
     assert np.array_equal(topv.cpu().numpy(), rtopv)
+
+
+@pytest.mark.parametrize("D,K,T,bias", [(64, 20, 1, False), (64, 20, 2, True), (32, 8, 3, False), (50, 32, 1, True)])
+def test_fullrank_tensor_core_kernel_matches_fp64_truth(D, K, T, bias):
+    """tcgen05 3xTF32 path: scores fp32-accurate, ranks / top-K equal to the truth except between near-ties."""
+    from recad_b200 import ops
+    rng = np.random.default_rng(D * 7 + K)
+    U, I = 333, 1000                                   # neither a multiple of 128
+    ue = rng.standard_normal((U, D)).astype(np.float32)
+    ie = rng.standard_normal((I, D)).astype(np.float32)
+    ib = rng.standard_normal(I).astype(np.float32) if bias else None
+    train = {u: sorted(rng.choice(I, size=rng.integers(0, 80), replace=False).tolist()) for u in range(U)}
+    train[7], train[8] = list(range(I)), []
+    ptr, idx = _train_csr(train, U, I)
+    users = np.concatenate([[0, 7, 8, 332], np.arange(10, 300)]).astype(np.int64)
+    targets = [int(t) for t in rng.choice(I, size=T, replace=False)]
+    targets[0] = train[0][0] if train[0] else targets[0]
+    topi, topv, trank, tscore = ops.fullrank_eval(
+        torch.as_tensor(ue, device=DEV), torch.as_tensor(ie, device=DEV), torch.as_tensor(users, device=DEV),
+        torch.as_tensor(ptr, device=DEV), torch.as_tensor(idx.astype(np.int32), device=DEV), targets, K,
+        item_bias=None if ib is None else torch.as_tensor(ib, device=DEV), precision="tf32x3")
+    S = ue[users].astype(np.float64) @ ie.astype(np.float64).T + (0 if ib is None else ib.astype(np.float64))
+    mag = np.abs(ue[users]).astype(np.float64) @ np.abs(ie).astype(np.float64).T + 1.0
+    ts = tscore.cpu().numpy().astype(np.float64)
+    for j, t in enumerate(targets):
+        assert np.all(np.abs(ts[:, j] - S[:, t]) <= 3e-6 * mag[:, t]), "target score not fp32-accurate"
+    masked = np.zeros((len(users), I), dtype=bool)
+    for r, u in enumerate(users):
+        masked[r, train[int(u)]] = True
+    rk = trank.cpu().numpy()
+    ids = np.arange(I)
+    n_bad = 0
+    for r in range(len(users)):
+        for j, t in enumerate(targets):
+            if masked[r, t]:
+                assert rk[r, j] == -1
+                continue
+            ok = ~masked[r]
+            true_rank = int(np.sum(ok & (S[r] > S[r, t])) + np.sum(ok & (S[r] == S[r, t]) & (ids < t)))
+            assert abs(rk[r, j] - true_rank) <= 2
+            n_bad += rk[r, j] != true_rank
+        sm = np.where(masked[r], -np.inf, S[r])
+        order = np.lexsort((ids, -sm))[:K]
+        order = order[~masked[r, order]]
+        got = topi[r].cpu().numpy()
+        assert np.array_equal(got[len(order):], -np.ones(K - len(order), dtype=got.dtype))
+        n_bad += int(np.sum(got[:len(order)] != order) > 2)
+        assert np.allclose(topv[r, :len(order)].cpu().numpy(), sm[order], rtol=1e-5, atol=1e-5)
+    assert n_bad <= 0.01 * len(users) * (T + 1)
 
 
 def test_fullrank_ties_follow_documented_rule():
@@ -51,10 +100,11 @@ def test_fullrank_ties_follow_documented_rule():
     ie = torch.ones((I, D), device=DEV)
     ptr = torch.tensor([0, 0, 2, 2, 2], device=DEV)
     col = torch.tensor([3, 150], dtype=torch.int32, device=DEV)      # user 1 has train items 3 and 150
-    topi, topv, trank, _ = ops.fullrank_eval(ue, ie, torch.arange(U, device=DEV), ptr, col, [100], K)
-    assert trank[:, 0].tolist() == [100, 99, 100, 100]
-    assert topi[0].tolist() == list(range(20))
-    assert topi[1].tolist() == [0, 1, 2] + list(range(4, 21))
+    for prec in ("exact", "tf32x3"):
+        topi, topv, trank, _ = ops.fullrank_eval(ue, ie, torch.arange(U, device=DEV), ptr, col, [100], K, precision=prec)
+        assert trank[:, 0].tolist() == [100, 99, 100, 100], prec
+        assert topi[0].tolist() == list(range(20)), prec
+        assert topi[1].tolist() == [0, 1, 2] + list(range(4, 21)), prec
 
 
 def test_rank_from_scores_matches_fused_kernel():
@@ -67,7 +117,7 @@ def test_rank_from_scores_matches_fused_kernel():
     ptr, idx = _train_csr(train, U, I)
     ptr_d, idx_d = torch.as_tensor(ptr, device=DEV), torch.as_tensor(idx.astype(np.int32), device=DEV)
     users = torch.arange(U, device=DEV)
-    a = ops.fullrank_eval(ue, ie, users, ptr_d, idx_d, [11, 400], K)
+    a = ops.fullrank_eval(ue, ie, users, ptr_d, idx_d, [11, 400], K, precision="exact")
     scores = torch.as_tensor(oev.fma_dot_rows(ue[0].cpu().numpy(), ie.cpu().numpy()))   # row 0 exact
     full = torch.stack([torch.as_tensor(oev.fma_dot_rows(ue[u].cpu().numpy(), ie.cpu().numpy())) for u in range(U)]).to(DEV)
     assert torch.equal(full[0].cpu(), scores)
