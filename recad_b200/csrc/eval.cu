@@ -13,6 +13,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "rank_epilogue.cuh"
 
 namespace recad {
 
@@ -29,7 +30,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-template <int DP>
+template <int DP, int TMAX>
 __global__ void __launch_bounds__(kEvalThreads)
 fullrank_kernel(const float* __restrict__ user_emb, const float* __restrict__ item_T, int64_t ld, int64_t n_items,
                 int D, const int64_t* __restrict__ user_ids, int64_t n_eval, const int64_t* __restrict__ train_rowptr,
@@ -56,20 +57,15 @@ fullrank_kernel(const float* __restrict__ user_emb, const float* __restrict__ it
   if (active) { cur = train_rowptr[uid]; end = train_rowptr[uid + 1]; }
 
   // target scores with the SAME fma sequence as the tiles; rank = -1 if the target is a train item
-  float st[kMaxT];
-  int tg[kMaxT], rk[kMaxT];
+  RankState<TMAX> rs;
+  rank_state_init(rs, T, targets, train_col, cur, end);
 #pragma unroll
-  for (int t = 0; t < kMaxT; ++t) {
-    st[t] = 0.f; tg[t] = -1; rk[t] = 0;
+  for (int t = 0; t < TMAX; ++t) {
     if (t < T) {
-      tg[t] = targets[t];
       float acc = 0.f;
 #pragma unroll
-      for (int d = 0; d < DP; ++d) acc = fmaf(a[d], d < D ? item_T[(int64_t)d * ld + tg[t]] : 0.f, acc);
-      st[t] = acc;
-      int64_t lo = cur, hi = end;  // binary search the train list
-      while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (train_col[mid] < tg[t]) lo = mid + 1; else hi = mid; }
-      if (lo < end && train_col[lo] == tg[t]) rk[t] = -1;
+      for (int d = 0; d < DP; ++d) acc = fmaf(a[d], d < D ? item_T[(int64_t)d * ld + rs.tg[t]] : 0.f, acc);
+      rank_state_set_score(rs, t, acc);
     }
   }
 
@@ -121,28 +117,17 @@ fullrank_kernel(const float* __restrict__ user_emb, const float* __restrict__ it
           acc[4 * q + 3] = fmaf(a[d], b.w, acc[4 * q + 3]);
         }
       }
-      if (active) {
+      {
+        const int64_t base = j0 + jb;
+        const int lim = (int)min((int64_t)kJB, n_items - base);
+        if (lim > 0) {
+          uint32_t drop = (uint32_t)((mask >> jb) & 0xffffull) | (lim < kJB ? (0xffffu << lim) & 0xffffu : 0u) |
+                          (active ? 0u : 0xffffu);
+          if (drop) {
 #pragma unroll
-        for (int j = 0; j < kJB; ++j) {
-          const int64_t item = j0 + jb + j;
-          if (item >= n_items) continue;
-          if ((mask >> (jb + j)) & 1ull) continue;
-          const float s = acc[j];
-#pragma unroll
-          for (int q = 0; q < kMaxT; ++q)
-            if (q < T && rk[q] >= 0 && (s > st[q] || (s == st[q] && item < tg[q]))) ++rk[q];
-          if (s > tau) {
-            // insert after every entry >= s (items arrive in ascending id => ties keep id order)
-            int p = K - 1;
-            while (p > 0 && topv[(p - 1) * kEvalThreads + tid] < s) {
-              topv[p * kEvalThreads + tid] = topv[(p - 1) * kEvalThreads + tid];
-              topi[p * kEvalThreads + tid] = topi[(p - 1) * kEvalThreads + tid];
-              --p;
-            }
-            topv[p * kEvalThreads + tid] = s;
-            topi[p * kEvalThreads + tid] = (int32_t)item;
-            tau = topv[(K - 1) * kEvalThreads + tid];
+            for (int j = 0; j < kJB; ++j) acc[j] = ((drop >> j) & 1u) ? -INFINITY : acc[j];
           }
+          rank_topk_chunk<kJB, TMAX>(acc, base, T, rs, tau, topv, topi, K, kEvalThreads, tid);
         }
       }
     }
@@ -153,10 +138,12 @@ fullrank_kernel(const float* __restrict__ user_emb, const float* __restrict__ it
       topk_idx[g * K + k] = topi[k * kEvalThreads + tid];
       topk_val[g * K + k] = topv[k * kEvalThreads + tid];
     }
-    for (int t = 0; t < T; ++t) {
-      target_rank[g * T + t] = rk[t];
-      target_score[g * T + t] = st[t];
-    }
+#pragma unroll
+    for (int t = 0; t < TMAX; ++t)
+      if (t < T) {
+        target_rank[g * T + t] = ((rs.in_train >> t) & 1u) ? -1 : rs.rk[t];
+        target_score[g * T + t] = rs.st[t];
+      }
   }
 }
 
@@ -294,20 +281,35 @@ rank_from_scores_kernel(const float* __restrict__ scores, int64_t n_rows, int64_
   }
 }
 
-template <int DP>
-static int launch_fullrank(const float* user_emb, const float* item_T, int64_t ld, int64_t n_items, int D,
+template <int DP, int TMAX>
+static int launch_fullrank_t(const float* user_emb, const float* item_T, int64_t ld, int64_t n_items, int D,
                            const int64_t* user_ids, int64_t n_eval, const int64_t* train_rowptr,
                            const int32_t* train_col, const int32_t* targets, int T, int K, int32_t* topk_idx,
                            float* topk_val, int32_t* target_rank, float* target_score, cudaStream_t s) {
   const size_t smem = (size_t)2 * DP * kTI * 4 + (size_t)K * kEvalThreads * 8;
   RECAD_REQUIRE(smem <= 227 * 1024, RECAD_ERR_UNSUPPORTED, "fullrank: K = %d needs %zu B of shared memory", K, smem);
-  RECAD_CUDA_CHECK(cudaFuncSetAttribute(fullrank_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RECAD_CUDA_CHECK(cudaFuncSetAttribute(fullrank_kernel<DP, TMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)((n_eval + kEvalThreads - 1) / kEvalThreads);
-  fullrank_kernel<DP><<<grid, kEvalThreads, smem, s>>>(user_emb, item_T, ld, n_items, D, user_ids, n_eval, train_rowptr,
+  fullrank_kernel<DP, TMAX><<<grid, kEvalThreads, smem, s>>>(user_emb, item_T, ld, n_items, D, user_ids, n_eval, train_rowptr,
                                                       train_col, targets, T, K, topk_idx, topk_val, target_rank,
                                                       target_score);
   RECAD_LAUNCH_CHECK();
   return RECAD_OK;
+}
+
+template <int DP>
+static int launch_fullrank(const float* user_emb, const float* item_T, int64_t ld, int64_t n_items, int D,
+                           const int64_t* user_ids, int64_t n_eval, const int64_t* train_rowptr,
+                           const int32_t* train_col, const int32_t* targets, int T, int K, int32_t* topk_idx,
+                           float* topk_val, int32_t* target_rank, float* target_score, cudaStream_t s) {
+#define RECAD_FR_T(TMAX)                                                                                             \
+  return launch_fullrank_t<DP, TMAX>(user_emb, item_T, ld, n_items, D, user_ids, n_eval, train_rowptr, train_col, targets, \
+                                     T, K, topk_idx, topk_val, target_rank, target_score, s);
+  if (T == 0) RECAD_FR_T(0)
+  if (T == 1) RECAD_FR_T(1)
+  if (T <= 4) RECAD_FR_T(4)
+  RECAD_FR_T(8)
+#undef RECAD_FR_T
 }
 
 }  // namespace recad

@@ -19,6 +19,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "rank_epilogue.cuh"
 
 namespace recad {
 
@@ -123,6 +124,7 @@ struct TcMaps {
 };
 
 // ---------------------------------------------------------------------------------------------- the kernel
+template <int TMAX>
 __global__ void __launch_bounds__(kTcThreads, 1)
 fullrank_tc_kernel(const __grid_constant__ TcMaps maps, int64_t n_items, const int64_t* __restrict__ user_ids,
                    int64_t n_eval, const int64_t* __restrict__ train_rowptr, const int32_t* __restrict__ train_col,
@@ -234,8 +236,8 @@ fullrank_tc_kernel(const __grid_constant__ TcMaps maps, int64_t n_items, const i
     float tau = -INFINITY;
     int64_t cur = 0, end = 0;
     if (active) { cur = train_rowptr[uid]; end = train_rowptr[uid + 1]; }
-    float st[kTcMaxT];
-    int tg[kTcMaxT], rk[kTcMaxT];
+    RankState<TMAX> rs;
+    rank_state_init(rs, T, targets, train_col, cur, end);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 
     // j = 0: the targets' scores, same arithmetic as every other score
@@ -246,16 +248,8 @@ fullrank_tc_kernel(const __grid_constant__ TcMaps maps, int64_t n_items, const i
       tmem_ld16(lane_addr, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int t = 0; t < kTcMaxT; ++t) {
-        st[t] = 0.f; tg[t] = -1; rk[t] = 0;
-        if (t < T) {
-          tg[t] = targets[t];
-          st[t] = __uint_as_float(v[t]) + (item_bias ? __ldg(item_bias + tg[t]) : 0.f);
-          int64_t lo = cur, hi = end;
-          while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (train_col[mid] < tg[t]) lo = mid + 1; else hi = mid; }
-          if (lo < end && train_col[lo] == tg[t]) rk[t] = -1;
-        }
-      }
+      for (int t = 0; t < TMAX; ++t)
+        if (t < T) rank_state_set_score(rs, t, __uint_as_float(v[t]) + (item_bias ? __ldg(item_bias + rs.tg[t]) : 0.f));
     }
     tc_fence_before();
     mbar_arrive(bar_acc_empty(0));
@@ -280,37 +274,33 @@ fullrank_tc_kernel(const __grid_constant__ TcMaps maps, int64_t n_items, const i
         tmem_ld_wait();
         const int64_t base = j0 + c * 32;
         const int lim = (int)min((int64_t)32, n_items - base);
-        if (active && lim > 0) {
-          const uint32_t m = mask[c];
+        if (lim <= 0) continue;                      // warp-uniform
+        float s[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            if (e >= lim || ((m >> e) & 1u)) continue;
-            const int item = (int)(base + e);
-            float s = __uint_as_float(v[e]);
-            if (item_bias) s += __ldg(item_bias + item);
+        for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(v[e]);
+        if (item_bias) {                             // uniform addresses: one broadcast load per item
 #pragma unroll
-            for (int t = 0; t < kTcMaxT; ++t)
-              if (t < T && rk[t] >= 0 && item != tg[t] && (s > st[t] || (s == st[t] && item < tg[t]))) ++rk[t];
-            if (s > tau) {
-              int p = K - 1;
-              while (p > 0 && topv[(p - 1) * kTcM + r] < s) {
-                topv[p * kTcM + r] = topv[(p - 1) * kTcM + r];
-                topi[p * kTcM + r] = topi[(p - 1) * kTcM + r];
-                --p;
-              }
-              topv[p * kTcM + r] = s;
-              topi[p * kTcM + r] = item;
-              tau = topv[(K - 1) * kTcM + r];
-            }
-          }
+          for (int e = 0; e < 32; ++e) s[e] += (e < lim) ? __ldg(item_bias + base + e) : 0.f;
         }
+        // train items, padding columns and idle rows drop out as -inf (no per-score branch afterwards)
+        uint32_t drop = mask[c] | (lim < 32 ? ~0u << lim : 0u) | (active ? 0u : ~0u);
+        if (drop) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) s[e] = ((drop >> e) & 1u) ? -INFINITY : s[e];
+        }
+        rank_topk_chunk<32, TMAX>(s, base, T, rs, tau, topv, topi, K, kTcM, r);
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty(a));
     }
     if (active) {
       for (int k = 0; k < K; ++k) { topk_idx[g * K + k] = topi[k * kTcM + r]; topk_val[g * K + k] = topv[k * kTcM + r]; }
-      for (int t = 0; t < T; ++t) { target_rank[g * T + t] = rk[t]; target_score[g * T + t] = st[t]; }
+#pragma unroll
+      for (int t = 0; t < TMAX; ++t)
+        if (t < T) {
+          target_rank[g * T + t] = ((rs.in_train >> t) & 1u) ? -1 : rs.rk[t];
+          target_score[g * T + t] = rs.st[t];
+        }
     }
   }
   tc_fence_before();
@@ -417,14 +407,19 @@ int recad_fullrank_eval_tc(const float* user_emb, const float* item_emb, int64_t
   if ((rc = make_map(&maps.t_lo, t_lo, kTcTgtN, kTcTgtN))) return rc;
   const size_t smem_bytes = 1024 + kSmemTiles + (size_t)K * kTcM * 8 + 16 * 8 + 16;
   RECAD_REQUIRE(smem_bytes <= 227 * 1024, RECAD_ERR_UNSUPPORTED, "fullrank_tc: shared memory %zu B", smem_bytes);
-  static bool attr = false;
-  if (!attr) {
-    RECAD_CUDA_CHECK(cudaFuncSetAttribute(fullrank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+#define RECAD_TC_LAUNCH(TMAX)                                                                                          \
+  {                                                                                                                    \
+    RECAD_CUDA_CHECK(cudaFuncSetAttribute(fullrank_tc_kernel<TMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+    fullrank_tc_kernel<TMAX><<<(unsigned)(np / kTcM), kTcThreads, smem_bytes, s>>>(                                    \
+        maps, n_items, user_ids, n_eval, train_rowptr, train_col, targets, T, K, item_bias, topk_idx, topk_val,        \
+        target_rank, target_score);                                                                                    \
   }
-  fullrank_tc_kernel<<<(unsigned)(np / kTcM), kTcThreads, smem_bytes, s>>>(maps, n_items, user_ids, n_eval, train_rowptr, train_col,
-                                                                         targets, T, K, item_bias, topk_idx, topk_val,
-                                                                         target_rank, target_score);
+  if (T == 0) RECAD_TC_LAUNCH(0)
+  else if (T == 1) RECAD_TC_LAUNCH(1)
+  else if (T == 2) RECAD_TC_LAUNCH(2)
+  else if (T <= 4) RECAD_TC_LAUNCH(4)
+  else RECAD_TC_LAUNCH(8)
+#undef RECAD_TC_LAUNCH
   RECAD_LAUNCH_CHECK();
   return RECAD_OK;
 }
