@@ -267,11 +267,15 @@ fullrank_tc_kernel(const __grid_constant__ TcMaps maps, int64_t n_items, const i
       }
       mbar_wait(bar_acc_full(a), (uint32_t)(j / kTcAcc) & 1);
       tc_fence_after();
-#pragma unroll 1
+      uint32_t vn[32];
+      tmem_ld32(lane_addr + a * kTcN, vn);
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
-        tmem_ld32(lane_addr + a * kTcN + c * 32, v);
         tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = vn[e];
+        if (c < 3) tmem_ld32(lane_addr + a * kTcN + (c + 1) * 32, vn);   // next 32 columns fly while these are ranked
         const int64_t base = j0 + c * 32;
         const int lim = (int)min((int64_t)32, n_items - base);
         if (lim <= 0) continue;                      // warp-uniform

@@ -50,10 +50,15 @@ __device__ __forceinline__ void rank_topk_chunk(float (&s)[NC], int64_t base, in
       const int tg = rs.tg[t];
       if (base + NC <= tg || base > tg) {          // warp-uniform: targets are the same for every user
         const float thr = base > tg ? rs.st[t] : rs.st_lo[t];
-        int c = 0;
-#pragma unroll
-        for (int e = 0; e < NC; ++e) c += s[e] > thr ? 1 : 0;
-        rs.rk[t] += c;
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;          // four independent chains: one warp per scheduler has
+#pragma unroll                                     // nothing else to hide the add latency behind
+        for (int e = 0; e < NC; e += 4) {
+          c0 += s[e] > thr ? 1 : 0;
+          c1 += s[e + 1] > thr ? 1 : 0;
+          c2 += s[e + 2] > thr ? 1 : 0;
+          c3 += s[e + 3] > thr ? 1 : 0;
+        }
+        rs.rk[t] += (c0 + c1) + (c2 + c3);
       } else {                                     // the one chunk that holds the target itself
 #pragma unroll
         for (int e = 0; e < NC; ++e) {
@@ -64,9 +69,15 @@ __device__ __forceinline__ void rank_topk_chunk(float (&s)[NC], int64_t base, in
       }
     }
   }
-  float cmax = s[0];
+  float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];
 #pragma unroll
-  for (int e = 1; e < NC; ++e) cmax = fmaxf(cmax, s[e]);
+  for (int e = 4; e < NC; e += 4) {
+    m0 = fmaxf(m0, s[e]);
+    m1 = fmaxf(m1, s[e + 1]);
+    m2 = fmaxf(m2, s[e + 2]);
+    m3 = fmaxf(m3, s[e + 3]);
+  }
+  const float cmax = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
   if (cmax > tau) {
 #pragma unroll
     for (int e = 0; e < NC; ++e)
