@@ -52,6 +52,7 @@ fullrank_kernel(const float* __restrict__ user_emb, const float* __restrict__ it
   for (int d = 0; d < DP; ++d) a[d] = (active && d < D) ? user_emb[uid * D + d] : 0.f;
   for (int k = 0; k < K; ++k) { topv[k * kEvalThreads + tid] = -INFINITY; topi[k * kEvalThreads + tid] = -1; }
   float tau = -INFINITY;  // current K-th best
+  int min_pos = 0;        // its slot in the (unsorted) list
 
   int64_t cur = 0, end = 0;
   if (active) { cur = train_rowptr[uid]; end = train_rowptr[uid + 1]; }
@@ -127,13 +128,14 @@ fullrank_kernel(const float* __restrict__ user_emb, const float* __restrict__ it
 #pragma unroll
             for (int j = 0; j < kJB; ++j) acc[j] = ((drop >> j) & 1u) ? -INFINITY : acc[j];
           }
-          rank_topk_chunk<kJB, TMAX>(acc, base, T, rs, tau, topv, topi, K, kEvalThreads, tid);
+          rank_topk_chunk<kJB, TMAX>(acc, base, T, rs, tau, topv, topi, K, kEvalThreads, tid, min_pos);
         }
       }
     }
     __syncthreads();  // everyone is done with `buf` before it is refilled two iterations later
   }
   if (active) {
+    topk_finalize(topv, topi, K, kEvalThreads, tid);
     for (int k = 0; k < K; ++k) {
       topk_idx[g * K + k] = topi[k * kEvalThreads + tid];
       topk_val[g * K + k] = topv[k * kEvalThreads + tid];

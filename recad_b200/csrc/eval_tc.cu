@@ -17,6 +17,7 @@
 // The targets' scores come from the SAME arithmetic: a first 16-column MMA over the gathered target rows.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "rank_epilogue.cuh"
@@ -130,7 +131,7 @@ fullrank_tc_kernel(const __grid_constant__ TcMaps maps, int64_t n_items, const i
                    int64_t n_eval, const int64_t* __restrict__ train_rowptr, const int32_t* __restrict__ train_col,
                    const int32_t* __restrict__ targets, int T, int K, const float* __restrict__ item_bias,
                    int32_t* __restrict__ topk_idx, float* __restrict__ topk_val, int32_t* __restrict__ target_rank,
-                   float* __restrict__ target_score) {
+                   float* __restrict__ target_score, int dbg) {
   extern __shared__ unsigned char smem_raw[];
   // 128-byte-swizzled operand tiles need a 1024-byte aligned base (the launch reserves the slack)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -234,6 +235,7 @@ fullrank_tc_kernel(const __grid_constant__ TcMaps maps, int64_t n_items, const i
     const int64_t uid = active ? user_ids[g] : 0;
     for (int k = 0; k < K; ++k) { topv[k * kTcM + r] = -INFINITY; topi[k * kTcM + r] = -1; }
     float tau = -INFINITY;
+    int min_pos = 0;
     int64_t cur = 0, end = 0;
     if (active) { cur = train_rowptr[uid]; end = train_rowptr[uid + 1]; }
     RankState<TMAX> rs;
@@ -267,15 +269,13 @@ fullrank_tc_kernel(const __grid_constant__ TcMaps maps, int64_t n_items, const i
       }
       mbar_wait(bar_acc_full(a), (uint32_t)(j / kTcAcc) & 1);
       tc_fence_after();
-      uint32_t vn[32];
-      tmem_ld32(lane_addr + a * kTcN, vn);
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
+        if (dbg == 2) continue;                      // profiling aid: MMA/TMA pipeline only
         uint32_t v[32];
+        tmem_ld32(lane_addr + a * kTcN + c * 32, v);
         tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = vn[e];
-        if (c < 3) tmem_ld32(lane_addr + a * kTcN + (c + 1) * 32, vn);   // next 32 columns fly while these are ranked
+        if (dbg == 1) { if (v[0] == 0x7fc00001u) tau = 1.f; continue; }   // profiling aid: + TMEM loads
         const int64_t base = j0 + c * 32;
         const int lim = (int)min((int64_t)32, n_items - base);
         if (lim <= 0) continue;                      // warp-uniform
@@ -292,12 +292,13 @@ fullrank_tc_kernel(const __grid_constant__ TcMaps maps, int64_t n_items, const i
 #pragma unroll
           for (int e = 0; e < 32; ++e) s[e] = ((drop >> e) & 1u) ? -INFINITY : s[e];
         }
-        rank_topk_chunk<32, TMAX>(s, base, T, rs, tau, topv, topi, K, kTcM, r);
+        rank_topk_chunk<32, TMAX>(s, base, T, rs, tau, topv, topi, K, kTcM, r, min_pos);
       }
       tc_fence_before();
       mbar_arrive(bar_acc_empty(a));
     }
     if (active) {
+      topk_finalize(topv, topi, K, kTcM, r);
       for (int k = 0; k < K; ++k) { topk_idx[g * K + k] = topi[k * kTcM + r]; topk_val[g * K + k] = topv[k * kTcM + r]; }
 #pragma unroll
       for (int t = 0; t < TMAX; ++t)
@@ -411,12 +412,13 @@ int recad_fullrank_eval_tc(const float* user_emb, const float* item_emb, int64_t
   if ((rc = make_map(&maps.t_lo, t_lo, kTcTgtN, kTcTgtN))) return rc;
   const size_t smem_bytes = 1024 + kSmemTiles + (size_t)K * kTcM * 8 + 16 * 8 + 16;
   RECAD_REQUIRE(smem_bytes <= 227 * 1024, RECAD_ERR_UNSUPPORTED, "fullrank_tc: shared memory %zu B", smem_bytes);
+  static const int dbg = getenv("RECAD_TC_DEBUG") ? atoi(getenv("RECAD_TC_DEBUG")) : 0;
 #define RECAD_TC_LAUNCH(TMAX)                                                                                          \
   {                                                                                                                    \
     RECAD_CUDA_CHECK(cudaFuncSetAttribute(fullrank_tc_kernel<TMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
     fullrank_tc_kernel<TMAX><<<(unsigned)(np / kTcM), kTcThreads, smem_bytes, s>>>(                                    \
         maps, n_items, user_ids, n_eval, train_rowptr, train_col, targets, T, K, item_bias, topk_idx, topk_val,        \
-        target_rank, target_score);                                                                                    \
+        target_rank, target_score, dbg);                                                                               \
   }
   if (T == 0) RECAD_TC_LAUNCH(0)
   else if (T == 1) RECAD_TC_LAUNCH(1)

@@ -25,25 +25,51 @@ struct RankState {
   unsigned in_train = 0;  // bit t: the target is one of the user's train items (reported rank -1)
 };
 
-// Insert (v, item) after every entry >= v (items arrive in ascending id, so ties keep id order); returns the
-// new K-th best.  Rare (about K ln(I / K) times per user), hence out of line.
-static __device__ __noinline__ float topk_insert(float v, int32_t item, float* __restrict__ topv, int32_t* __restrict__ topi, int K,
-                                          int stride, int slot) {
-  int p = K - 1;
-  while (p > 0 && topv[(p - 1) * stride + slot] < v) {
-    topv[p * stride + slot] = topv[(p - 1) * stride + slot];
-    topi[p * stride + slot] = topi[(p - 1) * stride + slot];
-    --p;
+// The K best of a row are kept UNSORTED in shared memory; `tau` / `min_pos` (registers) are the value and slot
+// of the current worst entry (lowest score, ties: highest id).  A candidate v > tau overwrites that slot and the
+// list is rescanned for the new worst: K independent loads, no dependent shift chain.  Rare (about K ln(I / K)
+// times per user), hence out of line.  Items arrive in ascending id and only a STRICTLY better score replaces,
+// so among equal scores the lower ids survive.  topk_finalize() sorts once at the end.
+static __device__ __noinline__ float topk_replace(float v, int32_t item, float* __restrict__ topv, int32_t* __restrict__ topi,
+                                                  int K, int stride, int slot, int& min_pos) {
+  topv[min_pos * stride + slot] = v;
+  topi[min_pos * stride + slot] = item;
+  float mv = topv[slot];
+  int mi = topi[slot], mp = 0;
+#pragma unroll 4
+  for (int k = 1; k < K; ++k) {
+    const float x = topv[k * stride + slot];
+    const int xi = topi[k * stride + slot];
+    if (x < mv || (x == mv && xi > mi)) { mv = x; mi = xi; mp = k; }
   }
-  topv[p * stride + slot] = v;
-  topi[p * stride + slot] = item;
-  return topv[(K - 1) * stride + slot];
+  min_pos = mp;
+  return mv;
+}
+
+// order the row's list by (score desc, id asc); empty slots (id -1, -inf) end up last
+static __device__ __noinline__ void topk_finalize(float* __restrict__ topv, int32_t* __restrict__ topi, int K, int stride, int slot) {
+  for (int a = 0; a < K - 1; ++a) {
+    float bv = topv[a * stride + slot];
+    int bi = topi[a * stride + slot], bp = a;
+    for (int k = a + 1; k < K; ++k) {
+      const float x = topv[k * stride + slot];
+      const int xi = topi[k * stride + slot];
+      if (xi >= 0 && (bi < 0 || x > bv || (x == bv && xi < bi))) { bv = x; bi = xi; bp = k; }
+    }
+    if (bp != a) {
+      topv[bp * stride + slot] = topv[a * stride + slot];
+      topi[bp * stride + slot] = topi[a * stride + slot];
+      topv[a * stride + slot] = bv;
+      topi[a * stride + slot] = bi;
+    }
+  }
 }
 
 template <int NC, int TMAX>
 __device__ __forceinline__ void rank_topk_chunk(float (&s)[NC], int64_t base, int T, RankState<TMAX>& rs, float& tau,
                                                 float* __restrict__ topv, int32_t* __restrict__ topi, int K, int stride,
-                                                int slot) {
+                                                int slot, int& min_pos) {
+  static_assert(NC % 8 == 0, "chunks are scanned in groups of 8");
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) {
     if (t < T) {
@@ -69,19 +95,26 @@ __device__ __forceinline__ void rank_topk_chunk(float (&s)[NC], int64_t base, in
       }
     }
   }
-  float m0 = s[0], m1 = s[1], m2 = s[2], m3 = s[3];
+  // group maxima (8 consecutive items each): only a group that beats tau is looked at element by element
+  float gm[NC / 8];
 #pragma unroll
-  for (int e = 4; e < NC; e += 4) {
-    m0 = fmaxf(m0, s[e]);
-    m1 = fmaxf(m1, s[e + 1]);
-    m2 = fmaxf(m2, s[e + 2]);
-    m3 = fmaxf(m3, s[e + 3]);
+  for (int q = 0; q < NC / 8; ++q) {
+    const float a = fmaxf(fmaxf(s[8 * q], s[8 * q + 1]), fmaxf(s[8 * q + 2], s[8 * q + 3]));
+    const float b = fmaxf(fmaxf(s[8 * q + 4], s[8 * q + 5]), fmaxf(s[8 * q + 6], s[8 * q + 7]));
+    gm[q] = fmaxf(a, b);
   }
-  const float cmax = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  float cmax = gm[0];
+#pragma unroll
+  for (int q = 1; q < NC / 8; ++q) cmax = fmaxf(cmax, gm[q]);
   if (cmax > tau) {
 #pragma unroll
-    for (int e = 0; e < NC; ++e)
-      if (s[e] > tau) tau = topk_insert(s[e], (int32_t)(base + e), topv, topi, K, stride, slot);
+    for (int q = 0; q < NC / 8; ++q) {
+      if (gm[q] > tau) {
+#pragma unroll
+        for (int e = 8 * q; e < 8 * q + 8; ++e)
+          if (s[e] > tau) tau = topk_replace(s[e], (int32_t)(base + e), topv, topi, K, stride, slot, min_pos);
+      }
+    }
   }
 }
 
