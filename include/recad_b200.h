@@ -149,9 +149,15 @@ int recad_spmm(const recad_csr* A, const float* X, float* Y, const float* C, flo
  *   loss_acc [dev] double[4]: [0] += sum softplus(x), [1] += sum (|E_u|^2+|E_p|^2+|E_n|^2),
  *                             [3] is set non-zero (as an int) if a sample id is out of range */
 int recad_bpr_fwd_bwd(const float* O, const float* E, int64_t n_users, int64_t n_items,
-                      const int64_t* samples, const int64_t* perm, int64_t B,
+                      const int64_t* samples, const int64_t* perm, int64_t B, int64_t B_norm,
                       float grad_scale, float* gO, float* cnt, double* loss_acc, int32_t D,
                       void* stream);
+/* B_norm: the batch size the mean loss / gradients are normalised by.  B_norm == B on one GPU; in the
+ * user-sharded multi-GPU path each rank passes only its own users' B rows of a global batch of B_norm. */
+
+/* z = a * x + b * y over n floats (n % 4 == 0; z may alias x or y): the layer-mean / Horner accumulation of the
+ * sharded path, where the item rows of an SpMM result must be all-reduced BEFORE they are accumulated. */
+int recad_axpby(float* z, float a, const float* x, float b, const float* y, int64_t n, void* stream);
 
 /* Dense Adam over n elements (torch.optim.Adam defaults, lightgcn.py:17-19):
  *   G = g + reg_scale * cnt[i / D] * p   (cnt may be NULL)

@@ -17,14 +17,14 @@ template <int LPR, int VPL>
 __global__ void __launch_bounds__(256)
 bpr_kernel(const float* __restrict__ O, const float* __restrict__ E, int64_t n_users, int64_t n_items,
            const int64_t* __restrict__ samples, const int64_t* __restrict__ perm,
-           int64_t B, float grad_scale, float* __restrict__ gO, float* __restrict__ cnt,
+           int64_t B, int64_t B_norm, float grad_scale, float* __restrict__ gO, float* __restrict__ cnt,
            double* __restrict__ loss_acc, int nvec, int* __restrict__ bad) {
   constexpr int GPW = 32 / LPR;  // sample groups per warp
   const int lane = threadIdx.x & 31;
   const int l = lane % LPR;
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LPR;
-  const float inv_B = 1.0f / (float)B;
+  const float inv_B = 1.0f / (float)B_norm;   // the GLOBAL batch size: a rank of a sharded run sees only its users' rows
   float sp_sum = 0.f, sq_sum = 0.f;
   const float4* __restrict__ O4 = reinterpret_cast<const float4*>(O);
   const float4* __restrict__ E4 = reinterpret_cast<const float4*>(E);
@@ -182,26 +182,35 @@ int launch_adam(float* p, const float* g, const float* cnt, float reg_scale, flo
 
 template <int LPR, int VPL>
 static int launch_bpr_t(const float* O, const float* E, int64_t U, int64_t I, const int64_t* samples,
-                        const int64_t* perm, int64_t B, float gs, float* gO, float* cnt, double* loss, int nvec,
+                        const int64_t* perm, int64_t B, int64_t B_norm, float gs, float* gO, float* cnt, double* loss, int nvec,
                         int* bad, cudaStream_t s) {
   const int64_t groups_per_block = 256 / LPR;
   const int64_t want = (B + groups_per_block - 1) / groups_per_block;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 32));
-  bpr_kernel<LPR, VPL><<<grid, 256, 0, s>>>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad);
+  bpr_kernel<LPR, VPL><<<grid, 256, 0, s>>>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad);
   RECAD_LAUNCH_CHECK();
   return RECAD_OK;
 }
 
 int launch_bpr(const float* O, const float* E, int64_t U, int64_t I, const int64_t* samples, const int64_t* perm,
-               int64_t B, float gs, float* gO, float* cnt, double* loss, int D, int* bad,
+               int64_t B, int64_t B_norm, float gs, float* gO, float* cnt, double* loss, int D, int* bad,
                cudaStream_t s) {
   const int nvec = D / 4;
-  if (nvec <= 8) return launch_bpr_t<8, 1>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 16) return launch_bpr_t<16, 1>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 32) return launch_bpr_t<32, 1>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 64) return launch_bpr_t<32, 2>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 128) return launch_bpr_t<32, 4>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
-  return launch_bpr_t<32, 8>(O, E, U, I, samples, perm, B, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 8) return launch_bpr_t<8, 1>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 16) return launch_bpr_t<16, 1>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 32) return launch_bpr_t<32, 1>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 64) return launch_bpr_t<32, 2>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 128) return launch_bpr_t<32, 4>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  return launch_bpr_t<32, 8>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+}
+
+// z = a * x + b * y (float4 grid-stride); z may alias x or y
+__global__ void __launch_bounds__(256) axpby_kernel(float* z, float a, const float* x, float b, const float* y, int64_t n4) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 X = reinterpret_cast<const float4*>(x)[i], Y = reinterpret_cast<const float4*>(y)[i];
+    reinterpret_cast<float4*>(z)[i] = make_float4(a * X.x + b * Y.x, a * X.y + b * Y.y, a * X.z + b * Y.z, a * X.w + b * Y.w);
+  }
 }
 
 __global__ void dot_scores_kernel(const float* __restrict__ O, int64_t n_users, const int64_t* __restrict__ users,
@@ -238,12 +247,13 @@ using namespace recad;
 extern "C" {
 
 int recad_bpr_fwd_bwd(const float* O, const float* E, int64_t n_users, int64_t n_items, const int64_t* samples,
-                      const int64_t* perm, int64_t B, float grad_scale, float* gO, float* cnt,
+                      const int64_t* perm, int64_t B, int64_t B_norm, float grad_scale, float* gO, float* cnt,
                       double* loss_acc, int32_t D, void* stream) {
   RECAD_REQUIRE(O && E && samples && gO && cnt && loss_acc, RECAD_ERR_ARG, "bpr: null pointer");
-  RECAD_REQUIRE(B > 0 && D >= 4 && D % 4 == 0 && D <= 1024, RECAD_ERR_UNSUPPORTED, "bpr: bad B or D");
+  RECAD_REQUIRE(B >= 0 && B_norm >= B && B_norm > 0 && D >= 4 && D % 4 == 0 && D <= 1024, RECAD_ERR_UNSUPPORTED, "bpr: bad B or D");
+  if (B == 0) return RECAD_OK;
   // loss_acc[3] doubles as the out-of-range flag (stays 0.0 when all ids are valid)
-  return launch_bpr(O, E, n_users, n_items, samples, perm, B, grad_scale, gO, cnt, loss_acc, D,
+  return launch_bpr(O, E, n_users, n_items, samples, perm, B, B_norm, grad_scale, gO, cnt, loss_acc, D,
                     reinterpret_cast<int*>(loss_acc + 3), as_stream(stream));
 }
 
@@ -295,7 +305,7 @@ int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* samples,
     if (rc) return rc;
     RECAD_CUDA_CHECK(cudaMemsetAsync(st->g, 0, N * D * sizeof(float), s));
     RECAD_CUDA_CHECK(cudaMemsetAsync(st->cnt, 0, N * sizeof(float), s));
-    rc = launch_bpr(st->O, st->E, st->n_users, st->n_items, perm ? samples : samples + 3 * b0, perm ? perm + b0 : nullptr, B,
+    rc = launch_bpr(st->O, st->E, st->n_users, st->n_items, perm ? samples : samples + 3 * b0, perm ? perm + b0 : nullptr, B, B,
                     1.0f / (float)(L + 1), st->g, st->cnt, st->loss_acc, D, reinterpret_cast<int*>(st->loss_acc + 3), s);
     if (rc) return rc;
     // Horner: t <- g + A t, L times, so that t = (I + A + ... + A^L) g
@@ -311,6 +321,15 @@ int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* samples,
                      adam_scalars(st->lr, st->beta1, st->beta2, st->eps, step), fold, s);
     if (rc) return rc;
   }
+  return RECAD_OK;
+}
+
+int recad_axpby(float* z, float a, const float* x, float b, const float* y, int64_t n, void* stream) {
+  RECAD_REQUIRE(z && x && y && n > 0 && n % 4 == 0, RECAD_ERR_ARG, "axpby: n must be a positive multiple of 4");
+  const int64_t n4 = n / 4;
+  const unsigned grid = (unsigned)std::min<int64_t>((n4 + 255) / 256, (int64_t)sm_count() * 16);
+  axpby_kernel<<<grid, 256, 0, as_stream(stream)>>>(z, a, x, b, y, n4);
+  RECAD_LAUNCH_CHECK();
   return RECAD_OK;
 }
 

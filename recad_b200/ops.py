@@ -67,9 +67,11 @@ class Graph:
 
     # -- construction ------------------------------------------------------ #
     @classmethod
-    def from_edges(cls, users, items, n_users, n_items, seg_len=SEG_LEN):
+    def from_edges(cls, users, items, n_users, n_items, seg_len=SEG_LEN, degree_hook=None):
         """Symmetric-normalised bipartite adjacency (implicit.py:243-298) from an
-        edge list on the device.  users / items: int64 CUDA tensors."""
+        edge list on the device.  users / items: int64 CUDA tensors.
+        degree_hook(degree int32 [N]) may complete the degrees in place before normalisation (the sharded
+        path all-reduces the item block: a rank's rows hold only its own users' edges)."""
         _need_cuda(users, items)
         L = _lib.lib()
         dev = users.device
@@ -88,6 +90,8 @@ class Graph:
                   "recad_csr_build_structure")
             del scratch
             colidx, mult = colidx[:nnz.value].clone(), mult[:nnz.value].clone()
+            if degree_hook is not None:
+                degree_hook(degree)
             vals = cls._normalize(rowptr, colidx, mult, degree, N)
         return cls(N, N, rowptr, colidx, vals, mult, degree, seg_len)
 
@@ -194,13 +198,22 @@ def spmm(graph, X, Y=None, C_=None, Z=None, alpha=1.0):
     return Y, Z
 
 
-def bpr_fwd_bwd(O, E, n_users, n_items, samples, perm, grad_scale, gO, cnt, loss_acc):
-    """samples: int64 [n, 3] (user, pos, neg); perm: int64 [B] rows of this batch or None (= all rows in order)."""
+def axpby(z, a, x, b, y):
+    """z = a * x + b * y (z may alias x or y)."""
+    _need_cuda(z, x, y)
+    with torch.cuda.device(z.device):
+        check(_lib.lib().recad_axpby(_ptr(z), float(a), _ptr(x), float(b), _ptr(y), z.numel(), _stream(z.device)), "recad_axpby")
+    return z
+
+
+def bpr_fwd_bwd(O, E, n_users, n_items, samples, perm, grad_scale, gO, cnt, loss_acc, B_norm=None):
+    """samples: int64 [n, 3] (user, pos, neg); perm: int64 [B] rows of this batch or None (= all rows in order).
+    B_norm: batch size used for the 1/B normalisation (default: the number of rows processed)."""
     _need_cuda(O, E, samples, perm, gO, cnt, loss_acc)
     B = perm.numel() if perm is not None else samples.shape[0]
     with torch.cuda.device(O.device):
         check(_lib.lib().recad_bpr_fwd_bwd(_ptr(O), _ptr(E), n_users, n_items, _ptr(samples), _ptr(perm), B,
-                                           float(grad_scale), _ptr(gO), _ptr(cnt), _ptr(loss_acc), O.shape[1], _stream(O.device)),
+                                           int(B_norm or B), float(grad_scale), _ptr(gO), _ptr(cnt), _ptr(loss_acc), O.shape[1], _stream(O.device)),
               "recad_bpr_fwd_bwd")
 
 

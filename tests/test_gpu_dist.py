@@ -1,0 +1,66 @@
+"""Multi-GPU parity (needs >= 2 GPUs; run with `gpurun --gpus 2`): the user-sharded NCCL path reproduces the
+single-GPU epoch (loss, tables) and evaluation up to fp32 summation order."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from recad_b200 import dist as rdist, ops, synthetic
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    U, I, E, D, L, B = 3001, 1200, 60_000, 64, 3, 8192
+    u, i = synthetic.make_edges(U, I, E, seed=3)
+    eu, ei = torch.as_tensor(u, device=dev), torch.as_tensor(i, device=dev)
+    g = torch.Generator().manual_seed(1)
+    init_u, init_i = torch.randn(U, D, generator=g) * 0.1, torch.randn(I, D, generator=g) * 0.1
+    n = 30_000
+    samples = torch.stack([torch.randint(0, U, (n,), generator=g), torch.randint(0, I, (n,), generator=g),
+                           torch.randint(0, I, (n,), generator=g)], 1).to(dev)
+    perm = torch.randperm(n, generator=g).to(dev)
+    m = rdist.ShardedLightGCN(U, I, (eu, ei), D=D, n_layers=L, batch=B, device=dev, init_user=init_u.to(dev), init_item=init_i.to(dev))
+    losses = [m.train_epoch(samples, perm) for _ in range(2)]
+    eu_all, ei_all = m.gather_tables()
+    topi, topv, rank_, score = m.full_rank([5], 20)
+    if rank == 0:
+        # single-GPU run of the same thing
+        from recad_b200 import dataset, model
+        data = dataset.ArrayImplicitData("t", U, I, (eu, ei), dev, batch_size=B, prefetch=False)
+        ref = model.from_config("victim", "lightgcn", latent_dim_rec=D, lightGCN_n_layers=L, device=dev).I(dataset=data)
+        ref.embedding_user.weight.data.copy_(init_u)
+        ref.embedding_item.weight.data.copy_(init_i)
+        data.epoch_samples = lambda device=None: (samples, perm)
+        ref_losses = [ref.train_step()[0] for _ in range(2)]
+        ok = np.allclose(losses, ref_losses, rtol=1e-5)
+        ok &= torch.allclose(eu_all, ref.embedding_user.weight, rtol=1e-4, atol=2e-6)
+        ok &= torch.allclose(ei_all, ref.embedding_item.weight, rtol=1e-4, atol=2e-6)
+        rp, rc = data.train_csr(dev)
+        rtopi, rtopv, rrank, rscore, _ = ref.full_rank(torch.arange(m.Ug, device=dev), [5], 20, rp, rc)
+        ok &= torch.allclose(score, rscore, rtol=1e-4, atol=1e-6)
+        ok &= float((rank_ != rrank).float().mean()) < 0.01
+        q.put((bool(ok), losses, ref_losses))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_sharded_epoch_matches_single_gpu():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    ok, losses, ref_losses = q.get()
+    assert ok, (losses, ref_losses)
