@@ -346,7 +346,10 @@ def main():
     w = WORKLOADS[args.workload]
     out = run_reference(args, w) if args.impl == "reference" else run_b200(args, w)
     if out is not None and int(os.environ.get("RANK", 0)) == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
