@@ -334,6 +334,19 @@ int recad_recall_ndcg(const int32_t* topk_idx, int64_t n_eval, int32_t K, const 
 int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items,
                            int64_t train_size, const int64_t* allpos_rowptr,
                            const int32_t* allpos_col, int64_t* out, int64_t* n_out);
+/* Same result and same stream consumption as recad_mt19937_pairwise, built for 10^7..10^8 samples: the sequential
+ * stream parse reads only the row pointer and a per-user 1024-bit membership filter (filter [host] uint64[n_users * 16],
+ * filled once per dataset by recad_pairwise_filter_build; no false negatives, a "maybe" falls back to the exact
+ * search), and the positive items are gathered afterwards on n_threads host threads. */
+int recad_host_advise_huge(void* ptr, int64_t bytes);   /* madvise(MADV_HUGEPAGE) on an untouched host buffer; best effort */
+int recad_pairwise_filter_build(const int64_t* allpos_rowptr, const int32_t* allpos_col, int64_t n_users,
+                                uint64_t* filter, uint32_t* ext, int32_t n_threads);
+int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items,
+                                int64_t train_size, const int64_t* allpos_rowptr,
+                                const int32_t* allpos_col, const uint64_t* filter, const uint32_t* ext,
+                                int32_t n_threads, int64_t* out, int64_t* n_out);
+/* ext [host] uint32[nnz of allpos]: second-level filter of the users with more than 96 positives. */
+
 /* Per user k (dict order): its |pos| positives (label 1, stored order) then
  * ratio * |pos| negatives drawn with replacement from the ascending complement.
  * pos_sorted: the same lists sorted ascending (for the complement).

@@ -8,7 +8,15 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+#include <sys/mman.h>
+
 #include <algorithm>
+#include <chrono>
+#include <functional>
+#include <thread>
+#include <vector>
 
 #include "../../include/recad_b200.h"
 
@@ -97,6 +105,153 @@ int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t
     ++w;
   }
   delete[] users;
+  *n_out = w;
+  *pos = mt.pos;
+  return RECAD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast exact pairwise sampler.  The stream parse is inherently sequential (every draw's position depends on all
+// earlier rejections), so it is made as light as possible: per sample it touches the row pointer and ONE OR TWO
+// cache lines of a per-user 1024-bit membership filter (no false negatives; a "maybe" falls back to the exact
+// binary search of the user's sorted list, a "no" accepts the negative without ever reading the list).  Both
+// addresses are known in advance (all users are drawn first) and software-prefetched.  The positive ITEM is only
+// recorded as an index during the parse; the gather of the items -- the other random access -- runs afterwards on
+// all host threads.
+// ---------------------------------------------------------------------------------------------------------
+static inline void filter_bits(uint32_t item, uint32_t& a, uint32_t& b) {
+  a = (item * 0x9E3779B1u) >> 22;  // two 10-bit positions in the user's 1024-bit block
+  b = (item * 0x85EBCA77u) >> 22;
+}
+
+static void parallel_for(int64_t n, int n_threads, const std::function<void(int64_t, int64_t)>& fn) {
+  n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, (n + 65535) / 65536));
+  if (n_threads == 1) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  const int64_t per = (n + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; ++t) {
+    const int64_t lo = t * per, hi = std::min(n, lo + per);
+    if (lo < hi) th.emplace_back(fn, lo, hi);
+  }
+  for (auto& t : th) t.join();
+}
+
+// Ask for transparent huge pages on a freshly allocated (not yet touched) host buffer: the samplers' random
+// accesses into 10^8-byte arrays otherwise pay a TLB miss each.  Best effort (no-op where THP is off).
+int recad_host_advise_huge(void* ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return RECAD_OK;
+  const uintptr_t a = ((uintptr_t)ptr + 4095) & ~(uintptr_t)4095;
+  const uintptr_t e = ((uintptr_t)ptr + (uintptr_t)bytes) & ~(uintptr_t)4095;
+  if (e > a) madvise(reinterpret_cast<void*>(a), e - a, MADV_HUGEPAGE);
+  return RECAD_OK;
+}
+
+// second level for heavy users (more than kHeavy positives, where the 1024-bit block saturates): 32 bits per
+// positive, three probes, stored at the user's own offset of a [nnz] uint32 array => ~0.1 % false positives
+constexpr int64_t kHeavy = 96;
+static inline uint64_t ext_probe(uint32_t item, int j, uint64_t nbits) {
+  const uint32_t h = (item + 0x7F4A7C15u * (uint32_t)(j + 1)) * (j == 0 ? 0xC2B2AE35u : (j == 1 ? 0x27D4EB2Fu : 0x165667B1u));
+  return ((uint64_t)h * nbits) >> 32;
+}
+
+int recad_pairwise_filter_build(const int64_t* allpos_rowptr, const int32_t* allpos_col, int64_t n_users, uint64_t* filter,
+                                uint32_t* ext, int32_t n_threads) {
+  if (!allpos_rowptr || !filter || !ext || n_users <= 0) {
+    recad::set_error("pairwise_filter_build: bad argument");
+    return RECAD_ERR_ARG;
+  }
+  parallel_for(n_users, n_threads, [&](int64_t lo, int64_t hi) {
+    for (int64_t u = lo; u < hi; ++u) {
+      uint64_t* f = filter + u * 16;
+      for (int q = 0; q < 16; ++q) f[q] = 0;
+      const int64_t a0 = allpos_rowptr[u], a1 = allpos_rowptr[u + 1];
+      for (int64_t e = a0; e < a1; ++e) {
+        uint32_t a, b;
+        filter_bits((uint32_t)allpos_col[e], a, b);
+        f[a >> 6] |= 1ull << (a & 63);
+        f[b >> 6] |= 1ull << (b & 63);
+      }
+      for (int64_t e = a0; e < a1; ++e) ext[e] = 0;
+      if (a1 - a0 > kHeavy) {
+        const uint64_t nbits = (uint64_t)(a1 - a0) * 32;
+        for (int64_t e = a0; e < a1; ++e)
+          for (int j = 0; j < 3; ++j) {
+            const uint64_t p = ext_probe((uint32_t)allpos_col[e], j, nbits);
+            ext[a0 + (p >> 5)] |= 1u << (p & 31);
+          }
+      }
+    }
+  });
+  return RECAD_OK;
+}
+
+int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items, int64_t train_size,
+                                const int64_t* allpos_rowptr, const int32_t* allpos_col, const uint64_t* filter,
+                                const uint32_t* ext, int32_t n_threads, int64_t* out, int64_t* n_out) {
+  if (!key || !pos || !allpos_rowptr || !filter || !ext || !out || !n_out || n_users <= 0 || n_items <= 0 || train_size < 0 ||
+      n_users > 0xffffffffLL || n_items > 0xffffffffLL) {
+    recad::set_error("mt19937_pairwise_fast: bad argument");
+    return RECAD_ERR_ARG;
+  }
+  MT mt{key, *pos};
+  const bool trace = getenv("RECAD_SAMPLER_TRACE") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[sampler] %s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  };
+  std::vector<int64_t> users((size_t)std::max<int64_t>(train_size, 1));
+  for (int64_t k = 0; k < train_size; ++k) users[k] = (int64_t)mt.masked((uint64_t)n_users - 1);
+  lap("draw users");
+  // the parse writes (user, INDEX of the positive in allpos_col, negative) into `out`; the index is resolved below
+  constexpr int64_t kAheadPtr = 32, kAheadFilter = 16;
+  int64_t w = 0;
+  for (int64_t k = 0; k < train_size; ++k) {
+    if (k + kAheadPtr < train_size) __builtin_prefetch(allpos_rowptr + users[k + kAheadPtr]);
+    if (k + kAheadFilter < train_size) {
+      const uint64_t* f = filter + users[k + kAheadFilter] * 16;
+      __builtin_prefetch(f);
+      __builtin_prefetch(f + 8);
+    }
+    const int64_t u = users[k];
+    const int64_t lo = allpos_rowptr[u], hi = allpos_rowptr[u + 1];
+    if (hi == lo) continue;
+    if (hi - lo >= n_items) {
+      recad::set_error("mt19937_pairwise_fast: user %lld interacted with every item; negative sampling cannot terminate",
+                       (long long)u);
+      return RECAD_ERR_ARG;
+    }
+    const int64_t pidx = lo + (int64_t)mt.masked((uint64_t)(hi - lo) - 1);
+    const uint64_t* f = filter + u * 16;
+    int64_t neg;
+    for (;;) {
+      neg = (int64_t)mt.masked((uint64_t)n_items - 1);
+      uint32_t a, b;
+      filter_bits((uint32_t)neg, a, b);
+      if (!((f[a >> 6] >> (a & 63)) & (f[b >> 6] >> (b & 63)) & 1ull)) break;                 // definitely not a positive
+      if (hi - lo > kHeavy) {                                                                  // heavy user: second level
+        const uint64_t nbits = (uint64_t)(hi - lo) * 32;
+        const uint64_t p0 = ext_probe((uint32_t)neg, 0, nbits), p1 = ext_probe((uint32_t)neg, 1, nbits),
+                       p2 = ext_probe((uint32_t)neg, 2, nbits);
+        if (!((ext[lo + (p0 >> 5)] >> (p0 & 31)) & (ext[lo + (p1 >> 5)] >> (p1 & 31)) & (ext[lo + (p2 >> 5)] >> (p2 & 31)) & 1u))
+          break;
+      }
+      if (!std::binary_search(allpos_col + lo, allpos_col + hi, (int32_t)neg)) break;          // filter false positive
+    }
+    out[3 * w] = u; out[3 * w + 1] = pidx; out[3 * w + 2] = neg;
+    ++w;
+  }
+  lap("parse stream");
+  parallel_for(w, n_threads, [&](int64_t a, int64_t b) {
+    constexpr int64_t kAhead = 16;
+    for (int64_t k = a; k < b; ++k) {
+      if (k + kAhead < b) __builtin_prefetch(allpos_col + out[3 * (k + kAhead) + 1]);
+      out[3 * k + 1] = allpos_col[out[3 * k + 1]];
+    }
+  });
+  lap("gather positives");
   *n_out = w;
   *pos = mt.pos;
   return RECAD_OK;

@@ -451,7 +451,7 @@ class ArrayImplicitData:
         n_train = int(rowptr_u[-1])
         col_u = (graph.colidx[:n_train] - U).contiguous()                 # int32 item ids, ascending per user
         self._train_csr_dev = (rowptr_u, col_u)
-        self._allpos = (rowptr_u.cpu().numpy(), col_u.cpu().numpy())      # host copy for the C++ sampler
+        self._allpos = (ops.to_host(rowptr_u), ops.to_host(col_u))        # host copy (huge pages) for the C++ sampler
         self._train_csr = self._allpos
         self.traindataSize = n_train
         # pointwise sampler: dict order = users ascending, each list ascending

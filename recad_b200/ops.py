@@ -352,10 +352,49 @@ def mt_pairwise_raw(key, pos, n_users, n_items, train_size, allpos_rowptr, allpo
         out = np.empty((max(train_size, 1), 3), dtype=np.int64)
     assert out.dtype == np.int64 and out.flags.c_contiguous and out.shape[0] >= train_size
     n_out, cpos = C.c_int64(), C.c_int32(pos[0])
-    check(_lib.lib().recad_mt19937_pairwise(key.ctypes.data, C.byref(cpos), n_users, n_items, train_size, rp.ctypes.data,
-                                            col.ctypes.data, out.ctypes.data, C.byref(n_out)), "recad_mt19937_pairwise")
+    if train_size >= FAST_SAMPLER_MIN:
+        filt, ext = pairwise_filter(rp, col, n_users)
+        check(_lib.lib().recad_mt19937_pairwise_fast(key.ctypes.data, C.byref(cpos), n_users, n_items, train_size, rp.ctypes.data,
+                                                     col.ctypes.data, filt.ctypes.data, ext.ctypes.data, min(os.cpu_count() or 1, 32),
+                                                     out.ctypes.data, C.byref(n_out)), "recad_mt19937_pairwise_fast")
+    else:
+        check(_lib.lib().recad_mt19937_pairwise(key.ctypes.data, C.byref(cpos), n_users, n_items, train_size, rp.ctypes.data,
+                                                col.ctypes.data, out.ctypes.data, C.byref(n_out)), "recad_mt19937_pairwise")
     pos[0] = cpos.value
     return out[:n_out.value]
+
+
+def host_empty(shape, dtype):
+    """np.empty whose pages are requested as transparent huge pages (must be called before first touch)."""
+    a = np.empty(shape, dtype=dtype)
+    if a.nbytes >= (8 << 20):
+        _lib.lib().recad_host_advise_huge(a.ctypes.data, a.nbytes)
+    return a
+
+
+def to_host(t, dtype=None):
+    """Device tensor -> numpy array backed by huge pages (for arrays the samplers access at random)."""
+    out = host_empty(tuple(t.shape), dtype or {torch.int64: np.int64, torch.int32: np.int32, torch.float32: np.float32}[t.dtype])
+    torch.from_numpy(out).copy_(t)
+    return out
+
+
+FAST_SAMPLER_MIN = 1 << 20      # samples per epoch from which the filter-based parser pays off
+_filters = {}                   # id(allpos_col array) -> (weakref-free cache key, filter)
+
+
+def pairwise_filter(allpos_rowptr, allpos_col, n_users):
+    """Per-user 1024-bit membership filters for mt_pairwise_raw(fast); built once per positives array."""
+    key = (allpos_col.ctypes.data, len(allpos_col), int(n_users))
+    if key not in _filters:
+        _filters.clear()
+        filt = host_empty(int(n_users) * 16, np.uint64)
+        ext = host_empty(max(len(allpos_col), 1), np.uint32)
+        check(_lib.lib().recad_pairwise_filter_build(allpos_rowptr.ctypes.data, allpos_col.ctypes.data, n_users,
+                                                     filt.ctypes.data, ext.ctypes.data, os.cpu_count() or 1),
+              "recad_pairwise_filter_build")
+        _filters[key] = (filt, ext)
+    return _filters[key]
 
 
 def mt_pointwise_raw(key, pos, user_ids, pos_rowptr, pos_items, n_items, ratio, out=None):

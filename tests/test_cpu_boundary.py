@@ -152,3 +152,35 @@ def test_eligible_users_like_reference():
     from oracle import evaluate as oev
     for tg in ([0], [5], [0, 5, 62]):
         assert evaluate.eligible_users(d, tg).tolist() == sorted(oev.eligible_users(tr, tg))
+
+
+def test_fast_filter_sampler_is_bit_identical_to_the_plain_one():
+    """The filter-based parser used for large epochs draws exactly the same samples and leaves exactly the same
+    RNG state as the plain one (and hence as the reference), including heavy users (> 96 positives)."""
+    tr, va, te = util.dicts("game")
+    m = META["game"]
+    U, I = m["n_users"], m["n_items"]
+    u, i, _, _ = og.flatten_dict(tr)
+    ptr, idx = og.all_pos(u, i, U, I)
+    ptr, idx = np.ascontiguousarray(ptr), np.ascontiguousarray(idx, dtype=np.int32)
+    assert np.diff(ptr).max() > 96
+    old = ops.FAST_SAMPLER_MIN
+    try:
+        outs = []
+        for thr in (1 << 60, 0):
+            ops.FAST_SAMPLER_MIN = thr
+            np.random.seed(7)
+            S = ops.mt_pairwise(U, I, 200_000, ptr, idx)
+            outs.append((S.copy(), np.random.get_state()[1].copy(), np.random.get_state()[2]))
+    finally:
+        ops.FAST_SAMPLER_MIN = old
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+    from oracle import sampler as osm
+    np.random.seed(7)
+    ref = osm.pairwise_sample_numpy(U, I, 3000, ptr, idx)
+    ops.FAST_SAMPLER_MIN = 0
+    try:
+        np.random.seed(7)
+        assert np.array_equal(ops.mt_pairwise(U, I, 3000, ptr, idx), ref)
+    finally:
+        ops.FAST_SAMPLER_MIN = old
