@@ -265,6 +265,12 @@ int recad_ncf_forward(const recad_ncf* st, const int64_t* users, const int64_t* 
 int recad_ncf_train_epoch(const recad_ncf* st, const int64_t* samples, const int64_t* perm,
                           int64_t n_samples, int64_t batch, int64_t step0, void* stream);
 
+/* The tensor-core GEMM of the NCF tower, exposed for testing: C[M, N] = A[M, K] . B[N, K]^T (+ bias[N]) (ReLU) on
+ * tcgen05 (kind::tf32, fp32 accumulators in TMEM, TMA operands) with the 3xTF32 operand split, i.e. fp32-accurate.
+ * A, B, C row-major [dev]; scratch [dev] float[2 * (M + N) * ((K + 3) / 4 * 4)]. */
+int recad_gemm_tn_tf32x3(const float* A, const float* B, int32_t M, int32_t N, int32_t K, const float* bias,
+                         int32_t relu, float* C, float* scratch, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * Full-ranking evaluation  (recad/workflow/normal.py:57-93, 111-160;
  * lightgcn.py:115-120 getUsersRating)

@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "librecad_b200.so")
-SOURCES = ["api.cu", "scan.cu", "sort.cu", "csr.cu", "spmm.cu", "bpr.cu", "mf.cu", "ncf.cu", "eval.cu", "eval_tc.cu", "sampler.cpp"]
-HEADERS = ["common.cuh", "rank_epilogue.cuh", os.path.join(ROOT, "include", "recad_b200.h")]
+SOURCES = ["api.cu", "scan.cu", "sort.cu", "csr.cu", "spmm.cu", "bpr.cu", "mf.cu", "ncf.cu", "eval.cu", "eval_tc.cu", "gemm_tc.cu", "sampler.cpp"]
+HEADERS = ["common.cuh", "rank_epilogue.cuh", "tc_common.cuh", os.path.join(ROOT, "include", "recad_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -225,6 +225,20 @@ def adam(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, cnt=None, reg_sc
                                     int(step), _stream(p.device)), "recad_adam")
 
 
+def gemm_tn(A, B, bias=None, relu=False):
+    """C = A @ B.T (+ bias) (relu) on the tensor cores (tcgen05, 3xTF32 = fp32-accurate).  A [M, K], B [N, K]."""
+    _need_cuda(A, B, bias)
+    M, K = A.shape
+    N = B.shape[0]
+    ld = (K + 3) // 4 * 4
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        scratch = torch.empty(2 * (M + N) * ld, dtype=torch.float32, device=A.device)
+        check(_lib.lib().recad_gemm_tn_tf32x3(_ptr(A.contiguous()), _ptr(B.contiguous()), M, N, K, _ptr(bias), int(relu), _ptr(out),
+                                              _ptr(scratch), _stream(A.device)), "recad_gemm_tn_tf32x3")
+    return out
+
+
 def dot_scores(O, n_users, users, items):
     _need_cuda(O, users, items)
     out = torch.empty(users.numel(), dtype=torch.float32, device=O.device)

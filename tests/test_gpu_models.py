@@ -230,3 +230,19 @@ def test_ncf_default_tower_init_stream_and_epoch_match_reference():
     _close(m.embed_user_MLP.weight[:4].cpu(), z["final_um_rows"], rtol=1e-3, atol=2e-6)
     _close(lins[4].weight.cpu(), z["final_W4"], rtol=1e-3, atol=2e-6)
     _close(m(torch.as_tensor(z["q_users"]), torch.as_tensor(z["q_items"])).cpu(), z["q_scores"], rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------ tensor-core GEMM (NCF tower)
+@pytest.mark.parametrize("M,N,K,bias,relu", [(1024, 512, 1024, True, True), (317, 32, 64, True, False), (128, 64, 1000, False, False),
+                                             (1000, 1, 64, True, False), (5, 200, 36, False, True), (512, 1024, 317, False, False)])
+def test_tensor_core_gemm_is_fp32_accurate(M, N, K, bias, relu):
+    from recad_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    b = torch.randn(N, generator=g) if bias else None
+    C = ops.gemm_tn(A.to(DEV), B.to(DEV), None if b is None else b.to(DEV), relu).cpu().double()
+    ref = A.double() @ B.double().T + (0 if b is None else b.double())
+    mag = A.abs().double() @ B.abs().double().T + 1.0
+    if relu:
+        ref = ref.clamp_min(0)
+    assert float(((C - ref).abs() / mag).max()) < 2e-6
