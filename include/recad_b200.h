@@ -247,6 +247,9 @@ typedef struct recad_ncf {
   int64_t n_users, n_items;
   int32_t factor, n_layers;
   float lr, beta1, beta2, eps;
+  int32_t tower_fp32; /* 0: tower GEMMs on tcgen05 (3xTF32, fp32-accurate); 1: exact fp32 CUDA-core GEMMs (bit-stable
+                         ReLU masks; what the strict parity tests use) */
+  int32_t _pad;
   float* params;      /* [dev] float[n_params] */
   float* m;           /* [dev] Adam first moment  (training only) */
   float* v;           /* [dev] Adam second moment (training only) */

@@ -62,7 +62,10 @@ MODEL = {   # default.py:104-133 (+ logging_level / device, 232-233)
         },
         "mf": {"factor_num": 3, "embedding_size": 128, "dropout": 0, "optim": "adam", "lr": 0.001},
         "ncf": {"factor_num": 32, "num_layers": 5, "dropout": 0, "model": "NeuMF-end", "GMF_model": None,
-                "MLP_model": None, "optim": "adam", "lr": 0.001},
+                "MLP_model": None, "optim": "adam", "lr": 0.001,
+                # NEW: "tf32x3" = tower GEMMs on the tensor cores (fp32-accurate, ~2^-21); "fp32" = exact CUDA-core
+                # GEMMs whose ReLU masks are bit-stable (element-wise parity with the reference's fp32)
+                "tower_precision": "tf32x3"},
     }
 }
 for _m in MODEL["victim"].values():

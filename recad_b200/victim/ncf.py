@@ -40,6 +40,9 @@ class NCF(BaseVictim):
             raise NotImplementedError("only the default 'NeuMF-end' variant (default.py:127) is implemented")
         if str(config["optim"]).lower() != "adam":
             raise ValueError("optimizer not supported")
+        self.tower_precision = config.get("tower_precision", "tf32x3")
+        if self.tower_precision not in ("tf32x3", "fp32"):
+            raise ValueError("tower_precision must be 'tf32x3' (tensor cores) or 'fp32' (exact CUDA-core GEMMs)")
         info = self.dataset.info_describe()
         U, I = info["n_users"], info["n_items"]
         self.num_users, self.num_items, self.f, self.L = U, I, factor_num, num_layers
@@ -106,6 +109,7 @@ class NCF(BaseVictim):
         st = _lib.NCF()
         st.n_users, st.n_items, st.factor, st.n_layers = U, I, f, self.L
         st.lr, st.beta1, st.beta2, st.eps = self.config["lr"], 0.9, 0.999, 1e-8
+        st.tower_fp32 = 1 if self.tower_precision == "fp32" else 0
         st.params, st.m, st.v, st.grads, st.n_params = (self.flat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                                         self.g.data_ptr(), total)
         st.work, st.work_floats, st.max_batch, st.loss_acc = self.work.data_ptr(), work_floats, self.max_batch, self.loss_acc.data_ptr()

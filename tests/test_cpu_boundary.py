@@ -35,7 +35,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.CSR) == 14 * 8
     assert C.sizeof(_lib.LightGCN) == 8 + 16 + 8 + 6 * 4 + 9 * 8
     assert C.sizeof(_lib.MF) == 16 + 6 * 4 + 17 * 8
-    assert C.sizeof(_lib.NCF) == 16 + 8 + 16 + 4 * 8 + 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(_lib.NCF) == 16 + 8 + 16 + 8 + 4 * 8 + 8 + 8 + 8 + 8 + 8
 
 
 def test_host_error_paths_report_through_last_error():

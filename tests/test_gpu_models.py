@@ -191,25 +191,43 @@ def _load_ncf(m, z, prefix, L):
     m.predict_layer.bias.data.copy_(torch.as_tensor(z[f"{prefix}_bp"]))
 
 
-def test_ncf_small_tower_two_epochs_match_reference():
+def _rows_close(a, b, rtol, atol, min_rows):
+    """Tensor-core tower: a ReLU unit whose pre-activation sits within ~1e-7 of zero can switch under ANY change of
+    summation order, and Adam then moves every weight fed by that sample differently.  So: almost all ROWS must
+    agree element-wise, and nothing may be far off."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    ok_rows = np.all(np.abs(a - b) <= atol + rtol * np.abs(b), axis=-1)
+    assert ok_rows.mean() >= min_rows, f"only {ok_rows.mean():.3f} of the rows agree"
+    assert np.abs(a - b).max() <= 5e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_ncf_small_tower_two_epochs_match_reference(precision):
     from recad_b200 import model
     z = util.load("ncf_dev.npz")
     U, I = META["dev"]["n_users"], META["dev"]["n_items"]
     batches = util.split_batches(z, ("batch_users", "batch_items", "batch_labels"))
     data = StubData(U, I, batches, ("users", "items", "labels"))
     data.per_epoch = len(batches) // 2
-    m = model.from_config("victim", "ncf", factor_num=8, num_layers=3, device=torch.device(DEV)).I(dataset=data)
+    m = model.from_config("victim", "ncf", factor_num=8, num_layers=3, tower_precision=precision,
+                          device=torch.device(DEV)).I(dataset=data)
     _load_ncf(m, z, "init", 3)
     losses = [m.train_step()[0] for _ in range(2)]
     _close(losses, z["losses"], rtol=1e-4, atol=0)
     lins = [x for x in m.MLP_layers if isinstance(x, torch.nn.Linear)]
-    _close(m.embed_user_MLP.weight.cpu(), z["final_um"], rtol=1e-3, atol=2e-6)
-    _close(lins[0].weight.cpu(), z["final_W0"], rtol=1e-3, atol=2e-6)
-    _close(m.predict_layer.weight.cpu(), z["final_Wp"], rtol=1e-3, atol=2e-6)
-    _close(m(torch.as_tensor(z["q_users"]), torch.as_tensor(z["q_items"])).cpu(), z["q_scores"], rtol=1e-4, atol=1e-6)
+    if precision == "fp32":
+        _close(m.embed_user_MLP.weight.cpu(), z["final_um"], rtol=1e-3, atol=2e-6)
+        _close(lins[0].weight.cpu(), z["final_W0"], rtol=1e-3, atol=2e-6)
+        _close(m.predict_layer.weight.cpu(), z["final_Wp"], rtol=1e-3, atol=2e-6)
+        _close(m(torch.as_tensor(z["q_users"]), torch.as_tensor(z["q_items"])).cpu(), z["q_scores"], rtol=1e-4, atol=1e-6)
+    else:
+        _rows_close(m.embed_user_MLP.weight.cpu(), z["final_um"], 1e-3, 2e-6, 0.8)
+        _rows_close(m.predict_layer.weight.cpu(), z["final_Wp"], 1e-2, 1e-5, 1.0)
+        _close(m(torch.as_tensor(z["q_users"]), torch.as_tensor(z["q_items"])).cpu(), z["q_scores"], rtol=2e-3, atol=1e-5)
 
 
-def test_ncf_default_tower_init_stream_and_epoch_match_reference():
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_ncf_default_tower_init_stream_and_epoch_match_reference(precision):
     """Default NeuMF (f=32, 5 layers).  The fixture stores no initial weights: they are re-created by
     replaying the reference's constructor on the CPU generator (torch.manual_seed(2023)), which also
     pins that the drop-in consumes the torch RNG exactly like the reference."""
@@ -220,16 +238,21 @@ def test_ncf_default_tower_init_stream_and_epoch_match_reference():
                                sample="pointwise", device=torch.device(DEV))
     torch.manual_seed(2023)
     np.random.seed(2023)
-    m = model.from_config("victim", "ncf", device=torch.device(DEV)).I(dataset=data)
+    m = model.from_config("victim", "ncf", tower_precision=precision, device=torch.device(DEV)).I(dataset=data)
     lins = [x for x in m.MLP_layers if isinstance(x, torch.nn.Linear)]
     if not np.array_equal(m.embed_user_MLP.weight[:4].cpu().numpy(), z["init_um_rows"]):
         pytest.skip("torch CPU generator stream differs on this host; init replay not possible")
     assert np.array_equal(lins[4].weight.cpu().numpy(), z["init_W4"])
     loss = m.train_step()[0]
     assert abs(loss - z["losses"][0]) <= 1e-4 * z["losses"][0]
-    _close(m.embed_user_MLP.weight[:4].cpu(), z["final_um_rows"], rtol=1e-3, atol=2e-6)
-    _close(lins[4].weight.cpu(), z["final_W4"], rtol=1e-3, atol=2e-6)
-    _close(m(torch.as_tensor(z["q_users"]), torch.as_tensor(z["q_items"])).cpu(), z["q_scores"], rtol=1e-4, atol=1e-6)
+    if precision == "fp32":
+        _close(m.embed_user_MLP.weight[:4].cpu(), z["final_um_rows"], rtol=1e-3, atol=2e-6)
+        _close(lins[4].weight.cpu(), z["final_W4"], rtol=1e-3, atol=2e-6)
+        _close(m(torch.as_tensor(z["q_users"]), torch.as_tensor(z["q_items"])).cpu(), z["q_scores"], rtol=1e-4, atol=1e-6)
+    else:
+        assert np.abs(m.embed_user_MLP.weight[:4].cpu().numpy() - z["final_um_rows"]).max() <= 3.5e-3   # <= 3 Adam steps of lr
+        _close(lins[4].weight.cpu(), z["final_W4"], rtol=5e-2, atol=2e-5)
+        _close(m(torch.as_tensor(z["q_users"]), torch.as_tensor(z["q_items"])).cpu(), z["q_scores"], rtol=5e-3, atol=1e-5)
 
 
 # ------------------------------------------------------------------ tensor-core GEMM (NCF tower)
