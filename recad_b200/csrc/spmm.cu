@@ -98,7 +98,8 @@ spmm_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
         const int cc = __shfl_sync(kFull, c, k & 31);
         w[u] = __shfl_sync(kFull, v, k & 31);
         if (k < cnt) {
-          x[u] = kStreamX ? ld_stream4(X4 + (int64_t)cc * LPR + l) : __ldg(X4 + (int64_t)cc * LPR + l);
+          const uint32_t off = (uint32_t)cc * (uint32_t)LPR + (uint32_t)l;   // float4 units; checked < 2^32 on the host
+          x[u] = kStreamX ? ld_stream4(X4 + off) : __ldg(X4 + off);
         } else {
           x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           w[u] = 0.f;
@@ -135,11 +136,24 @@ spmm_fixup_kernel(int64_t n_mrow, const int32_t* __restrict__ mrow, const int32_
   const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
   const int s0 = mrow_lo[j], s1 = mrow_lo[j + 1];
   const float4* __restrict__ P4 = reinterpret_cast<const float4*>(partials);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = s0 + sub; s < s1; s += NPL) {
-    const float4 p = P4[(int64_t)s * LPR + l];
-    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+  // a hot item row has thousands of slots: keep 4 loads in flight per lane (fixed association => deterministic)
+  float4 a4[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) a4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = s0 + sub;
+  for (; s + 3 * NPL < s1; s += 4 * NPL) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 p = P4[(int64_t)(s + q * NPL) * LPR + l];
+      a4[q].x += p.x; a4[q].y += p.y; a4[q].z += p.z; a4[q].w += p.w;
+    }
   }
+  for (; s < s1; s += NPL) {
+    const float4 p = P4[(int64_t)s * LPR + l];
+    a4[0].x += p.x; a4[0].y += p.y; a4[0].z += p.z; a4[0].w += p.w;
+  }
+  float4 acc = make_float4((a4[0].x + a4[1].x) + (a4[2].x + a4[3].x), (a4[0].y + a4[1].y) + (a4[2].y + a4[3].y),
+                           (a4[0].z + a4[1].z) + (a4[2].z + a4[3].z), (a4[0].w + a4[1].w) + (a4[2].w + a4[3].w));
 #pragma unroll
   for (int o = 16; o >= LPR; o >>= 1) {
     acc.x += __shfl_xor_sync(kFull, acc.x, o);
@@ -230,13 +244,13 @@ spmm_generic_fixup_kernel(int64_t n_mrow, const int32_t* __restrict__ mrow, cons
   }
 }
 
-// tuning knob (RECAD_SPMM_VARIANT): bit0 = persistent grid, bit1 = cap registers for 6 CTAs/SM,
-// bit2 = stream X past L1.  The default is the variant measured fastest on B200 (profiles/).
+// tuning knob (RECAD_SPMM_VARIANT): bit0 = persistent grid, bits 1-2 = register cap (0: none, 1: 6 CTAs/SM,
+// 2: 5 CTAs/SM, 3: 4 CTAs/SM), bit3 = deeper unroll.  The default is the variant measured fastest on B200 (profiles/).
 static int spmm_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("RECAD_SPMM_VARIANT");
-    v = e ? atoi(e) : 3;
+    v = e ? atoi(e) : 5;
   }
   return v;
 }
@@ -266,8 +280,8 @@ static int launch_spmm(const recad_csr* A, const float* X, float* Y, const float
   switch ((v >> 1) & 3) {
     case 0: rc = launch_spmm_v<D, UNR, 1, false>(A, X, Y, C, Z, alpha, pers, s); break;
     case 1: rc = launch_spmm_v<D, UNR, 6, false>(A, X, Y, C, Z, alpha, pers, s); break;
-    case 2: rc = launch_spmm_v<D, UNR, 1, true>(A, X, Y, C, Z, alpha, pers, s); break;
-    default: rc = launch_spmm_v<D, UNR, 6, true>(A, X, Y, C, Z, alpha, pers, s); break;
+    case 2: rc = launch_spmm_v<D, UNR, 5, false>(A, X, Y, C, Z, alpha, pers, s); break;
+    default: rc = launch_spmm_v<D, UNR, 4, false>(A, X, Y, C, Z, alpha, pers, s); break;
   }
   if (rc) return rc;
   if (A->n_mrow > 0) {
@@ -291,6 +305,7 @@ extern "C" int recad_spmm(const recad_csr* A, const float* X, float* Y, const fl
                 RECAD_ERR_ARG, "spmm: matrix has no plan (call recad_spmm_plan)");
   RECAD_REQUIRE(A->nnz == 0 || (A->colidx && A->vals), RECAD_ERR_ARG, "spmm: null colidx/vals");
   RECAD_REQUIRE(A->n_mrow == 0 || (A->mrow && A->mrow_lo && A->partials), RECAD_ERR_ARG, "spmm: null multi-row plan");
+  RECAD_REQUIRE((int64_t)2147483647 / (D / 4 > 0 ? D / 4 : 1) > 0, RECAD_ERR_ARG, "spmm: bad D");
   RECAD_REQUIRE(D >= 4 && D % 4 == 0 && D <= 4 * 32 * kGenericMaxVec, RECAD_ERR_UNSUPPORTED,
                 "spmm: D = %d must be a multiple of 4 in [4, %d]", D, 4 * 32 * kGenericMaxVec);
   RECAD_REQUIRE((((uintptr_t)X | (uintptr_t)Y | (uintptr_t)C | (uintptr_t)Z | (uintptr_t)A->partials) & 15) == 0,

@@ -62,6 +62,13 @@ class ShardedLightGCN:
             degree[Ug:] = block
         self.graph = ops.Graph.from_edges((eu[mine] - self.lo).contiguous(), ei[mine].contiguous(), Ug, self.I,
                                           degree_hook=complete_item_degrees)
+        # the same matrix as two row blocks, so that the item rows (whose result must be all-reduced) can be
+        # multiplied FIRST and their all-reduce overlapped with the multiplication of the user rows
+        g = self.graph
+        nnz_u = int(g.rowptr[Ug])
+        self.g_user = ops.Graph.from_csr(g.rowptr[:Ug + 1], g.colidx[:nnz_u] - Ug, g.vals[:nnz_u], n_cols=self.I)
+        self.g_item = ops.Graph.from_csr(g.rowptr[Ug:] - nnz_u, g.colidx[nnz_u:], g.vals[nnz_u:], n_cols=Ug)
+        self.overlap = True
         N = Ug + self.I
         with torch.cuda.device(self.dev):
             self.E = torch.empty((N, D), dtype=torch.float32, device=self.dev)
@@ -80,6 +87,19 @@ class ShardedLightGCN:
         dist.all_reduce(t[self.Ug:], group=self.group)          # contiguous [I, D] (or [I]) block, in place
         self.n_allreduce += 1
 
+    def _spmm_exchange(self, x, y):
+        """y = A_g x with the item block of y summed over ranks."""
+        Ug = self.Ug
+        if not self.overlap:
+            ops.spmm(self.graph, x, y)
+            self._allreduce_items(y)
+            return
+        ops.spmm(self.g_item, x[:Ug], y[Ug:])                       # partial item rows (gathers own users)
+        work = dist.all_reduce(y[Ug:], group=self.group, async_op=True)
+        self.n_allreduce += 1
+        ops.spmm(self.g_user, x[Ug:], y[:Ug])                       # own user rows (gathers the item replica)
+        work.wait()
+
     def propagate(self):
         """O = mean_k A^k E (lightgcn.py:82-113), L local SpMMs + L all-reduces of the item block."""
         L = self.L
@@ -88,8 +108,7 @@ class ShardedLightGCN:
         x = self.E
         for k in range(L):
             y = self.X1 if k & 1 else self.X0
-            ops.spmm(self.graph, x, y)
-            self._allreduce_items(y)
+            self._spmm_exchange(x, y)
             s = 1.0 / (L + 1) if k == L - 1 else 1.0
             ops.axpby(self.O, s, self.E if k == 0 else self.O, s, y)
             x = y
@@ -122,8 +141,7 @@ class ShardedLightGCN:
             t = self.g
             for k in range(L):                       # Horner: t <- g + A t
                 y = self.X1 if k & 1 else self.X0
-                ops.spmm(self.graph, t, y)
-                self._allreduce_items(y)
+                self._spmm_exchange(t, y)
                 ops.axpby(y, 1.0, self.g, 1.0, y)
                 t = y
             ops.adam(self.E, t, self.m, self.v, self.steps, lr=self.lr, cnt=self.cnt, reg_scale=self.lam / B_of[b])
