@@ -34,6 +34,7 @@ WORKLOADS = {
     "tiny": dict(n_users=20_000, n_items=5_000, n_edges=400_000, D=64, L=3, batch=65_536),
 }
 METRIC = "lightgcn_bpr_epoch_plus_fullrank_eval_seconds"
+NCU_SPMM_DRAM_BYTES = 10_500_000_000   # measured per launch on the synthetic graph: 9.5 GB read + 1.0 GB written
 
 
 def synth_edges(w, device, seed=0):
@@ -241,7 +242,10 @@ def run_b200(args, w):
         "eval_users_per_s": round(U / (float(np.mean(evl_ms)) / 1e3), 1), "epoch_loss": loss,
         "graph_build_s": round(t_graph, 4), "edge_gen_s": round(t_gen, 3), "host_sampler_s": round(t_sampler, 3),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "kernel": "spmm_seg_kernel<64,4>",
+                     "frac": round(achieved / pk["hbm_gbs"], 4),
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/ncu_spmm_r01.md)
+                     "traffic": NCU_SPMM_DRAM_BYTES if args.workload == "synthetic" else None,
+                     "kernel": "spmm_seg_kernel<64,4,5> + spmm_fixup_kernel<64>",
                      "ms_per_launch": round(spmm_ms, 4), "algorithmic_bytes": alg, "peak_source": pk_src,
                      "model": "no-reuse gather: nnz*(8+4D) + 3*N*4D + (N+1)*4"},
         "e2e": {"value": round(float(np.mean(e2e)), 6), "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

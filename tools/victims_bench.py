@@ -1,0 +1,67 @@
+"""Epoch / evaluation timings of the three victims on the ml1m-shaped graph (BASELINE.json configs[0..2] shapes):
+one JSON line per model, with the CPU oracle port (torch CPU, all host threads) timed on a bounded sample beside it.
+    python tools/victims_bench.py > profiles/victims_ml1m_r01.jsonl"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pointwise_models as opm  # noqa: E402  (CPU baseline leg only)
+from recad_b200 import dataset, evaluate, model, synthetic  # noqa: E402
+
+DEV = torch.device("cuda:0")
+tr, va, te = synthetic.make_splits(synthetic.ML1M, seed=0)
+
+
+def timed(fn, n=3):
+    fn()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(n):
+        out = fn()
+    torch.cuda.synchronize()
+    return (time.time() - t0) / n, out
+
+
+def cpu_epoch_estimate(oracle, samples, batch, n_batches_total, n_time=20):
+    t0 = time.time()
+    for k in range(n_time):
+        s = samples[k * batch:(k + 1) * batch]
+        oracle.step(s[:, 0], s[:, 1], s[:, 2])
+    return (time.time() - t0) / n_time * n_batches_total
+
+
+for name, kw in (("mf", {"embedding_size": 64}), ("ncf", {}), ("ncf", {"tower_precision": "fp32"}), ("lightgcn", {"latent_dim_rec": 64})):
+    pairwise = name == "lightgcn"
+    data = dataset.from_config("implicit", "ml1m", train_dict=tr, valid_dict=va, test_dict=te, need_graph=pairwise,
+                               graph_edges="train", sample="pairwise" if pairwise else "pointwise", device=DEV)
+    torch.manual_seed(2023)
+    np.random.seed(2023)
+    m = model.from_config("victim", name, device=DEV, **kw).I(dataset=data)
+    ep_s, loss = timed(lambda: m.train_step())
+    ev_s, rows = timed(lambda: evaluate.model_rows(m, data, [0], [10, 20, 50, 100])[0])
+    n = data.traindataSize * (1 if pairwise else 5)
+    B = 1024
+    rec = {"victim": name, **{k: v for k, v in kw.items()}, "workload": "ml1m-shaped 5950 x 3702, 468 649 train interactions",
+           "samples_per_epoch": n, "batch": B, "epoch_s (train_step, incl. exact host sampler + H2D)": round(ep_s, 4),
+           "loss": loss[0], "fullrank_eval_s (all eligible users, HR@k rows)": round(ev_s, 5), "eval_users": int(len(rows))}
+    if not pairwise:
+        samples, perm = data.epoch_samples(DEV)
+        S = samples[perm].cpu().numpy()
+        torch.manual_seed(2023)
+        if name == "mf":
+            o = opm.MFOracle(*(p.detach().cpu().numpy() for p in (m.user_emb.weight, m.user_bias.weight, m.item_emb.weight, m.item_bias.weight)))
+        else:
+            lin = [l for l in m.MLP_layers if isinstance(l, torch.nn.Linear)]
+            o = opm.NCFOracle({"ug": m.embed_user_GMF.weight.cpu().numpy(), "ig": m.embed_item_GMF.weight.cpu().numpy(),
+                               "um": m.embed_user_MLP.weight.cpu().numpy(), "im": m.embed_item_MLP.weight.cpu().numpy(),
+                               "W": [l.weight.cpu().numpy() for l in lin], "b": [l.bias.cpu().numpy() for l in lin],
+                               "Wp": m.predict_layer.weight.cpu().numpy(), "bp": m.predict_layer.bias.cpu().numpy()})
+        rec["cpu_port_epoch_s (extrapolated from 20 batches, %d threads)" % torch.get_num_threads()] = round(
+            cpu_epoch_estimate(o, S, B, (n + B - 1) // B), 2)
+    print(json.dumps(rec), flush=True)
