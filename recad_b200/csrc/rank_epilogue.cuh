@@ -65,11 +65,9 @@ static __device__ __noinline__ void topk_finalize(float* __restrict__ topv, int3
   }
 }
 
+// (a): per target, count the scores of this chunk that outrank it
 template <int NC, int TMAX>
-__device__ __forceinline__ void rank_topk_chunk(float (&s)[NC], int64_t base, int T, RankState<TMAX>& rs, float& tau,
-                                                float* __restrict__ topv, int32_t* __restrict__ topi, int K, int stride,
-                                                int slot, int& min_pos) {
-  static_assert(NC % 8 == 0, "chunks are scanned in groups of 8");
+__device__ __forceinline__ void rank_count_chunk(const float (&s)[NC], int64_t base, int T, RankState<TMAX>& rs) {
 #pragma unroll
   for (int t = 0; t < TMAX; ++t) {
     if (t < T) {
@@ -95,6 +93,14 @@ __device__ __forceinline__ void rank_topk_chunk(float (&s)[NC], int64_t base, in
       }
     }
   }
+}
+
+template <int NC, int TMAX>
+__device__ __forceinline__ void rank_topk_chunk(float (&s)[NC], int64_t base, int T, RankState<TMAX>& rs, float& tau,
+                                                float* __restrict__ topv, int32_t* __restrict__ topi, int K, int stride,
+                                                int slot, int& min_pos) {
+  static_assert(NC % 8 == 0, "chunks are scanned in groups of 8");
+  rank_count_chunk<NC, TMAX>(s, base, T, rs);
   // group maxima (8 consecutive items each): only a group that beats tau is looked at element by element
   float gm[NC / 8];
 #pragma unroll
