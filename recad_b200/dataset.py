@@ -485,6 +485,36 @@ class ArrayImplicitData:
         out = self._gt[split]
         return out if device is None else tuple(torch.from_numpy(a).to(device) for a in out)
 
+    # ---------------------------------------------------------------- injection (implicit.py:482-494)
+    @staticmethod
+    def fake_rows(data, filter_num=4):
+        """fake_array2dict (implicit.py:107-114) as CSR: row r keeps the columns rated STRICTLY above
+        filter_num; n_users = max uid + 1 (implicit.py:194), so trailing rows with nothing left do not
+        become users.  -> (rowptr int64 [F + 1], items int32 ascending per row)"""
+        data = np.asarray(data)
+        assert len(data.shape) == 2, "Expect a user-item 2D rating matrix"
+        r, c = np.nonzero(data > filter_num)
+        F = int(r.max()) + 1 if r.size else 0
+        rowptr = np.zeros(F + 1, dtype=np.int64)
+        np.cumsum(np.bincount(r, minlength=F), out=rowptr[1:])
+        return rowptr, c.astype(np.int32)
+
+    def inject_data(self, data_mode, data, **kwargs):
+        """New, independent dataset with the fake users appended.  The device graph is EXTENDED (rows
+        appended, touched items re-normalised, no re-sort); the reference rebuilds everything from dicts
+        (implicit.py:493, base.py:108-118)."""
+        if data_mode != "explicit":
+            raise NotImplementedError(f"Injection not supported in {data_mode} mode")
+        rowptr, items = self.fake_rows(data, kwargs["filter_num"])
+        assert data.shape[1] <= self.n_items, "fake profiles rate items outside the item universe"
+        F = len(rowptr) - 1
+        graph = self.Graph.append_users(self.n_users, self.n_items, torch.from_numpy(rowptr), torch.from_numpy(items))
+        c = self.config
+        batch = c["pairwise_batch_size"] if c["sample"] == "pairwise" else c["pointwise_batch_size"]
+        return ArrayImplicitData(self._dataset_name, self.n_users + F, self.n_items, None, c["device"], test=self._test,
+                                 sample=c["sample"], batch_size=batch, negative_ratio=c["negative_ratio"],
+                                 need_graph=c["need_graph"], graph=graph, prefetch=c.get("prefetch"))
+
     def info_describe(self):
         infos = {"n_users": self.n_users, "n_items": self.n_items, "train_interactions": self.traindataSize,
                  "train_dict": None}

@@ -45,23 +45,27 @@ def route_epoch(samples, perm, batch, lo, hi):
 
 class ShardedLightGCN:
     def __init__(self, n_users, n_items, edges, D=64, n_layers=3, lam=1e-4, lr=1e-3, batch=1024, device=None,
-                 init_user=None, init_item=None, group=None):
+                 init_user=None, init_item=None, group=None, graph=None, bounds=None):
+        """edges: (users, items) int64 CUDA tensors of the GLOBAL edge list (every rank passes the same), or
+        None with `graph` = this rank's prebuilt local matrix and `bounds` = its user range (inject())."""
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.dev = torch.device(device)
         self.U, self.I, self.D, self.L, self.lam, self.lr, self.batch = int(n_users), int(n_items), D, n_layers, lam, lr, batch
-        self.lo, self.hi = user_range(n_users, self.rank, self.world)
+        self.lo, self.hi = bounds if bounds is not None else user_range(n_users, self.rank, self.world)
         self.Ug = self.hi - self.lo
-        eu, ei = edges
-        mine = (eu >= self.lo) & (eu < self.hi)
         Ug = self.Ug
+        if graph is None:
+            eu, ei = edges
+            mine = (eu >= self.lo) & (eu < self.hi)
 
-        def complete_item_degrees(degree):            # users' degrees are complete locally, items' are partial
-            block = degree[Ug:].clone()
-            dist.all_reduce(block, group=group)
-            degree[Ug:] = block
-        self.graph = ops.Graph.from_edges((eu[mine] - self.lo).contiguous(), ei[mine].contiguous(), Ug, self.I,
-                                          degree_hook=complete_item_degrees)
+            def complete_item_degrees(degree):        # users' degrees are complete locally, items' are partial
+                block = degree[Ug:].clone()
+                dist.all_reduce(block, group=group)
+                degree[Ug:] = block
+            graph = ops.Graph.from_edges((eu[mine] - self.lo).contiguous(), ei[mine].contiguous(), Ug, self.I,
+                                         degree_hook=complete_item_degrees)
+        self.graph = graph
         # the same matrix as two row blocks, so that the item rows (whose result must be all-reduced) can be
         # multiplied FIRST and their all-reduce overlapped with the multiplication of the user rows
         g = self.graph
@@ -72,7 +76,13 @@ class ShardedLightGCN:
         N = Ug + self.I
         with torch.cuda.device(self.dev):
             self.E = torch.empty((N, D), dtype=torch.float32, device=self.dev)
-            self.E[:Ug].copy_(init_user[self.lo:self.hi])
+            if init_user is None:                     # N(0, 0.1) like lightgcn.py:52-53; same item replica on every rank
+                gen = torch.Generator(device=self.dev).manual_seed(2023)
+                init_item = torch.randn(self.I, D, device=self.dev, generator=gen) * 0.1
+                gen.manual_seed(2024 + self.rank)
+                self.E[:Ug].copy_(torch.randn(Ug, D, device=self.dev, generator=gen) * 0.1)
+            else:
+                self.E[:Ug].copy_(init_user[self.lo:self.hi])
             self.E[Ug:].copy_(init_item)
             self.m, self.v = torch.zeros_like(self.E), torch.zeros_like(self.E)
             self.O, self.X0, self.X1, self.g = (torch.empty_like(self.E) for _ in range(4))
@@ -167,10 +177,37 @@ class ShardedLightGCN:
 
     def gather_tables(self):
         """(user table [U, D], item table [I, D]) assembled on every rank (tests / checkpoints)."""
-        parts = [torch.empty((user_range(self.U, r, self.world)[1] - user_range(self.U, r, self.world)[0], self.D),
-                             dtype=torch.float32, device=self.dev) for r in range(self.world)]
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+        sizes[self.rank] = self.Ug
+        dist.all_reduce(sizes, group=self.group)
+        parts = [torch.empty((int(n), self.D), dtype=torch.float32, device=self.dev) for n in sizes.tolist()]
         dist.all_gather(parts, self.E[:self.Ug].contiguous(), group=self.group)
         return torch.cat(parts), self.E[self.Ug:].clone()
+
+    def inject(self, fake_rowptr, fake_items, init_user=None, init_item=None):
+        """The attacked model of normal.py:198-206 on the sharded path: a NEW, freshly initialised model
+        over U + F users.  The fake users' rows are appended to the LAST rank's shard (no re-sort); every
+        rank knows the fake rows, adds their item counts to its copy of the global item degrees and
+        re-normalises its values -- no exchange at all.
+        fake_rowptr int64 [F + 1], fake_items int32 (ascending, distinct per row): identical on every rank."""
+        fake_rowptr = torch.as_tensor(fake_rowptr).to(self.dev, torch.int64)
+        fake_items = torch.as_tensor(fake_items).to(self.dev, torch.int32)
+        F = int(fake_rowptr.numel()) - 1
+        delta = torch.bincount(fake_items.long(), minlength=self.I).to(torch.int32)
+        item_degree = self.graph.degree[self.Ug:] + delta
+        last = self.rank == self.world - 1
+        if last:
+            def complete(degree):
+                degree[self.Ug + F:] = item_degree
+            graph = self.graph.append_users(self.Ug, self.I, fake_rowptr, fake_items, degree_hook=complete)
+        else:
+            degree = self.graph.degree.clone()
+            degree[self.Ug:] = item_degree
+            graph = self.graph.renormalized(degree)
+        bounds = (self.lo, self.hi + F) if last else (self.lo, self.hi)
+        return ShardedLightGCN(self.U + F, self.I, None, D=self.D, n_layers=self.L, lam=self.lam, lr=self.lr, batch=self.batch,
+                               device=self.dev, init_user=init_user, init_item=init_item, group=self.group, graph=graph,
+                               bounds=bounds)
 
 
 # ---------------------------------------------------------------------------------------------- bench.py --gpus N

@@ -104,9 +104,10 @@ class Graph:
               "recad_csr_normalize")
         return vals
 
-    def append_users(self, n_users, n_items, fake_rowptr, fake_items):
+    def append_users(self, n_users, n_items, fake_rowptr, fake_items, degree_hook=None):
         """In-place injection (implicit.py:482-494): returns the graph over
-        n_users + F users with the fake rows appended; no sort, no Python dict."""
+        n_users + F users with the fake rows appended; no sort, no Python dict.
+        degree_hook: as in from_edges (a shard completes its item degrees before normalisation)."""
         L = _lib.lib()
         dev = self.device
         F = int(fake_rowptr.numel()) - 1
@@ -125,8 +126,17 @@ class Graph:
                                            _ptr(fake_rowptr), _ptr(fake_items), nf, _ptr(rowptr), _ptr(colidx), _ptr(mult),
                                            _ptr(degree), _ptr(scratch), nbytes, _stream(dev)), "recad_csr_append_users")
             colidx, mult = colidx[:self.nnz + 2 * nf], mult[:self.nnz + 2 * nf]
+            if degree_hook is not None:
+                degree_hook(degree)
             vals = self._normalize(rowptr, colidx, mult, degree, Nn)
         return Graph(Nn, Nn, rowptr, colidx, vals, mult, degree, self.seg_len)
+
+    def renormalized(self, degree):
+        """The same structure with values recomputed from new degrees (a shard whose own rows did not
+        change while fake users elsewhere changed the item degrees)."""
+        with torch.cuda.device(self.device):
+            vals = self._normalize(self.rowptr, self.colidx, self.mult, degree, self.n_rows)
+        return Graph(self.n_rows, self.n_cols, self.rowptr, self.colidx, vals, self.mult, degree, self.seg_len)
 
     @classmethod
     def from_csr(cls, rowptr, colidx, vals, n_cols, seg_len=SEG_LEN):

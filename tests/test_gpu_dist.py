@@ -29,6 +29,18 @@ def _worker(rank, world, port, q):
     losses = [m.train_epoch(samples, perm) for _ in range(2)]
     eu_all, ei_all = m.gather_tables()
     topi, topv, rank_, score = m.full_rank([5], 20)
+    # attacked model: 7 fake users appended to the last shard, fresh tables, one epoch that also samples them
+    F = 7
+    fake = (torch.rand(F, I, generator=g) < 0.03).float() * 5.0          # rating 5 on ~3 % of the items
+    fake[:, 5] = 5.0
+    init_u2, init_i2 = torch.randn(U + F, D, generator=g) * 0.1, torch.randn(I, D, generator=g) * 0.1
+    samples2 = torch.stack([torch.randint(0, U + F, (n,), generator=g), torch.randint(0, I, (n,), generator=g),
+                            torch.randint(0, I, (n,), generator=g)], 1).to(dev)
+    from recad_b200.dataset import ArrayImplicitData
+    frp, fit = ArrayImplicitData.fake_rows(fake.numpy(), 4)
+    m2 = m.inject(frp, fit, init_user=init_u2.to(dev), init_item=init_i2.to(dev))
+    loss2 = m2.train_epoch(samples2, perm)
+    eu2, ei2 = m2.gather_tables()
     if rank == 0:
         # single-GPU run of the same thing
         from recad_b200 import dataset, model
@@ -45,7 +57,17 @@ def _worker(rank, world, port, q):
         rtopi, rtopv, rrank, rscore, _ = ref.full_rank(torch.arange(m.Ug, device=dev), [5], 20, rp, rc)
         ok &= torch.allclose(score, rscore, rtol=1e-4, atol=1e-6)
         ok &= float((rank_ != rrank).float().mean()) < 0.01
-        q.put((bool(ok), losses, ref_losses))
+        data2 = data.inject_data("explicit", fake.numpy(), filter_num=4)
+        assert data2.n_users == U + F
+        ref2 = model.from_config("victim", "lightgcn", latent_dim_rec=D, lightGCN_n_layers=L, device=dev).I(dataset=data2)
+        ref2.embedding_user.weight.data.copy_(init_u2)
+        ref2.embedding_item.weight.data.copy_(init_i2)
+        data2.epoch_samples = lambda device=None: (samples2, perm)
+        ref_loss2 = ref2.train_step()[0]
+        ok2 = np.allclose(loss2, ref_loss2, rtol=1e-5)
+        ok2 &= torch.allclose(eu2, ref2.embedding_user.weight, rtol=1e-4, atol=2e-6)
+        ok2 &= torch.allclose(ei2, ref2.embedding_item.weight, rtol=1e-4, atol=2e-6)
+        q.put((bool(ok) and bool(ok2), losses + [loss2], ref_losses + [ref_loss2]))
     dist.barrier()
     dist.destroy_process_group()
 

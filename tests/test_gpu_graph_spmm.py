@@ -109,6 +109,28 @@ def test_append_users_equals_rebuild(with_edges):
     assert np.array_equal(g2.degree.cpu().numpy(), deg)
 
 
+def test_array_dataset_injection_matches_oracle_graph():
+    """ArrayImplicitData.inject_data (device-resident, the 1M-user path): the fake_array -> rows rule of
+    implicit.py:107-114 (rating > filter_num, trailing empty rows are not users) and the extended graph."""
+    from recad_b200 import dataset
+    U, I = 900, 400
+    u, i = synthetic.make_edges(U, I, 9000, seed=11)
+    dev = torch.device("cuda:0")
+    data = dataset.ArrayImplicitData("t", U, I, (torch.as_tensor(u, device=dev), torch.as_tensor(i, device=dev)), dev, prefetch=False)
+    rng = np.random.default_rng(5)
+    fake = rng.integers(0, 6, size=(12, I)).astype(np.float32)          # ratings 0..5, keep the 5s
+    fake[3] = 0                                                         # an interior user with nothing left
+    fake[10:] = 4                                                       # trailing rows filtered away entirely
+    d2 = data.inject_data("explicit", fake, filter_num=4)
+    assert d2.n_users == U + 10 and d2.n_items == I
+    fr, fc = np.nonzero(fake > 4)
+    ptr, col, val, _, deg = og.norm_adj_csr(np.concatenate([u, fr + U]), np.concatenate([i, fc]), U + 10, I)
+    _assert_same_csr(d2.Graph, ptr, col, val)
+    rp, rc = d2.train_csr()
+    assert rp[-1] == len(u) + len(fr) and rp[U + 4] == rp[U + 3]        # user U + 3 has no positives
+    assert data.n_users == U and data.Graph.n_rows == U + I              # the clean dataset is untouched
+
+
 # ------------------------------------------------------------------ SpMM
 def _rand_graph(U, I, E, seed, seg_len=256):
     u, i = synthetic.make_edges(U, I, E, seed=seed)
