@@ -255,9 +255,74 @@ def run_b200(args, w):
         "gpu_launches": args.steps * (n_batches * (2 * L * (2 if graph.n_mrow else 1) + 2) + 3),
         "clocks": clocks.summary(),
     }
+    if not args.no_gpu_baseline:
+        try:
+            out["gpu_library_baseline"] = torch_gpu_reference(graph, U, I, D, L, B, n_batches, dev)
+        except Exception as e:   # noqa: BLE001 -- informative only, never fail the bench line
+            out["gpu_library_baseline"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        torch.cuda.empty_cache()
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference(w, B, graph, m, data, steps=1)
     return out
+
+
+def torch_gpu_reference(graph, U, I, D, L, B, n_batches, dev):
+    """The reference's own formulation (lightgcn.py:82-172: coalesced COO + torch.sparse.mm + autograd +
+    torch.optim.Adam; evaluation as batched getUsersRating + topk, lightgcn.py:115-120) written with stock
+    torch ops and run on the SAME B200 -- the GPU-library baseline of SURVEY.md 8(d).  Two training steps are
+    timed and extrapolated to the epoch; evaluation is timed on 16384 users and extrapolated."""
+    ev = lambda: torch.cuda.Event(enable_timing=True)     # noqa: E731
+    N = U + I
+    A = graph.to_torch_sparse()
+    gen = torch.Generator(device=dev).manual_seed(0)
+    E = torch.nn.Parameter(torch.randn(N, D, device=dev, generator=gen) * 0.1)
+    opt = torch.optim.Adam([E], lr=1e-3)
+    us, ps, ns = (torch.randint(0, hi, (B,), device=dev, generator=gen) for hi in (U, I, I))
+
+    def computer():
+        X, acc = E, E
+        for _ in range(L):
+            X = torch.sparse.mm(A, X)
+            acc = acc + X
+        return acc / (L + 1)
+
+    def step():
+        O = computer()
+        u, p, q = O[us], O[U + ps], O[U + ns]
+        u0, p0, q0 = E[us], E[U + ps], E[U + ns]
+        loss = torch.nn.functional.softplus((u * q).sum(1) - (u * p).sum(1)).mean() + 1e-4 * 0.5 * (
+            u0.norm(2).pow(2) + p0.norm(2).pow(2) + q0.norm(2).pow(2)) / B
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    step()
+    a, b, c, d = ev(), ev(), ev(), ev()
+    a.record()
+    for _ in range(2):
+        step()
+    b.record()
+    with torch.no_grad():
+        X = E.detach()
+        torch.sparse.mm(A, X)
+        c.record()
+        for _ in range(3):
+            torch.sparse.mm(A, X)
+        d.record()
+        O = computer()
+        ne, chunk = min(16384, U), 4096
+        e0, e1 = ev(), ev()
+        e0.record()
+        for lo in range(0, ne, chunk):
+            torch.topk(O[lo:lo + chunk] @ O[U:].t(), 20)
+        e1.record()
+    torch.cuda.synchronize()
+    step_s, spmm_ms, eval_user = a.elapsed_time(b) / 2e3, c.elapsed_time(d) / 3, e0.elapsed_time(e1) / 1e3 / ne
+    epoch_s, eval_s = step_s * n_batches, eval_user * U
+    return {"value": round(epoch_s + eval_s, 4), "unit": "s", "kind": "port (stock torch ops on the same GPU)",
+            "epoch_s": round(epoch_s, 4), "eval_s": round(eval_s, 4), "step_s": round(step_s, 5), "spmm_ms": round(spmm_ms, 3),
+            "sample": f"2 steps of batch {B} x {n_batches} batches (torch.sparse.mm COO fwd + autograd bwd + torch.optim.Adam); "
+                      f"eval: {ne} users, matmul + topk without train-item masking, x {U} users"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -343,6 +408,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-torch-on-the-same-GPU comparison")
     ap.add_argument("--workload", default="synthetic", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -13,7 +13,15 @@ import torch
 from . import _lib
 from ._lib import RecadError, check
 
-SEG_LEN = 256   # SpMM plan: max stored entries one warp walks (multiple of 32)
+SEG_LEN = None  # SpMM plan: max stored entries one warp walks (multiple of 32); None = by size (auto_seg_len)
+
+
+def auto_seg_len(nnz):
+    """Measured on B200 (profiles/spmm_variant_sweep_r01.jsonl, spmm_sweep_ml1m_r01.jsonl): long segments
+    amortise the per-segment prologue when there are far more segments than resident warps (synthetic,
+    100 M entries: 256 is fastest); an L2-resident graph with ~1 segment per warp slot is latency-bound and
+    wants more, shorter chains (ml1m-shaped, 0.94 M entries: 64 is 25 % faster than 256)."""
+    return 64 if nnz <= 8_000_000 else 256
 
 
 def _ptr(t):
@@ -61,7 +69,7 @@ class Graph:
         self.rowptr, self.colidx, self.vals, self.mult, self.degree = rowptr, colidx, vals, mult, degree
         self.nnz = int(colidx.numel())
         self.device = rowptr.device
-        self.seg_len = seg_len
+        self.seg_len = seg_len or auto_seg_len(self.nnz)
         self._partials = None
         self._plan()
 
