@@ -228,6 +228,13 @@ int recad_mf_forward(const recad_mf* st, const int64_t* users, const int64_t* it
  * recad_lightgcn_train_epoch.  Loss as in the LightGCN epoch. */
 int recad_mf_train_epoch(const recad_mf* st, const int64_t* samples, const int64_t* perm,
                          int64_t n_samples, int64_t batch, int64_t step0, void* stream);
+/* The gradient half of ONE step (mf.py:58-64, forward + backward, no optimiser): g* = d(BCE sum / B_norm)
+ * over the B rows samples[perm[0..B)] (perm NULL: rows 0..B-1), g* zeroed here; loss_acc[0] += BCE sum
+ * (the caller zeroes loss_acc).  For data-parallel training the rows of a batch are split over ranks,
+ * B_norm is the GLOBAL batch size, the caller all-reduces g* and applies recad_adam.  B = 0 is
+ * allowed (zero gradient). */
+int recad_mf_grad(const recad_mf* st, const int64_t* samples, const int64_t* perm, int64_t B, int64_t B_norm,
+                  void* stream);
 
 /* ------------------------------------------------------------------------ *
  * NCF / NeuMF-end pointwise BCE step  (recad/model/victim/ncf.py:32-53, 112-153)
@@ -267,6 +274,9 @@ int recad_ncf_forward(const recad_ncf* st, const int64_t* users, const int64_t* 
 /* One epoch of NCF.train_step (ncf.py:133-153); loss bookkeeping as in the MF epoch. */
 int recad_ncf_train_epoch(const recad_ncf* st, const int64_t* samples, const int64_t* perm,
                           int64_t n_samples, int64_t batch, int64_t step0, void* stream);
+/* The gradient half of ONE step (ncf.py:139-148): as recad_mf_grad, into st->grads (layout of recad_ncf_layout). */
+int recad_ncf_grad(const recad_ncf* st, const int64_t* samples, const int64_t* perm, int64_t B, int64_t B_norm,
+                   void* stream);
 
 /* The tensor-core GEMM of the NCF tower, exposed for testing: C[M, N] = A[M, K] . B[N, K]^T (+ bias[N]) (ReLU) on
  * tcgen05 (kind::tf32, fp32 accumulators in TMEM, TMA operands) with the 3xTF32 operand split, i.e. fp32-accurate.

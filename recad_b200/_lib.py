@@ -79,10 +79,12 @@ SIGNATURES = {
     "recad_dot_scores": (C.c_int, [vp, i64, vp, vp, i64, i32, vp, vp]),
     "recad_mf_forward": (C.c_int, [C.POINTER(MF), vp, vp, i64, vp, vp]),
     "recad_mf_train_epoch": (C.c_int, [C.POINTER(MF), vp, vp, i64, i64, i64, vp]),
+    "recad_mf_grad": (C.c_int, [C.POINTER(MF), vp, vp, i64, i64, vp]),
     "recad_ncf_layout": (C.c_int, [i32, i32, i64, i64, C.POINTER(i64)]),
     "recad_ncf_work_floats": (i64, [i32, i32, i64]),
     "recad_ncf_forward": (C.c_int, [C.POINTER(NCF), vp, vp, i64, vp, vp]),
     "recad_ncf_train_epoch": (C.c_int, [C.POINTER(NCF), vp, vp, i64, i64, i64, vp]),
+    "recad_ncf_grad": (C.c_int, [C.POINTER(NCF), vp, vp, i64, i64, vp]),
     "recad_gemm_tn_tf32x3": (C.c_int, [vp, vp, i32, i32, i32, vp, i32, vp, vp, vp]),
     "recad_transpose_items": (C.c_int, [vp, i64, i32, vp, i64, vp]),
     "recad_fullrank_eval": (C.c_int, [vp, vp, i64, i64, i32, vp, i64, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),

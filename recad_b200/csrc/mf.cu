@@ -15,13 +15,12 @@ __global__ void __launch_bounds__(256)
 mf_kernel(const float* __restrict__ Ue, const float* __restrict__ Ub, const float* __restrict__ Ie,
           const float* __restrict__ Ib, float mean, int64_t n_users, int64_t n_items,
           const int64_t* __restrict__ users, const int64_t* __restrict__ items, const int64_t* __restrict__ samples,
-          const int64_t* __restrict__ perm, int64_t B, int nvec, float* __restrict__ pred, float* __restrict__ gUe, float* __restrict__ gUb,
+          const int64_t* __restrict__ perm, int64_t B, float inv_B, int nvec, float* __restrict__ pred, float* __restrict__ gUe, float* __restrict__ gUb,
           float* __restrict__ gIe, float* __restrict__ gIb, double* __restrict__ loss_acc, int* __restrict__ bad) {
   const int lane = threadIdx.x & 31, l = lane % LPR;
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / LPR;
   const int64_t iters = (B + n_groups - 1) / n_groups;
-  const float inv_B = 1.0f / (float)B;
   const float4* __restrict__ U4 = reinterpret_cast<const float4*>(Ue);
   const float4* __restrict__ I4 = reinterpret_cast<const float4*>(Ie);
   float loss_sum = 0.f;
@@ -94,15 +93,16 @@ mf_kernel(const float* __restrict__ Ue, const float* __restrict__ Ub, const floa
 
 template <bool kTrain>
 static int launch_mf(const recad_mf* st, const int64_t* users, const int64_t* items, const int64_t* samples,
-                     const int64_t* perm, int64_t B, float* pred, cudaStream_t s) {
+                     const int64_t* perm, int64_t B, int64_t B_norm, float* pred, cudaStream_t s) {
   const int nvec = st->D / 4;
+  const float inv_B = 1.0f / (float)B_norm;     // mean over the (global) batch
   int* bad = st->loss_acc ? reinterpret_cast<int*>(st->loss_acc + 3) : nullptr;
 #define RECAD_MF_LAUNCH(LPR, VPL)                                                                              \
   {                                                                                                            \
     const int64_t gpb = 256 / LPR;                                                                             \
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((B + gpb - 1) / gpb, (int64_t)sm_count() * 32)); \
     mf_kernel<LPR, VPL, kTrain><<<grid, 256, 0, s>>>(st->Ue, st->Ub, st->Ie, st->Ib, st->mean, st->n_users,     \
-                                                     st->n_items, users, items, samples, perm, B, nvec, pred, st->gUe, \
+                                                     st->n_items, users, items, samples, perm, B, inv_B, nvec, pred, st->gUe, \
                                                      st->gUb, st->gIe, st->gIb, st->loss_acc, bad);            \
   }
   if (nvec <= 8) RECAD_MF_LAUNCH(8, 1)
@@ -138,7 +138,7 @@ int recad_mf_forward(const recad_mf* st, const int64_t* users, const int64_t* it
   int rc = check_mf(st, false);
   if (rc) return rc;
   RECAD_REQUIRE(users && items && pred && B > 0, RECAD_ERR_ARG, "mf_forward: bad argument");
-  return launch_mf<false>(st, users, items, nullptr, nullptr, B, pred, as_stream(stream));
+  return launch_mf<false>(st, users, items, nullptr, nullptr, B, B, pred, as_stream(stream));
 }
 
 int recad_mf_train_epoch(const recad_mf* st, const int64_t* samples, const int64_t* perm, int64_t n_samples,
@@ -171,7 +171,7 @@ int recad_mf_train_epoch(const recad_mf* st, const int64_t* samples, const int64
     } else {
       for (int k = 0; k < 4; ++k) RECAD_CUDA_CHECK(cudaMemsetAsync(G[k], 0, sz[k] * sizeof(float), s));
     }
-    rc = launch_mf<true>(st, nullptr, nullptr, perm ? samples : samples + 3 * b0, perm ? perm + b0 : nullptr, B, nullptr, s);
+    rc = launch_mf<true>(st, nullptr, nullptr, perm ? samples : samples + 3 * b0, perm ? perm + b0 : nullptr, B, B, nullptr, s);
     if (rc) return rc;
     const AdamScalars a = adam_scalars(st->lr, st->beta1, st->beta2, st->eps, step);
     // fold: epoch_sum += batch_sum / B   (half_lambda = 0: no regulariser in MF)
@@ -188,6 +188,19 @@ int recad_mf_train_epoch(const recad_mf* st, const int64_t* samples, const int64
     }
   }
   return RECAD_OK;
+}
+
+int recad_mf_grad(const recad_mf* st, const int64_t* samples, const int64_t* perm, int64_t B, int64_t B_norm,
+                  void* stream) {
+  int rc = check_mf(st, true);
+  if (rc) return rc;
+  RECAD_REQUIRE(samples && B >= 0 && B_norm >= B && B_norm > 0, RECAD_ERR_ARG, "mf_grad: bad batch");
+  cudaStream_t s = as_stream(stream);
+  const int64_t sz[4] = {st->n_users * st->D, st->n_items * st->D, st->n_users, st->n_items};
+  float* G[4] = {st->gUe, st->gIe, st->gUb, st->gIb};
+  for (int k = 0; k < 4; ++k) RECAD_CUDA_CHECK(cudaMemsetAsync(G[k], 0, sz[k] * sizeof(float), s));
+  if (B == 0) return RECAD_OK;     // a rank may own no row of a short last batch: its gradient is zero
+  return launch_mf<true>(st, nullptr, nullptr, samples, perm, B, B_norm, nullptr, s);
 }
 
 }  // extern "C"

@@ -210,6 +210,67 @@ class ShardedLightGCN:
                                bounds=bounds)
 
 
+def batch_rows(perm, b0, B, rank, world):
+    """This rank's rows of the global batch perm[b0 : b0 + B]: every world-th row starting at `rank`
+    (an even split whatever the user ids are; any split gives the same sum)."""
+    return perm[b0 + rank:b0 + B:world].contiguous()
+
+
+class DataParallelVictim:
+    """Plain data parallelism for the pointwise victims (MF, NCF): every rank holds a full
+    replica (same seed -> same init), takes every world-th row of each global batch, computes its part of
+    the batch gradient with the 1/B of the GLOBAL batch (recad_mf_grad / recad_ncf_grad), the flat gradient
+    is all-reduced over NCCL and every rank applies the same dense Adam step (recad_adam).  Equal to the
+    single-GPU epoch up to fp32 summation order."""
+
+    def __init__(self, victim, group=None):
+        from .victim.mf import MF
+        from .victim.ncf import NCF
+        if not isinstance(victim, (MF, NCF)):
+            raise TypeError("DataParallelVictim wraps an instantiated recad_b200 MF or NCF victim")
+        victim._require_instance("DataParallelVictim")
+        self.victim, self.group = victim, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._grad = _lib.lib().recad_mf_grad if isinstance(victim, MF) else _lib.lib().recad_ncf_grad
+        self._name = "recad_mf_grad" if isinstance(victim, MF) else "recad_ncf_grad"
+        # replicas must start identical: rank 0's tables win (a no-op when every rank used the same seed)
+        dist.broadcast(victim.flat, 0, group=group)
+        self.n_allreduce = 0
+
+    def train_epoch(self, samples, perm=None, batch=None):
+        """One epoch over the GLOBAL (samples [n, 3] int64 = user, item, label; perm [n]) on the device;
+        returns the mean batch loss (mf.py:49-69 / ncf.py:131-153)."""
+        v = self.victim
+        dev = v._dev
+        n = int(samples.shape[0])
+        if perm is None:
+            perm = torch.arange(n, device=dev)
+        B = int(batch or (v.dataset.config["pointwise_batch_size"] if hasattr(v.dataset, "config") else 1024))
+        n_batches = (n + B - 1) // B
+        parts = torch.zeros(n_batches, dtype=torch.float64, device=dev)
+        cfg = v.config
+        with torch.cuda.device(dev):
+            v.loss_acc.zero_()
+            for b in range(n_batches):
+                b0 = b * B
+                Bg = min(B, n - b0)
+                rows = batch_rows(perm, b0, Bg, self.rank, self.world)
+                v.loss_acc[0:1].zero_()                 # [3] keeps the out-of-range flag of the whole epoch
+                _lib.check(self._grad(C.byref(v._st), v._vp(samples), v._vp(rows) if rows.numel() else None, int(rows.numel()), Bg,
+                                      ops._stream(dev)), self._name)
+                parts[b] = v.loss_acc[0] / Bg
+                dist.all_reduce(v.g, group=self.group)
+                self.n_allreduce += 1
+                v._steps += 1
+                ops.adam(v.flat, v.g, v.m, v.v, v._steps, lr=cfg["lr"])
+            bad = v.loss_acc[3:4].view(torch.int64).clone()
+            dist.all_reduce(parts, group=self.group)
+            dist.all_reduce(bad, group=self.group)
+        if int(bad.item()):
+            raise ops.RecadError("DataParallelVictim.train_epoch: a sample id is out of range")
+        return float(parts.mean().item())
+
+
 # ---------------------------------------------------------------------------------------------- bench.py --gpus N
 def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, peaks):
     import time

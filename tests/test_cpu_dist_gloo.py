@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from recad_b200.dist import route_epoch, user_range
+from recad_b200.dist import batch_rows, route_epoch, user_range
 
 
 def _worker(rank, world, port, U, I, n, batch, out):
@@ -48,6 +48,19 @@ def _worker(rank, world, port, U, I, n, batch, out):
     assert torch.allclose(sp_local, ref, rtol=1e-12)
     out.put((rank, lo, hi, int(local.shape[0])))
     dist.destroy_process_group()
+
+
+def test_batch_rows_partition_every_global_batch():
+    """Data-parallel MF / NCF: the ranks' row sets of a batch are disjoint, balanced and cover it (so the
+    all-reduced gradient sums every row exactly once); a short last batch may leave a rank empty."""
+    perm = torch.randperm(1000, generator=torch.Generator().manual_seed(0))
+    for B, world in ((256, 2), (256, 8), (3, 8), (1000, 3)):
+        for b0 in range(0, 1000, B):
+            Bg = min(B, 1000 - b0)
+            parts = [batch_rows(perm, b0, Bg, r, world) for r in range(world)]
+            assert sorted(torch.cat(parts).tolist()) == sorted(perm[b0:b0 + Bg].tolist())
+            sizes = [p.numel() for p in parts]
+            assert max(sizes) - min(sizes) <= 1 and all(p.is_contiguous() for p in parts)
 
 
 def test_user_range_is_a_balanced_partition():

@@ -72,17 +72,67 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_sharded_epoch_matches_single_gpu():
+def _dp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from recad_b200 import dataset, dist as rdist, model, synthetic
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    U, I, B, n = 1500, 700, 1000, 7300                                   # last batch: 300 rows
+    u, i = synthetic.make_edges(U, I, 20_000, seed=4)
+    data = dataset.ArrayImplicitData("t", U, I, (torch.as_tensor(u, device=dev), torch.as_tensor(i, device=dev)), dev,
+                                     sample="pointwise", batch_size=B, need_graph=False, prefetch=False)
+    g = torch.Generator().manual_seed(2)
+    samples = torch.stack([torch.randint(0, U, (n,), generator=g), torch.randint(0, I, (n,), generator=g),
+                           torch.randint(0, 2, (n,), generator=g)], 1).to(dev)
+    perm = torch.randperm(n, generator=g).to(dev)
+    results = {}
+    for name, kw in (("mf", dict(embedding_size=32)), ("ncf", dict(factor_num=8, num_layers=3, tower_precision="fp32"))):
+        torch.manual_seed(11)
+        v = model.from_config("victim", name, device=dev, **kw).I(dataset=data)
+        dp = rdist.DataParallelVictim(v)
+        losses = [dp.train_epoch(samples, perm, batch=B) for _ in range(2)]
+        if rank == 0:
+            torch.manual_seed(11)
+            ref = model.from_config("victim", name, device=dev, **kw).I(dataset=data)
+            data.epoch_samples = lambda device=None: (samples, perm)
+            ref_losses = [ref.train_step()[0] for _ in range(2)]
+            close = bool(torch.allclose(v.flat, ref.flat, rtol=1e-4, atol=2e-6))
+            results[name] = (losses, ref_losses, close, float((v.flat - ref.flat).abs().max()), v._steps == ref._steps)
+    if rank == 0:
+        q.put(results)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _spawn(worker, world=2):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(timeout=600)
         assert p.exitcode == 0
-    ok, losses, ref_losses = q.get()
+    return q.get()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_data_parallel_mf_ncf_match_single_gpu():
+    """MF / NCF with the rows of every batch split over 2 GPUs and the flat gradient all-reduced: same
+    epoch losses and tables as one GPU up to fp32 summation order (NCF with the exact fp32 tower so that no
+    ReLU mask can flip)."""
+    results = _spawn(_dp_worker)
+    for name, (losses, ref_losses, close, max_abs, same_steps) in results.items():
+        assert np.allclose(losses, ref_losses, rtol=1e-5), (name, losses, ref_losses)
+        assert close, (name, max_abs)
+        assert same_steps
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_sharded_epoch_matches_single_gpu():
+    ok, losses, ref_losses = _spawn(_worker)
     assert ok, (losses, ref_losses)
