@@ -133,6 +133,19 @@ int recad_spmm_plan(const int64_t* rowptr, int64_t n_rows, int32_t seg_len, int3
 int recad_spmm(const recad_csr* A, const float* X, float* Y, const float* C, float* Z,
                float alpha, int32_t D, void* stream);
 
+/* Sharded path: Y = A X where row i is not stored locally but written, as soon as it is
+ * finished, to dst[i / slice_rows] + (i % slice_rows) * D.  dst[r] [host array of n_dst <= 16 device pointers]
+ * is rank r's staging block for THIS sender, mapped into this process over NVLink (torch symmetric memory):
+ * the partial item rows of lightgcn.py:99-108 travel to their owner inside the SpMM epilogue instead of
+ * through a separate all-reduce.  D in {32, 64, 128}. */
+int recad_spmm_scatter(const recad_csr* A, const float* X, float* const* dst, int32_t n_dst,
+                       int64_t slice_rows, int32_t D, void* stream);
+/* The owner's half of that exchange: out[r][e] = sum over s < n_src of stage[s * src_stride + e], e < n_floats,
+ * for every r < n_out (<= 16): partial rows summed in rank order (identical bits on every replica) and stored
+ * directly into each peer's table.  The caller brackets it with cross-device barriers. */
+int recad_peer_reduce_bcast(const float* stage, int32_t n_src, int64_t src_stride, int64_t n_floats,
+                            float* const* out, int32_t n_out, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * LightGCN BPR step  (recad/model/victim/lightgcn.py:122-172)
  * ------------------------------------------------------------------------ */

@@ -27,12 +27,26 @@ struct RowLanes {
   static constexpr int NPL = 32 / LPR;   // neighbour rows per warp-wide load
 };
 
-template <int D>
+// Peer-memory epilogue of the sharded path (recad_spmm_scatter): row i of the product is not stored in a local
+// Y but sent to the rank that OWNS item i -- dst[i / slice] is that rank's staging block for this sender, mapped
+// into this process over NVLink (torch symmetric memory), so the partial sums travel while the SpMM still runs.
+constexpr int kMaxPeers = 16;
+struct RowScatter {
+  float* dst[kMaxPeers];
+  int32_t slice;
+};
+
+template <int D, bool kScatter = false>
 __device__ __forceinline__ void spmm_epilogue(int64_t row, int slot, int l, float4 y, float* Y, const float* C,
-                                              float* Z, float alpha, float* partials) {  // Z may alias C
+                                              float* Z, float alpha, float* partials, const RowScatter* sc = nullptr) {  // Z may alias C
   constexpr int LPR = D / 4;
   if (slot >= 0) {
     reinterpret_cast<float4*>(partials)[(int64_t)slot * LPR + l] = y;
+    return;
+  }
+  if (kScatter) {
+    const int owner = (int)(row / sc->slice);
+    reinterpret_cast<float4*>(sc->dst[owner])[(row - (int64_t)owner * sc->slice) * LPR + l] = y;
     return;
   }
   const int64_t o = row * LPR + l;
@@ -49,12 +63,13 @@ __device__ __forceinline__ void spmm_epilogue(int64_t row, int slot, int l, floa
   }
 }
 
-template <int D, int UNR, int MINB, bool kStreamX>
+template <int D, int UNR, int MINB, bool kStreamX, bool kScatter = false>
 __global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
 spmm_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float* __restrict__ vals,
                 int64_t n_seg, int32_t seg_len, const int32_t* __restrict__ seg_row,
                 const int64_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_slot,
-                const float* __restrict__ X, float* Y, const float* C, float* Z, float alpha, float* partials) {
+                const float* __restrict__ X, float* Y, const float* C, float* Z, float alpha, float* partials,
+                const __grid_constant__ RowScatter sc) {
   constexpr int LPR = RowLanes<D>::LPR, NPL = RowLanes<D>::NPL;
   static_assert(32 % (NPL * UNR) == 0, "unroll must divide the staged chunk");
   const int lane = threadIdx.x & 31;
@@ -121,15 +136,16 @@ spmm_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
     acc.z += __shfl_xor_sync(kFull, acc.z, o);
     acc.w += __shfl_xor_sync(kFull, acc.w, o);
   }
-  if (sub == 0) spmm_epilogue<D>(row, slot, l, acc, Y, C, Z, alpha, partials);
+  if (sub == 0) spmm_epilogue<D, kScatter>(row, slot, l, acc, Y, C, Z, alpha, partials, &sc);
   }
 }
 
 // rows with more than one segment: sum their partial slots in slot order, then the same epilogue
-template <int D>
+template <int D, bool kScatter = false>
 __global__ void __launch_bounds__(kSpmmWarps * 32)
 spmm_fixup_kernel(int64_t n_mrow, const int32_t* __restrict__ mrow, const int32_t* __restrict__ mrow_lo,
-                  const float* __restrict__ partials, float* Y, const float* C, float* Z, float alpha) {
+                  const float* __restrict__ partials, float* Y, const float* C, float* Z, float alpha,
+                  const __grid_constant__ RowScatter sc) {
   constexpr int LPR = RowLanes<D>::LPR, NPL = RowLanes<D>::NPL;
   const int64_t j = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5);
   if (j >= n_mrow) return;
@@ -161,7 +177,7 @@ spmm_fixup_kernel(int64_t n_mrow, const int32_t* __restrict__ mrow, const int32_
     acc.z += __shfl_xor_sync(kFull, acc.z, o);
     acc.w += __shfl_xor_sync(kFull, acc.w, o);
   }
-  if (sub == 0) spmm_epilogue<D>(mrow[j], -1, l, acc, Y, C, Z, alpha, nullptr);
+  if (sub == 0) spmm_epilogue<D, kScatter>(mrow[j], -1, l, acc, Y, C, Z, alpha, nullptr, &sc);
 }
 
 // any D that is a multiple of 4 (<= 1024): a lane owns float4 columns lane, lane+32, ...
@@ -255,10 +271,10 @@ static int spmm_variant() {
   return v;
 }
 
-template <int D, int UNR, int MINB, bool kStreamX>
+template <int D, int UNR, int MINB, bool kStreamX, bool kScatter = false>
 static int launch_spmm_v(const recad_csr* A, const float* X, float* Y, const float* C, float* Z, float alpha,
-                         bool persistent, cudaStream_t s) {
-  auto kern = spmm_seg_kernel<D, UNR, MINB, kStreamX>;
+                         bool persistent, cudaStream_t s, const RowScatter& sc = RowScatter{}) {
+  auto kern = spmm_seg_kernel<D, UNR, MINB, kStreamX, kScatter>;
   int64_t grid = (A->n_seg + kSpmmWarps - 1) / kSpmmWarps;
   if (persistent) {
     static int per_sm = 0;
@@ -266,8 +282,22 @@ static int launch_spmm_v(const recad_csr* A, const float* X, float* Y, const flo
     grid = std::min<int64_t>(grid, (int64_t)sm_count() * std::max(per_sm, 1));
   }
   kern<<<(unsigned)grid, kSpmmWarps * 32, 0, s>>>(A->rowptr, A->colidx, A->vals, A->n_seg, A->seg_len, A->seg_row,
-                                                 A->seg_lo, A->seg_slot, X, Y, C, Z, alpha, A->partials);
+                                                 A->seg_lo, A->seg_slot, X, Y, C, Z, alpha, A->partials, sc);
   RECAD_LAUNCH_CHECK();
+  return RECAD_OK;
+}
+
+// Y = A X with every finished row sent to its owner (see RowScatter)
+template <int D, int UNR>
+static int launch_spmm_scatter(const recad_csr* A, const float* X, const RowScatter& sc, cudaStream_t s) {
+  int rc = launch_spmm_v<D, UNR, 5, false, true>(A, X, nullptr, nullptr, nullptr, 1.f, true, s, sc);
+  if (rc) return rc;
+  if (A->n_mrow > 0) {
+    const unsigned g2 = (unsigned)((A->n_mrow + kSpmmWarps - 1) / kSpmmWarps);
+    spmm_fixup_kernel<D, true><<<g2, kSpmmWarps * 32, 0, s>>>(A->n_mrow, A->mrow, A->mrow_lo, A->partials, nullptr, nullptr,
+                                                             nullptr, 1.f, sc);
+    RECAD_LAUNCH_CHECK();
+  }
   return RECAD_OK;
 }
 
@@ -286,7 +316,7 @@ static int launch_spmm(const recad_csr* A, const float* X, float* Y, const float
   if (rc) return rc;
   if (A->n_mrow > 0) {
     const unsigned g2 = (unsigned)((A->n_mrow + kSpmmWarps - 1) / kSpmmWarps);
-    spmm_fixup_kernel<D><<<g2, kSpmmWarps * 32, 0, s>>>(A->n_mrow, A->mrow, A->mrow_lo, A->partials, Y, C, Z, alpha);
+    spmm_fixup_kernel<D><<<g2, kSpmmWarps * 32, 0, s>>>(A->n_mrow, A->mrow, A->mrow_lo, A->partials, Y, C, Z, alpha, RowScatter{});
     RECAD_LAUNCH_CHECK();
   }
   return RECAD_OK;
@@ -326,5 +356,77 @@ extern "C" int recad_spmm(const recad_csr* A, const float* X, float* Y, const fl
                                                             alpha, D);
     RECAD_LAUNCH_CHECK();
   }
+  return RECAD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- peer-memory path
+namespace recad {
+
+struct PeerOut {
+  float* out[kMaxPeers];
+};
+
+// out[r][e] = sum_s stage[s * stride + e] for every peer r: the owner adds the partial rows its peers sent (fixed
+// rank order => every replica receives the same bits) and stores the sum straight into each peer's table
+__global__ void __launch_bounds__(256)
+peer_reduce_bcast_kernel(const float4* __restrict__ stage, int n_src, int64_t stride4, int64_t n4, const __grid_constant__ PeerOut po,
+                         int n_out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = stage[e];
+    for (int s = 1; s < n_src; ++s) {
+      const float4 p = stage[s * stride4 + e];
+      a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    }
+    for (int r = 0; r < n_out; ++r) reinterpret_cast<float4*>(po.out[r])[e] = a;
+  }
+}
+
+}  // namespace recad
+
+extern "C" int recad_spmm_scatter(const recad_csr* A, const float* X, float* const* dst, int32_t n_dst, int64_t slice_rows,
+                                  int32_t D, void* stream) {
+  cudaStream_t s = as_stream(stream);
+  RECAD_REQUIRE(A && X && dst, RECAD_ERR_ARG, "spmm_scatter: null argument");
+  RECAD_REQUIRE(A->n_rows > 0 && A->n_seg >= A->n_rows && A->rowptr && A->seg_row && A->seg_lo && A->seg_slot,
+                RECAD_ERR_ARG, "spmm_scatter: matrix has no plan (call recad_spmm_plan)");
+  RECAD_REQUIRE(A->n_mrow == 0 || (A->mrow && A->mrow_lo && A->partials), RECAD_ERR_ARG, "spmm_scatter: null multi-row plan");
+  RECAD_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers && slice_rows > 0 && slice_rows < ((int64_t)1 << 31) &&
+                    slice_rows * n_dst >= A->n_rows,
+                RECAD_ERR_ARG, "spmm_scatter: %d destinations of %lld rows do not cover %lld rows", n_dst,
+                (long long)slice_rows, (long long)A->n_rows);
+  RowScatter sc{};
+  sc.slice = (int32_t)slice_rows;
+  for (int r = 0; r < n_dst; ++r) {
+    RECAD_REQUIRE(dst[r] && ((uintptr_t)dst[r] & 15) == 0, RECAD_ERR_ARG, "spmm_scatter: destination %d null or misaligned", r);
+    sc.dst[r] = dst[r];
+  }
+  RECAD_REQUIRE((((uintptr_t)X | (uintptr_t)A->partials) & 15) == 0, RECAD_ERR_ARG, "spmm_scatter: buffers must be 16-byte aligned");
+  switch (D) {
+    case 32: return launch_spmm_scatter<32, 2>(A, X, sc, s);
+    case 64: return launch_spmm_scatter<64, 4>(A, X, sc, s);
+    case 128: return launch_spmm_scatter<128, 8>(A, X, sc, s);
+    default: break;
+  }
+  RECAD_REQUIRE(false, RECAD_ERR_UNSUPPORTED, "spmm_scatter: D = %d (supported: 32, 64, 128)", D);
+  return RECAD_OK;
+}
+
+extern "C" int recad_peer_reduce_bcast(const float* stage, int32_t n_src, int64_t src_stride, int64_t n_floats,
+                                       float* const* out, int32_t n_out, void* stream) {
+  RECAD_REQUIRE(stage && out && n_src >= 1 && n_out >= 1 && n_out <= kMaxPeers && n_floats >= 0 && src_stride >= n_floats,
+                RECAD_ERR_ARG, "peer_reduce_bcast: bad argument");
+  RECAD_REQUIRE(n_floats % 4 == 0 && src_stride % 4 == 0 && ((uintptr_t)stage & 15) == 0, RECAD_ERR_ARG,
+                "peer_reduce_bcast: sizes must be multiples of 4 floats, 16-byte aligned");
+  if (n_floats == 0) return RECAD_OK;
+  PeerOut po{};
+  for (int r = 0; r < n_out; ++r) {
+    RECAD_REQUIRE(out[r] && ((uintptr_t)out[r] & 15) == 0, RECAD_ERR_ARG, "peer_reduce_bcast: output %d null or misaligned", r);
+    po.out[r] = out[r];
+  }
+  const int64_t n4 = n_floats / 4;
+  const unsigned grid = (unsigned)std::min<int64_t>((n4 + 255) / 256, (int64_t)sm_count() * 8);
+  peer_reduce_bcast_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(stage), n_src, src_stride / 4, n4, po,
+                                                                n_out);
+  RECAD_LAUNCH_CHECK();
   return RECAD_OK;
 }

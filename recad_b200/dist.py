@@ -43,9 +43,60 @@ def route_epoch(samples, perm, batch, lo, hi):
     return local, ptr
 
 
+class _PeerExchange:
+    """Peer-memory plumbing of the fused exchange: NVLink-mapped buffers from torch symmetric memory and the
+    pointer tables the two kernels take.  Per rank: a staging block [world, slice, D] (slot s receives rank s's
+    partial rows of the items this rank owns, slice = ceil(I / world)) and the layer buffers X0 / X1, whose
+    item blocks every owner writes its reduced slice into."""
+
+    def __init__(self, Ug, I, D, dev, group):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 16:
+            raise ops.RecadError("fused exchange supports at most 16 ranks")
+        ugs = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        ugs[self.rank] = Ug
+        dist.all_reduce(ugs, group=group)
+        self.Ugs = [int(x) for x in ugs.tolist()]
+        self.I, self.D, self.dev = I, D, dev
+        self.slice = (I + self.world - 1) // self.world
+        self.rows_mine = max(0, min(self.slice, I - self.rank * self.slice))
+        n_max = max(self.Ugs) + I
+        self.stage = symm.empty((self.world, self.slice, D), dtype=torch.float32, device=dev)
+        self.h_stage = symm.rendezvous(self.stage, self.group)
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm.empty((n_max, D), dtype=torch.float32, device=dev)
+            self.handles.append(symm.rendezvous(t, self.group))
+            self.bufs.append(t)
+        fb = 4 * D                                   # bytes per row
+        # where MY partial rows for owner o go: slot `rank` of o's staging block
+        self._dst = (C.c_void_p * self.world)(*[int(p) + self.rank * self.slice * fb for p in self.h_stage.buffer_ptrs])
+        # where MY reduced slice goes in peer r's layer buffer k: its item block starts after ITS users
+        self._out = [(C.c_void_p * self.world)(*[int(p) + (self.Ugs[r] + self.rank * self.slice) * fb
+                                                 for r, p in enumerate(h.buffer_ptrs)]) for h in self.handles]
+
+    def barrier(self):
+        self.h_stage.barrier(channel=0)
+
+    def scatter_item_rows(self, g_item, x_users):
+        """partial item rows R_g^T x_users -> the owners' staging blocks, from inside the SpMM epilogue"""
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().recad_spmm_scatter(C.byref(g_item.struct(self.D)), x_users.data_ptr(), self._dst, self.world,
+                                                     self.slice, self.D, ops._stream(self.dev)), "recad_spmm_scatter")
+
+    def reduce_bcast(self, k):
+        """sum the world partial copies of my slice (rank order) and store the result into every rank's buffer k"""
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().recad_peer_reduce_bcast(self.stage.data_ptr(), self.world, self.slice * self.D,
+                                                          self.rows_mine * self.D, self._out[k], self.world,
+                                                          ops._stream(self.dev)), "recad_peer_reduce_bcast")
+
+
 class ShardedLightGCN:
     def __init__(self, n_users, n_items, edges, D=64, n_layers=3, lam=1e-4, lr=1e-3, batch=1024, device=None,
-                 init_user=None, init_item=None, group=None, graph=None, bounds=None):
+                 init_user=None, init_item=None, group=None, graph=None, bounds=None, fused=None):
         """edges: (users, items) int64 CUDA tensors of the GLOBAL edge list (every rank passes the same), or
         None with `graph` = this rank's prebuilt local matrix and `bounds` = its user range (inject())."""
         self.group = group
@@ -85,12 +136,39 @@ class ShardedLightGCN:
                 self.E[:Ug].copy_(init_user[self.lo:self.hi])
             self.E[Ug:].copy_(init_item)
             self.m, self.v = torch.zeros_like(self.E), torch.zeros_like(self.E)
-            self.O, self.X0, self.X1, self.g = (torch.empty_like(self.E) for _ in range(4))
+            self.O, self.g = torch.empty_like(self.E), torch.empty_like(self.E)
+            self.peer = self._make_peer(fused)
+            if self.peer is not None:                 # layer buffers live in NVLink-mapped memory
+                self.X0, self.X1 = self.peer.bufs[0][:N], self.peer.bufs[1][:N]
+            else:
+                self.X0, self.X1 = torch.empty_like(self.E), torch.empty_like(self.E)
             self.cnt = torch.empty(N, dtype=torch.float32, device=self.dev)
             self.loss_acc = torch.zeros(4, dtype=torch.float64, device=self.dev)
         self.steps = 0
         self._O_valid = False
         self.n_allreduce = 0
+        self.n_fused = 0
+
+    def _make_peer(self, fused):
+        """fused=None: use the peer-memory exchange when every rank can set it up (RECAD_DIST_FUSED=0 disables);
+        True: require it; False: NCCL all-reduce."""
+        import os
+        if fused is None and os.environ.get("RECAD_DIST_FUSED", "1") == "0":
+            fused = False
+        if fused is False or self.world == 1 or self.D not in (32, 64, 128):
+            return None
+        peer, err = None, None
+        try:
+            peer = _PeerExchange(self.Ug, self.I, self.D, self.dev, self.group)
+        except Exception as e:   # noqa: BLE001 -- no symmetric memory on this system
+            err = e
+        ok = torch.tensor([0 if peer is None else 1], device=self.dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            if fused:
+                raise ops.RecadError(f"fused exchange requested but symmetric memory is unavailable: {err}")
+            return None
+        return peer
 
     # ------------------------------------------------------------------ pieces
     def _allreduce_items(self, t):
@@ -100,6 +178,18 @@ class ShardedLightGCN:
     def _spmm_exchange(self, x, y):
         """y = A_g x with the item block of y summed over ranks."""
         Ug = self.Ug
+        if self.peer is not None:
+            # ONE pass: the item-row SpMM sends every finished partial row to its owner over NVLink from its epilogue;
+            # while that traffic drains the user rows are multiplied; then the owners add the partials (rank order)
+            # and store their slice into every replica.  Two device-side barriers, no NCCL, no extra pass over y.
+            k = 0 if y.data_ptr() == self.X0.data_ptr() else 1
+            self.peer.scatter_item_rows(self.g_item, x[:Ug])
+            ops.spmm(self.g_user, x[Ug:], y[:Ug])
+            self.peer.barrier()
+            self.peer.reduce_bcast(k)
+            self.peer.barrier()
+            self.n_fused += 1
+            return
         if not self.overlap:
             ops.spmm(self.graph, x, y)
             self._allreduce_items(y)
@@ -207,7 +297,7 @@ class ShardedLightGCN:
         bounds = (self.lo, self.hi + F) if last else (self.lo, self.hi)
         return ShardedLightGCN(self.U + F, self.I, None, D=self.D, n_layers=self.L, lam=self.lam, lr=self.lr, batch=self.batch,
                                device=self.dev, init_user=init_user, init_item=init_item, group=self.group, graph=graph,
-                               bounds=bounds)
+                               bounds=bounds, fused=self.peer is not None)
 
 
 def batch_rows(perm, b0, B, rank, world):
@@ -361,8 +451,13 @@ def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, 
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: LightGCN {U} users x {I} items x {w['n_edges']} interactions, D={D}, L={L}, "
                                f"BPR batch {B} ({n_batches} batches/epoch, {n} samples), full-rank eval of all {U} users K=20",
-                   "l2": "inputs exceed L2", "parallelism": f"user rows sharded over {world} GPUs; per layer one NCCL all-reduce of the "
-                                                            f"item block [{I} x {D}] fp32; {m.n_allreduce // max(1, args.steps + args.warmup)} all-reduces per epoch"},
+                   "l2": "inputs exceed L2",
+                   "parallelism": (f"user rows sharded over {world} GPUs; per layer the partial item rows [{I} x {D}] fp32 go to their "
+                                   f"owner from the SpMM epilogue over NVLink peer memory, owners reduce and store into every replica "
+                                   f"({m.n_fused // max(1, args.steps + args.warmup + 2)} fused exchanges per epoch); gradient block by NCCL "
+                                   f"({m.n_allreduce // max(1, args.steps + args.warmup + 2)} all-reduces per epoch)") if m.peer is not None else
+                                  (f"user rows sharded over {world} GPUs; per layer one NCCL all-reduce of the item block [{I} x {D}] fp32; "
+                                   f"{m.n_allreduce // max(1, args.steps + args.warmup + 2)} all-reduces per epoch")},
         "epoch_loss": loss, "HR@20(target 0)": hr, "graph_build_s": round(t_graph, 4), "host_sampler_s": round(t_sampler, 3),
         "roofline": {"bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None,
                      "note": "per-kernel roofline is reported by the 1-GPU run; this line is the sharded whole-step time"},

@@ -25,10 +25,16 @@ def _worker(rank, world, port, q):
     samples = torch.stack([torch.randint(0, U, (n,), generator=g), torch.randint(0, I, (n,), generator=g),
                            torch.randint(0, I, (n,), generator=g)], 1).to(dev)
     perm = torch.randperm(n, generator=g).to(dev)
-    m = rdist.ShardedLightGCN(U, I, (eu, ei), D=D, n_layers=L, batch=B, device=dev, init_user=init_u.to(dev), init_item=init_i.to(dev))
-    losses = [m.train_epoch(samples, perm) for _ in range(2)]
-    eu_all, ei_all = m.gather_tables()
-    topi, topv, rank_, score = m.full_rank([5], 20)
+    runs = {}
+    for fused in (False, True):       # NCCL all-reduce of the item block / partial rows sent to their owner from the SpMM epilogue
+        m = rdist.ShardedLightGCN(U, I, (eu, ei), D=D, n_layers=L, batch=B, device=dev, init_user=init_u.to(dev),
+                                  init_item=init_i.to(dev), fused=fused)
+        assert (m.peer is not None) == fused
+        losses = [m.train_epoch(samples, perm) for _ in range(2)]
+        eu_all, ei_all = m.gather_tables()
+        topi, topv, rank_, score = m.full_rank([5], 20)
+        assert (m.n_fused > 0) == fused
+        runs[fused] = (losses, eu_all, ei_all, rank_, score)
     # attacked model: 7 fake users appended to the last shard, fresh tables, one epoch that also samples them
     F = 7
     fake = (torch.rand(F, I, generator=g) < 0.03).float() * 5.0          # rating 5 on ~3 % of the items
@@ -50,13 +56,15 @@ def _worker(rank, world, port, q):
         ref.embedding_item.weight.data.copy_(init_i)
         data.epoch_samples = lambda device=None: (samples, perm)
         ref_losses = [ref.train_step()[0] for _ in range(2)]
-        ok = np.allclose(losses, ref_losses, rtol=1e-5)
-        ok &= torch.allclose(eu_all, ref.embedding_user.weight, rtol=1e-4, atol=2e-6)
-        ok &= torch.allclose(ei_all, ref.embedding_item.weight, rtol=1e-4, atol=2e-6)
         rp, rc = data.train_csr(dev)
         rtopi, rtopv, rrank, rscore, _ = ref.full_rank(torch.arange(m.Ug, device=dev), [5], 20, rp, rc)
-        ok &= torch.allclose(score, rscore, rtol=1e-4, atol=1e-6)
-        ok &= float((rank_ != rrank).float().mean()) < 0.01
+        ok = True
+        for fused, (losses, eu_all, ei_all, rank_, score) in runs.items():
+            ok &= np.allclose(losses, ref_losses, rtol=1e-5)
+            ok &= torch.allclose(eu_all, ref.embedding_user.weight, rtol=1e-4, atol=2e-6)
+            ok &= torch.allclose(ei_all, ref.embedding_item.weight, rtol=1e-4, atol=2e-6)
+            ok &= torch.allclose(score, rscore, rtol=1e-4, atol=1e-6)
+            ok &= float((rank_ != rrank).float().mean()) < 0.01
         data2 = data.inject_data("explicit", fake.numpy(), filter_num=4)
         assert data2.n_users == U + F
         ref2 = model.from_config("victim", "lightgcn", latent_dim_rec=D, lightGCN_n_layers=L, device=dev).I(dataset=data2)
