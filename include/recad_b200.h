@@ -142,9 +142,11 @@ int recad_spmm_scatter(const recad_csr* A, const float* X, float* const* dst, in
                        int64_t slice_rows, int32_t D, void* stream);
 /* The owner's half of that exchange: out[r][e] = sum over s < n_src of stage[s * src_stride + e], e < n_floats,
  * for every r < n_out (<= 16): partial rows summed in rank order (identical bits on every replica) and stored
- * directly into each peer's table.  The caller brackets it with cross-device barriers. */
+ * directly into each peer's table.  multicast != 0: n_out == 1 and out[0] is an NVSwitch multicast address
+ * (same offset in every rank's buffer): one multimem.st per element instead of n_out peer stores.
+ * The caller brackets it with cross-device barriers. */
 int recad_peer_reduce_bcast(const float* stage, int32_t n_src, int64_t src_stride, int64_t n_floats,
-                            float* const* out, int32_t n_out, void* stream);
+                            float* const* out, int32_t n_out, int32_t multicast, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * LightGCN BPR step  (recad/model/victim/lightgcn.py:122-172)

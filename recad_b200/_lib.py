@@ -72,7 +72,7 @@ SIGNATURES = {
     "recad_spmm_plan": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, C.POINTER(i64), vp, i64, vp]),
     "recad_spmm": (C.c_int, [C.POINTER(CSR), vp, vp, vp, vp, f32, i32, vp]),
     "recad_spmm_scatter": (C.c_int, [C.POINTER(CSR), vp, C.POINTER(vp), i32, i64, i32, vp]),
-    "recad_peer_reduce_bcast": (C.c_int, [vp, i32, i64, i64, C.POINTER(vp), i32, vp]),
+    "recad_peer_reduce_bcast": (C.c_int, [vp, i32, i64, i64, C.POINTER(vp), i32, i32, vp]),
     "recad_bpr_fwd_bwd": (C.c_int, [vp, vp, i64, i64, vp, vp, i64, i64, f32, vp, vp, vp, i32, vp]),
     "recad_axpby": (C.c_int, [vp, f32, vp, f32, vp, i64, vp]),
     "recad_adam": (C.c_int, [vp, vp, vp, f32, vp, vp, i64, i32, f32, f32, f32, f32, i64, vp]),

@@ -368,16 +368,25 @@ struct PeerOut {
 
 // out[r][e] = sum_s stage[s * stride + e] for every peer r: the owner adds the partial rows its peers sent (fixed
 // rank order => every replica receives the same bits) and stores the sum straight into each peer's table
+// kMulticast: out[0] is an NVSwitch multicast address -- ONE multimem.st is replicated into every rank's buffer by
+// the switch instead of world separate peer stores
+template <bool kMulticast>
 __global__ void __launch_bounds__(256)
-peer_reduce_bcast_kernel(const float4* __restrict__ stage, int n_src, int64_t stride4, int64_t n4, const __grid_constant__ PeerOut po,
+peer_reduce_bcast_kernel(const float4* stage, int n_src, int64_t stride4, int64_t n4, const __grid_constant__ PeerOut po,
                          int n_out) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
-    float4 a = stage[e];
+    float4 a = __ldcg(stage + e);                 // written by peers over NVLink: read at L2, never through L1 / nc
     for (int s = 1; s < n_src; ++s) {
-      const float4 p = stage[s * stride4 + e];
+      const float4 p = __ldcg(stage + s * stride4 + e);
       a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
     }
-    for (int r = 0; r < n_out; ++r) reinterpret_cast<float4*>(po.out[r])[e] = a;
+    if (kMulticast) {
+      asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(reinterpret_cast<float4*>(po.out[0]) + e),
+                   "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w)
+                   : "memory");
+    } else {
+      for (int r = 0; r < n_out; ++r) reinterpret_cast<float4*>(po.out[r])[e] = a;
+    }
   }
 }
 
@@ -412,7 +421,7 @@ extern "C" int recad_spmm_scatter(const recad_csr* A, const float* X, float* con
 }
 
 extern "C" int recad_peer_reduce_bcast(const float* stage, int32_t n_src, int64_t src_stride, int64_t n_floats,
-                                       float* const* out, int32_t n_out, void* stream) {
+                                       float* const* out, int32_t n_out, int32_t multicast, void* stream) {
   RECAD_REQUIRE(stage && out && n_src >= 1 && n_out >= 1 && n_out <= kMaxPeers && n_floats >= 0 && src_stride >= n_floats,
                 RECAD_ERR_ARG, "peer_reduce_bcast: bad argument");
   RECAD_REQUIRE(n_floats % 4 == 0 && src_stride % 4 == 0 && ((uintptr_t)stage & 15) == 0, RECAD_ERR_ARG,
@@ -425,8 +434,13 @@ extern "C" int recad_peer_reduce_bcast(const float* stage, int32_t n_src, int64_
   }
   const int64_t n4 = n_floats / 4;
   const unsigned grid = (unsigned)std::min<int64_t>((n4 + 255) / 256, (int64_t)sm_count() * 8);
-  peer_reduce_bcast_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(stage), n_src, src_stride / 4, n4, po,
-                                                                n_out);
+  RECAD_REQUIRE(!multicast || n_out == 1, RECAD_ERR_ARG, "peer_reduce_bcast: a multicast store has ONE output address");
+  if (multicast)
+    peer_reduce_bcast_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(stage), n_src, src_stride / 4,
+                                                                        n4, po, n_out);
+  else
+    peer_reduce_bcast_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(stage), n_src, src_stride / 4,
+                                                                         n4, po, n_out);
   RECAD_LAUNCH_CHECK();
   return RECAD_OK;
 }

@@ -76,6 +76,12 @@ class _PeerExchange:
         # where MY reduced slice goes in peer r's layer buffer k: its item block starts after ITS users
         self._out = [(C.c_void_p * self.world)(*[int(p) + (self.Ugs[r] + self.rank * self.slice) * fb
                                                  for r, p in enumerate(h.buffer_ptrs)]) for h in self.handles]
+        # NVSwitch multicast (one store lands in every replica): needs the item block at the SAME offset on every rank
+        import os
+        mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.handles]
+        self.multicast = (len(set(self.Ugs)) == 1 and all(mc) and os.environ.get("RECAD_DIST_MULTICAST", "1") != "0")
+        if self.multicast:
+            self._mc_out = [(C.c_void_p * 1)(p + (Ug + self.rank * self.slice) * fb) for p in mc]
 
     def barrier(self):
         self.h_stage.barrier(channel=0)
@@ -89,8 +95,9 @@ class _PeerExchange:
     def reduce_bcast(self, k):
         """sum the world partial copies of my slice (rank order) and store the result into every rank's buffer k"""
         with torch.cuda.device(self.dev):
+            out, n_out = (self._mc_out[k], 1) if self.multicast else (self._out[k], self.world)
             _lib.check(_lib.lib().recad_peer_reduce_bcast(self.stage.data_ptr(), self.world, self.slice * self.D,
-                                                          self.rows_mine * self.D, self._out[k], self.world,
+                                                          self.rows_mine * self.D, out, n_out, int(self.multicast),
                                                           ops._stream(self.dev)), "recad_peer_reduce_bcast")
 
 

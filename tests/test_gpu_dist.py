@@ -35,6 +35,20 @@ def _worker(rank, world, port, q):
         topi, topv, rank_, score = m.full_rank([5], 20)
         assert (m.n_fused > 0) == fused
         runs[fused] = (losses, eu_all, ei_all, rank_, score)
+    # equal shards (3000 users / 2): the owner's slice is stored with ONE NVSwitch multicast store when the box has NVLS
+    U2 = 3000
+    keep = eu < U2
+    s3 = samples.clone()
+    s3[:, 0] %= U2
+    mc = {}
+    for fused in (False, True):
+        m3 = rdist.ShardedLightGCN(U2, I, (eu[keep], ei[keep]), D=D, n_layers=L, batch=B, device=dev,
+                                   init_user=init_u[:U2].to(dev), init_item=init_i.to(dev), fused=fused)
+        l3 = m3.train_epoch(s3, perm)
+        mc[fused] = (l3, *m3.gather_tables(), bool(m3.peer.multicast) if fused else None)
+    ok_mc = bool(np.isclose(mc[True][0], mc[False][0], rtol=1e-5)) and all(
+        torch.allclose(a, b, rtol=1e-4, atol=2e-6) for a, b in zip(mc[True][1:3], mc[False][1:3]))
+    used_multicast = mc[True][3]
     # attacked model: 7 fake users appended to the last shard, fresh tables, one epoch that also samples them
     F = 7
     fake = (torch.rand(F, I, generator=g) < 0.03).float() * 5.0          # rating 5 on ~3 % of the items
@@ -75,7 +89,7 @@ def _worker(rank, world, port, q):
         ok2 = np.allclose(loss2, ref_loss2, rtol=1e-5)
         ok2 &= torch.allclose(eu2, ref2.embedding_user.weight, rtol=1e-4, atol=2e-6)
         ok2 &= torch.allclose(ei2, ref2.embedding_item.weight, rtol=1e-4, atol=2e-6)
-        q.put((bool(ok) and bool(ok2), losses + [loss2], ref_losses + [ref_loss2]))
+        q.put((bool(ok) and bool(ok2) and ok_mc, losses + [loss2, ("multicast", used_multicast, ok_mc)], ref_losses + [ref_loss2]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -143,4 +157,5 @@ def test_data_parallel_mf_ncf_match_single_gpu():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_sharded_epoch_matches_single_gpu():
     ok, losses, ref_losses = _spawn(_worker)
+    print("sharded run:", losses[-1])
     assert ok, (losses, ref_losses)
