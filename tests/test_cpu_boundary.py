@@ -184,3 +184,15 @@ def test_fast_filter_sampler_is_bit_identical_to_the_plain_one():
         assert np.array_equal(ops.mt_pairwise(U, I, 3000, ptr, idx), ref)
     finally:
         ops.FAST_SAMPLER_MIN = old
+
+
+def test_workflow_registry_mirrors_reference():
+    """recad/workflow/__init__.py:4-7: both workflows, the required user arguments raise a TypeError when missing."""
+    import pytest
+    from recad_b200 import config, workflow
+    assert set(workflow.factories) == {"no defense", "defense"}
+    assert config.WORKFLOW["defense"]["defense_epoch"] == 1 and config.WORKFLOW["no defense"]["topks"] == [10, 20, 50, 100]
+    with pytest.raises(TypeError):
+        workflow.from_config("defense", victim_data=None, attack_data=None, victim=None, attacker=None)
+    with pytest.raises(TypeError):
+        workflow.from_config("no defense", victim_data=None)

@@ -265,3 +265,76 @@ def test_whole_workflow_matches_reference(victim, kw, sample):
     assert wf.fake_dataset.n_users == data.n_users + 50
     if not rng_ok:
         pytest.skip("torch CPU generator stream differs on this host: attacked-model columns not compared")
+
+
+# ------------------------------------------------------------------ defense workflow (defense.py:175-303)
+class FixtureDefender:
+    """Stands in for the reference's PCASelectUsers (out of scope, CUDA-only in the reference): the fixed answer the
+    golden run used."""
+    model_name = "fixture_defender"
+
+    def __init__(self, flagged):
+        self.flagged = [int(u) for u in flagged]
+
+    def I(self, **kw):
+        return self
+
+    def to(self, device):
+        return self
+
+    def input_describe(self):
+        return {"defense_step": {}}
+
+    def defense_step(self, **kw):
+        return list(self.flagged)
+
+
+class ReplayAttacker(FixtureAttacker):
+    def generate_fake(self, **kw):      # the defense workflow re-seeds after the attack: no generator state to restore
+        z = self.z
+        fake = np.zeros(tuple(z["fake_shape"]), dtype=float)
+        fake[z["fake_rows"], z["fake_cols"]] = z["fake_vals"]
+        return fake
+
+
+def test_defense_workflow_matches_reference():
+    """attack -> re-seed -> retrain -> evaluate -> delete flagged users -> re-seed -> retrain -> evaluate, against the
+    two tables the live reference printed (tests/golden/make_golden_defense.py)."""
+    import json
+    import os
+    from recad_b200 import dataset, model, workflow
+    z = util.load("workflow_defense_mf_dev.npz")
+    with open(os.path.join(os.path.dirname(__file__), "golden", "meta_defense.json")) as f:
+        gold = json.load(f)
+    tr, va, te = util.dicts("dev")
+    data = dataset.from_config("implicit", "dev", train_dict=tr, valid_dict=va, test_dict=te, need_graph=False,
+                               sample="pointwise", device=torch.device(DEV))
+    assert data.n_users == gold["n_users"]
+    torch.manual_seed(2023)
+    wf = workflow.from_config("defense", victim_data=data, attack_data=None, defense_data=data,
+                              victim=model.from_config("victim", "mf", device=torch.device(DEV), **gold["victim_kwargs"]),
+                              attacker=ReplayAttacker(z), defender=FixtureDefender(z["flagged"]), rec_epoch=gold["rec_epoch"],
+                              attack_epoch=1, device=torch.device(DEV), verbose=False)
+    init = {k[len("init__"):]: z[k] for k in z.files if k.startswith("init__")}
+    sd = wf.victim.state_dict()
+    rng_ok = all(np.array_equal(sd[k].cpu().numpy(), v) for k, v in init.items() if k in sd)
+    for k, v in init.items():
+        if k in sd:
+            sd[k].copy_(torch.as_tensor(v))
+    np.random.set_state(("MT19937", z["np_key_start"], int(z["np_pos_start"]), 0, 0.0))
+    res2 = wf.execute()
+    assert wf.fake_dataset.n_users == data.n_users + 50
+    assert wf.cleaned_dataset.n_users == gold["cleaned_n_users"] and wf.cleaned_dataset.traindataSize == gold["cleaned_train_size"]
+    assert len(wf.flagged_users) == 35
+    n_eval = 310
+    for got, want in ((wf.results, gold["table_after_attack"]), (res2, gold["table_after_defense"])):
+        for k, v in want.items():
+            if "after attack" in k or k == "pred_shift":
+                if not rng_ok:
+                    continue
+                tol = dict(rtol=1e-2, atol=2e-6) if k == "pred_shift" else dict(rtol=2e-3, atol=1.5 / n_eval)
+                assert np.isclose(got[k], v, **tol), (k, got[k], v)
+            else:
+                assert np.isclose(got[k], v, rtol=1e-4, atol=1.0 / n_eval), (k, got[k], v)
+    if not rng_ok:
+        pytest.skip("torch CPU generator stream differs on this host: attacked-model columns not compared")
