@@ -369,9 +369,11 @@ int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t
                            int64_t train_size, const int64_t* allpos_rowptr,
                            const int32_t* allpos_col, int64_t* out, int64_t* n_out);
 /* Same result and same stream consumption as recad_mt19937_pairwise, built for 10^7..10^8 samples: the sequential
- * stream parse reads only the row pointer and a per-user 1024-bit membership filter (filter [host] uint64[n_users * 16],
- * filled once per dataset by recad_pairwise_filter_build; no false negatives, a "maybe" falls back to the exact
- * search), and the positive items are gathered afterwards on n_threads host threads. */
+ * stream parse normally reads ONE 64-byte line per sample (filter [host] uint64[n_users * 16]: word 0 = the user's
+ * row start | row length << 40, words 1..7 = 448 filter bits, words 8..15 = 512 more bits consulted only when the
+ * first probe hits; filled once per dataset by recad_pairwise_filter_build; no false negatives, a "maybe" falls
+ * back to the exact search; ext [host] uint32[nnz] = second-level filter of users with more than 96 positives),
+ * and the positive items are gathered afterwards on n_threads host threads. */
 int recad_host_advise_huge(void* ptr, int64_t bytes);   /* madvise(MADV_HUGEPAGE) on an untouched host buffer; best effort */
 int recad_pairwise_filter_build(const int64_t* allpos_rowptr, const int32_t* allpos_col, int64_t n_users,
                                 uint64_t* filter, uint32_t* ext, int32_t n_threads);

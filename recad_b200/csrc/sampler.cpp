@@ -24,42 +24,95 @@ namespace recad { void set_error(const char* fmt, ...); }
 
 namespace {
 
+// numpy's legacy generator, state-compatible (key[624] + pos).  The 624 outputs of a twist are tempered in one
+// vectorisable pass into `buf`, so that next() -- called 2-3 times per sample by the sequential stream parsers --
+// is a load and an increment.
+#if defined(__x86_64__) && defined(__GNUC__)
+#define RECAD_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define RECAD_CLONES
+#endif
+
+RECAD_CLONES
+static void mt_refill(uint32_t* __restrict__ key, uint32_t* __restrict__ buf) {
+  constexpr int N = 624, M = 397;
+  constexpr uint32_t UP = 0x80000000u, LOW = 0x7fffffffu, MAG = 0x9908b0dfu;
+  // key[k + 1] is read before any lane overwrites it and key[k + M] / key[k + M - N] are at least 227 apart
+#pragma GCC ivdep
+  for (int k = 0; k < N - M; ++k) {
+    const uint32_t y = (key[k] & UP) | (key[k + 1] & LOW);
+    key[k] = key[k + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & MAG);
+  }
+#pragma GCC ivdep
+  for (int k = N - M; k < N - 1; ++k) {
+    const uint32_t y = (key[k] & UP) | (key[k + 1] & LOW);
+    key[k] = key[k + (M - N)] ^ (y >> 1) ^ ((0u - (y & 1u)) & MAG);
+  }
+  const uint32_t y = (key[N - 1] & UP) | (key[0] & LOW);
+  key[N - 1] = key[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & MAG);
+  for (int k = 0; k < N; ++k) {
+    uint32_t t = key[k];
+    t ^= t >> 11;
+    t ^= (t << 7) & 0x9d2c5680u;
+    t ^= (t << 15) & 0xefc60000u;
+    t ^= t >> 18;
+    buf[k] = t;
+  }
+}
+
+RECAD_CLONES
+static void mt_temper_only(const uint32_t* __restrict__ key, uint32_t* __restrict__ buf) {
+  for (int k = 0; k < 624; ++k) {
+    uint32_t t = key[k];
+    t ^= t >> 11;
+    t ^= (t << 7) & 0x9d2c5680u;
+    t ^= (t << 15) & 0xefc60000u;
+    t ^= t >> 18;
+    buf[k] = t;
+  }
+}
+
 struct MT {
   uint32_t* key;
   int pos;
-  void twist() {
-    constexpr int N = 624, M = 397;
-    constexpr uint32_t UP = 0x80000000u, LOW = 0x7fffffffu, MAG = 0x9908b0dfu;
-    int k = 0;
-    for (; k < N - M; ++k) {
-      uint32_t y = (key[k] & UP) | (key[k + 1] & LOW);
-      key[k] = key[k + M] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
-    }
-    for (; k < N - 1; ++k) {
-      uint32_t y = (key[k] & UP) | (key[k + 1] & LOW);
-      key[k] = key[k + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
-    }
-    uint32_t y = (key[N - 1] & UP) | (key[0] & LOW);
-    key[N - 1] = key[M - 1] ^ (y >> 1) ^ ((y & 1u) ? MAG : 0u);
-    pos = 0;
-  }
+  alignas(64) uint32_t buf[624];
+  MT(uint32_t* k, int p) : key(k), pos(p) { mt_temper_only(key, buf); }   // outputs pos..623 of the current block
   inline uint32_t next() {
-    if (pos >= 624) twist();
-    uint32_t y = key[pos++];
-    y ^= y >> 11;
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= y >> 18;
-    return y;
+    if (__builtin_expect(pos >= 624, 0)) { mt_refill(key, buf); pos = 0; }
+    return buf[pos++];
+  }
+  static inline uint32_t mask_of(uint64_t r) {
+    uint64_t mask = r;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    return (uint32_t)mask;
   }
   inline uint64_t masked(uint64_t r) {
     if (r == 0) return 0;
-    uint64_t mask = r;
-    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    const uint32_t mask = mask_of(r);
     uint32_t v;
-    do { v = next() & (uint32_t)mask; } while (v > r);
+    do { v = next() & mask; } while (v > r);
     return v;
   }
+};
+
+// growable host scratch, huge-page advised, never zero-filled
+template <typename T>
+struct Scratch {
+  T* p = nullptr;
+  int64_t cap = 0;
+  T* get(int64_t n) {
+    if (n > cap) {
+      free(p);
+      cap = std::max<int64_t>(n, 1);
+      const size_t bytes = (((size_t)cap * sizeof(T)) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+      void* q = nullptr;
+      if (posix_memalign(&q, (size_t)2 << 20, bytes) != 0) { p = nullptr; cap = 0; return nullptr; }
+      madvise(q, bytes, MADV_HUGEPAGE);
+      p = static_cast<T*>(q);
+    }
+    return p;
+  }
+  ~Scratch() { free(p); }
 };
 
 }  // namespace
@@ -73,7 +126,7 @@ int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t
     recad::set_error("mt19937_pairwise: bad argument");
     return RECAD_ERR_ARG;
   }
-  MT mt{key, *pos};
+  MT mt(key, *pos);
   // np.random.randint(0, n_users, train_size): ONE vector call, all users drawn first (implicit.py:57)
   int64_t* users = new int64_t[train_size > 0 ? train_size : 1];
   for (int64_t k = 0; k < train_size; ++k) users[k] = (int64_t)mt.masked((uint64_t)n_users - 1);
@@ -119,9 +172,26 @@ int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t
 // recorded as an index during the parse; the gather of the items -- the other random access -- runs afterwards on
 // all host threads.
 // ---------------------------------------------------------------------------------------------------------
-static inline void filter_bits(uint32_t item, uint32_t& a, uint32_t& b) {
-  a = (item * 0x9E3779B1u) >> 22;  // two 10-bit positions in the user's 1024-bit block
-  b = (item * 0x85EBCA77u) >> 22;
+// Two 64-byte lines per user, of which a sample normally touches only the FIRST:
+//   line 0: word 0 = first entry of the user's row | row length << 40, words 1..7 = 448 filter bits (region A)
+//   line 1: 512 filter bits (region B)
+// Users with at most kLight positives keep all three probes of an item in region A.  For heavier users probe 1
+// is in region A and probes 2, 3 in region B, so a negative candidate whose first probe misses (80-90 % of them)
+// is accepted from line 0 alone.  The parse is bound by the cache misses it can keep in flight (about ten line-fill
+// buffers per core), hence everything a sample needs -- row bounds and the decisive filter bits -- sits in one line.
+constexpr int kFilterWords = 16;
+constexpr uint32_t kBitsA = 448, kBitsB = 512;
+constexpr int64_t kLight = 32;
+static inline uint32_t probe_a(uint32_t item) { return 64u + (uint32_t)(((uint64_t)(item * 0x9E3779B1u) * kBitsA) >> 32); }
+static inline void probes_bc(uint32_t item, bool light, uint32_t& b, uint32_t& c) {
+  const uint32_t hb = item * 0x85EBCA77u, hc = item * 0xC2B2AE3Du;
+  if (light) {
+    b = 64u + (uint32_t)(((uint64_t)hb * kBitsA) >> 32);
+    c = 64u + (uint32_t)(((uint64_t)hc * kBitsA) >> 32);
+  } else {
+    b = 512u + (hb >> 23);      // 9 bits: region B
+    c = 512u + (hc >> 23);
+  }
 }
 
 static void parallel_for(int64_t n, int n_threads, const std::function<void(int64_t, int64_t)>& fn) {
@@ -160,16 +230,29 @@ int recad_pairwise_filter_build(const int64_t* allpos_rowptr, const int32_t* all
     recad::set_error("pairwise_filter_build: bad argument");
     return RECAD_ERR_ARG;
   }
+  if (allpos_rowptr[n_users] >= ((int64_t)1 << 40)) {
+    recad::set_error("pairwise_filter_build: more than 2^40 interactions");
+    return RECAD_ERR_UNSUPPORTED;
+  }
+  for (int64_t u = 0; u < n_users; ++u)
+    if (allpos_rowptr[u + 1] - allpos_rowptr[u] >= ((int64_t)1 << 24)) {
+      recad::set_error("pairwise_filter_build: user %lld has 2^24 or more interactions", (long long)u);
+      return RECAD_ERR_UNSUPPORTED;
+    }
   parallel_for(n_users, n_threads, [&](int64_t lo, int64_t hi) {
     for (int64_t u = lo; u < hi; ++u) {
-      uint64_t* f = filter + u * 16;
-      for (int q = 0; q < 16; ++q) f[q] = 0;
+      uint64_t* f = filter + u * kFilterWords;
+      for (int q = 0; q < kFilterWords; ++q) f[q] = 0;
       const int64_t a0 = allpos_rowptr[u], a1 = allpos_rowptr[u + 1];
+      f[0] = (uint64_t)a0 | ((uint64_t)(a1 - a0) << 40);
+      const bool light = a1 - a0 <= kLight;
       for (int64_t e = a0; e < a1; ++e) {
-        uint32_t a, b;
-        filter_bits((uint32_t)allpos_col[e], a, b);
+        const uint32_t item = (uint32_t)allpos_col[e], a = probe_a(item);
+        uint32_t b, c;
+        probes_bc(item, light, b, c);
         f[a >> 6] |= 1ull << (a & 63);
         f[b >> 6] |= 1ull << (b & 63);
+        f[c >> 6] |= 1ull << (c & 63);
       }
       for (int64_t e = a0; e < a1; ++e) ext[e] = 0;
       if (a1 - a0 > kHeavy) {
@@ -193,7 +276,7 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
     recad::set_error("mt19937_pairwise_fast: bad argument");
     return RECAD_ERR_ARG;
   }
-  MT mt{key, *pos};
+  MT mt(key, *pos);
   const bool trace = getenv("RECAD_SAMPLER_TRACE") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -202,53 +285,81 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
     fprintf(stderr, "[sampler] %s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
     t0 = t1;
   };
-  std::vector<int64_t> users((size_t)std::max<int64_t>(train_size, 1));
-  for (int64_t k = 0; k < train_size; ++k) users[k] = (int64_t)mt.masked((uint64_t)n_users - 1);
+  // scratch of the sequential part, kept between calls (one sampler thread at a time per process): 32-bit users and
+  // compact (user, index of the positive, negative) triples -- the 64-bit rows of `out` are written by the parallel
+  // pass below, so the sequential thread moves 16 instead of 32 bytes per sample
+  static thread_local Scratch<uint32_t> users_buf;
+  static thread_local Scratch<uint32_t> neg_buf;
+  static thread_local Scratch<int64_t> pidx_buf;
+  uint32_t* users = users_buf.get(train_size);
+  uint32_t* negs = neg_buf.get(train_size);
+  int64_t* pidxs = pidx_buf.get(train_size);
+  if (!users || !negs || !pidxs) {
+    recad::set_error("mt19937_pairwise_fast: out of host memory");
+    return RECAD_ERR_ARG;
+  }
+  {
+    const uint32_t r = (uint32_t)(n_users - 1), mask = MT::mask_of(r);
+    if (r == 0) {
+      memset(users, 0, (size_t)train_size * sizeof(uint32_t));
+    } else {
+      for (int64_t k = 0; k < train_size; ++k) {
+        uint32_t v;
+        do { v = mt.next() & mask; } while (v > r);
+        users[k] = v;
+      }
+    }
+  }
   lap("draw users");
-  // the parse writes (user, INDEX of the positive in allpos_col, negative) into `out`; the index is resolved below
-  constexpr int64_t kAheadPtr = 32, kAheadFilter = 16;
+  constexpr int64_t kAhead = 24, kAhead2 = 12;
+  const uint32_t neg_r = (uint32_t)(n_items - 1), neg_mask = MT::mask_of(neg_r);
   int64_t w = 0;
   for (int64_t k = 0; k < train_size; ++k) {
-    if (k + kAheadPtr < train_size) __builtin_prefetch(allpos_rowptr + users[k + kAheadPtr]);
-    if (k + kAheadFilter < train_size) {
-      const uint64_t* f = filter + users[k + kAheadFilter] * 16;
-      __builtin_prefetch(f);
-      __builtin_prefetch(f + 8);
+    if (k + kAhead < train_size) __builtin_prefetch(filter + (int64_t)users[k + kAhead] * kFilterWords);
+    if (k + kAhead2 < train_size) {      // second stage: line 0 of that user has arrived; fetch line 1 if it will be consulted
+      const uint64_t* f2 = filter + (int64_t)users[k + kAhead2] * kFilterWords;
+      if ((int64_t)(f2[0] >> 40) > kLight) __builtin_prefetch(f2 + 8);
     }
     const int64_t u = users[k];
-    const int64_t lo = allpos_rowptr[u], hi = allpos_rowptr[u + 1];
-    if (hi == lo) continue;
-    if (hi - lo >= n_items) {
+    const uint64_t* f = filter + u * kFilterWords;
+    const int64_t lo = (int64_t)(f[0] & (((uint64_t)1 << 40) - 1)), len = (int64_t)(f[0] >> 40);
+    if (len == 0) continue;
+    if (len >= n_items) {
       recad::set_error("mt19937_pairwise_fast: user %lld interacted with every item; negative sampling cannot terminate",
                        (long long)u);
       return RECAD_ERR_ARG;
     }
-    const int64_t pidx = lo + (int64_t)mt.masked((uint64_t)(hi - lo) - 1);
-    const uint64_t* f = filter + u * 16;
-    int64_t neg;
+    const int64_t pidx = lo + (int64_t)mt.masked((uint64_t)len - 1);
+    uint32_t neg;
     for (;;) {
-      neg = (int64_t)mt.masked((uint64_t)n_items - 1);
-      uint32_t a, b;
-      filter_bits((uint32_t)neg, a, b);
-      if (!((f[a >> 6] >> (a & 63)) & (f[b >> 6] >> (b & 63)) & 1ull)) break;                 // definitely not a positive
-      if (hi - lo > kHeavy) {                                                                  // heavy user: second level
-        const uint64_t nbits = (uint64_t)(hi - lo) * 32;
-        const uint64_t p0 = ext_probe((uint32_t)neg, 0, nbits), p1 = ext_probe((uint32_t)neg, 1, nbits),
-                       p2 = ext_probe((uint32_t)neg, 2, nbits);
+      if (neg_r == 0) neg = 0;
+      else do { neg = mt.next() & neg_mask; } while (neg > neg_r);
+      const uint32_t a = probe_a(neg);
+      if (!((f[a >> 6] >> (a & 63)) & 1ull)) break;                                            // definitely not a positive
+      uint32_t b, c;
+      probes_bc(neg, len <= kLight, b, c);
+      if (!((f[b >> 6] >> (b & 63)) & (f[c >> 6] >> (c & 63)) & 1ull)) break;
+      if (len > kHeavy) {                                                                      // heavy user: second level
+        const uint64_t nbits = (uint64_t)len * 32;
+        const uint64_t p0 = ext_probe(neg, 0, nbits), p1 = ext_probe(neg, 1, nbits), p2 = ext_probe(neg, 2, nbits);
         if (!((ext[lo + (p0 >> 5)] >> (p0 & 31)) & (ext[lo + (p1 >> 5)] >> (p1 & 31)) & (ext[lo + (p2 >> 5)] >> (p2 & 31)) & 1u))
           break;
       }
-      if (!std::binary_search(allpos_col + lo, allpos_col + hi, (int32_t)neg)) break;          // filter false positive
+      if (!std::binary_search(allpos_col + lo, allpos_col + lo + len, (int32_t)neg)) break;    // filter false positive
     }
-    out[3 * w] = u; out[3 * w + 1] = pidx; out[3 * w + 2] = neg;
+    users[w] = (uint32_t)u;      // w <= k: compaction in place (users without positives are dropped, implicit.py:63-64)
+    pidxs[w] = pidx;
+    negs[w] = neg;
     ++w;
   }
   lap("parse stream");
   parallel_for(w, n_threads, [&](int64_t a, int64_t b) {
     constexpr int64_t kAhead = 16;
     for (int64_t k = a; k < b; ++k) {
-      if (k + kAhead < b) __builtin_prefetch(allpos_col + out[3 * (k + kAhead) + 1]);
-      out[3 * k + 1] = allpos_col[out[3 * k + 1]];
+      if (k + kAhead < b) __builtin_prefetch(allpos_col + pidxs[k + kAhead]);
+      out[3 * k] = users[k];
+      out[3 * k + 1] = allpos_col[pidxs[k]];
+      out[3 * k + 2] = negs[k];
     }
   });
   lap("gather positives");
@@ -264,7 +375,7 @@ int recad_mt19937_pointwise(uint32_t* key, int32_t* pos, int64_t n_dict_users, c
     recad::set_error("mt19937_pointwise: bad argument");
     return RECAD_ERR_ARG;
   }
-  MT mt{key, *pos};
+  MT mt(key, *pos);
   int64_t w = 0;
   for (int64_t k = 0; k < n_dict_users; ++k) {
     const int64_t lo = pos_rowptr[k], hi = pos_rowptr[k + 1], n = hi - lo, uid = user_ids[k];
@@ -307,7 +418,7 @@ int recad_mt19937_permutation(uint32_t* key, int32_t* pos, int64_t n, int64_t* p
     recad::set_error("mt19937_permutation: bad argument");
     return RECAD_ERR_ARG;
   }
-  MT mt{key, *pos};
+  MT mt(key, *pos);
   for (int64_t i = 0; i < n; ++i) perm[i] = i;
   // j = random_interval(i) depends on i only, not on the data: draw kAhead swaps ahead (same stream
   // order) and prefetch perm[j], which is otherwise one DRAM miss per element

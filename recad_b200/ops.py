@@ -416,7 +416,7 @@ _filters = {}                   # id(allpos_col array) -> (weakref-free cache ke
 
 
 def pairwise_filter(allpos_rowptr, allpos_col, n_users):
-    """Per-user 1024-bit membership filters for mt_pairwise_raw(fast); built once per positives array."""
+    """Per-user 128-byte blocks (row bounds + two-level membership filter, first line decisive) for mt_pairwise_raw(fast); built once per positives array."""
     key = (allpos_col.ctypes.data, len(allpos_col), int(n_users))
     if key not in _filters:
         _filters.clear()
