@@ -392,6 +392,12 @@ int recad_mt19937_pointwise(uint32_t* key, int32_t* pos, int64_t n_dict_users, c
                             const int64_t* pos_sorted, int64_t n_items, int32_t ratio, int64_t* out);
 /* np.random.shuffle(np.arange(n)) (implicit.py:24-25): perm [host] int64[n]. */
 int recad_mt19937_permutation(uint32_t* key, int32_t* pos, int64_t n, int64_t* perm);
+/* The same shuffle in two halves (identical result and stream consumption): _draw is the only part that
+ * consumes the stream (j_out [host] uint32[n], j_out[i] = random_interval(i) for i = n-1 .. 1), _apply turns
+ * the draws into the permutation without touching the generator -- so the caller can start drawing the next
+ * epoch while another thread applies the swaps of this one. */
+int recad_mt19937_permutation_draw(uint32_t* key, int32_t* pos, int64_t n, uint32_t* j_out);
+int recad_permutation_apply(int64_t n, const uint32_t* j, int64_t* perm);
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,8 @@ SIGNATURES = {
     "recad_mt19937_pairwise_fast": (C.c_int, [vp, C.POINTER(i32), i64, i64, i64, vp, vp, vp, vp, i32, vp, C.POINTER(i64)]),
     "recad_mt19937_pointwise": (C.c_int, [vp, C.POINTER(i32), i64, vp, vp, vp, vp, i64, i32, vp]),
     "recad_mt19937_permutation": (C.c_int, [vp, C.POINTER(i32), i64, vp]),
+    "recad_mt19937_permutation_draw": (C.c_int, [vp, C.POINTER(i32), i64, vp]),
+    "recad_permutation_apply": (C.c_int, [i64, vp, vp]),
 }
 
 _lib = None

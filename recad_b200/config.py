@@ -51,6 +51,8 @@ def implicit_defaults(name):
         #                interactions (implicit.py:233-235 overwrite quirk);
         #   "train":     the intended semantics (train interactions).
         "graph_edges": "reference",
+        # NEW: draw the next epochs' samples on background threads while the GPU trains (None = for large datasets)
+        "prefetch": None,
     }
 
 

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <chrono>
 #include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -285,12 +286,15 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
     fprintf(stderr, "[sampler] %s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
     t0 = t1;
   };
-  // scratch of the sequential part, kept between calls (one sampler thread at a time per process): 32-bit users and
-  // compact (user, index of the positive, negative) triples -- the 64-bit rows of `out` are written by the parallel
-  // pass below, so the sequential thread moves 16 instead of 32 bytes per sample
-  static thread_local Scratch<uint32_t> users_buf;
-  static thread_local Scratch<uint32_t> neg_buf;
-  static thread_local Scratch<int64_t> pidx_buf;
+  // scratch of the sequential part, kept between calls (callers are serialised: the epochs of one stream cannot be
+  // drawn concurrently anyway): 32-bit users and compact (user, index of the positive, negative) triples -- the
+  // 64-bit rows of `out` are written by the parallel pass below, so the sequential thread moves 16 instead of 32
+  // bytes per sample
+  static std::mutex scratch_mutex;
+  static Scratch<uint32_t> users_buf;
+  static Scratch<uint32_t> neg_buf;
+  static Scratch<int64_t> pidx_buf;
+  std::lock_guard<std::mutex> scratch_lock(scratch_mutex);
   uint32_t* users = users_buf.get(train_size);
   uint32_t* negs = neg_buf.get(train_size);
   int64_t* pidxs = pidx_buf.get(train_size);
@@ -440,6 +444,35 @@ int recad_mt19937_permutation(uint32_t* key, int32_t* pos, int64_t n, int64_t* p
     std::swap(perm[i], perm[j]);
   }
   *pos = mt.pos;
+  return RECAD_OK;
+}
+
+// The shuffle in two halves, so that the sequential stream can move on to the next epoch while another thread
+// applies the swaps: draw = the data-independent part (j_i = random_interval(i) for i = n-1 .. 1, the ONLY part that
+// consumes the stream), apply = the memory-bound part (perm = arange(n); swap(perm[i], perm[j_i]) in the same order).
+int recad_mt19937_permutation_draw(uint32_t* key, int32_t* pos, int64_t n, uint32_t* j_out) {
+  if (!key || !pos || !j_out || n < 0 || n > 0xffffffffLL) {
+    recad::set_error("mt19937_permutation_draw: bad argument");
+    return RECAD_ERR_ARG;
+  }
+  MT mt(key, *pos);
+  for (int64_t i = n - 1; i > 0; --i) j_out[i] = (uint32_t)mt.masked((uint64_t)i);
+  if (n > 0) j_out[0] = 0;
+  *pos = mt.pos;
+  return RECAD_OK;
+}
+
+int recad_permutation_apply(int64_t n, const uint32_t* j, int64_t* perm) {
+  if (!j || !perm || n < 0) {
+    recad::set_error("permutation_apply: bad argument");
+    return RECAD_ERR_ARG;
+  }
+  for (int64_t i = 0; i < n; ++i) perm[i] = i;
+  constexpr int64_t kAhead = 48;
+  for (int64_t i = n - 1; i > 0; --i) {
+    if (i > kAhead) __builtin_prefetch(perm + j[i - kAhead], 1);
+    std::swap(perm[i], perm[j[i]]);
+  }
   return RECAD_OK;
 }
 

@@ -83,26 +83,42 @@ def _sorted_distinct_csr(users, items, n_rows, n_cols):
     return indptr, i
 
 
+class _EpochJob:
+    """One prefetched epoch.  Its generator-dependent part (sampler, then the draws of the shuffle) runs as soon as
+    the previous job's generator-dependent part is finished -- it starts from that job's end state -- while the
+    previous job may still be applying its swaps."""
+
+    def __init__(self, slot, prev=None, key=None, pos=None):
+        import threading
+        self.slot, self.prev = slot, prev
+        self.start_key, self.start_pos = key, pos          # known now, or once prev.rng_done fires
+        self.end_key = self.end_pos = self.out = self.error = None
+        self.rng_done, self.done = threading.Event(), threading.Event()
+
+
 class _EpochPipe:
     """Host side of an epoch: draw (samples, perm) with the exact MT19937 replay into PINNED buffers and
     ship them to the device with one asynchronous copy each.
 
     Speculative prefetch: the sampler is a sequential state machine on numpy's global stream (seconds for
-    50 M samples), so while the GPU trains epoch e a background thread draws epoch e+1 from a COPY of
-    the state epoch e ended with.  At the next call the prefetch is used only if np.random's state still
-    equals that starting state (nobody else consumed the stream, the case inside normal_train's epoch
-    loop, normal.py:95-109); then the global state is advanced to where the prefetch ended.  Otherwise it is
-    discarded and the epoch is drawn synchronously -- the stream seen by every consumer is identical to
-    the reference's in both cases."""
+    50 M samples), so while the GPU trains epoch e background threads draw epochs e+1 and e+2, each from a
+    COPY of the state the previous one ended with.  Only the stream-consuming work is chained (sampler, then
+    the draws of the shuffle); applying the swaps needs no generator and overlaps the next epoch's sampler.
+    At the next call the head of the queue is used only if np.random's state still equals its starting state
+    (nobody else consumed the stream, the case inside normal_train's epoch loop, normal.py:95-109); then the
+    global state is advanced to where that epoch ended.  Otherwise the queue is discarded and the epoch is drawn
+    synchronously -- the stream seen by every consumer is identical to the reference's in both cases."""
+
+    DEPTH = 2
 
     def __init__(self, data):
-        import threading
+        from collections import deque
         self.data = data
-        self.threading = threading
-        self.bufs = [None, None]
-        self.turn = 0
-        self.pending = None      # (thread, start_key, start_pos, result dict)
-        self.prefetch = bool(data.config.get("prefetch", data.traindataSize >= (1 << 21)))
+        self.bufs = [None] * (self.DEPTH + 1)
+        self.queue = deque()
+        self.last_slot = -1          # its buffers may still be the source of an asynchronous H2D copy
+        pf = data.config.get("prefetch")
+        self.prefetch = bool(pf) if pf is not None else data.traindataSize >= (1 << 21)
 
     def _buffers(self, slot, cuda):
         n = self.data.traindataSize * (1 if self.data.config["sample"] == "pairwise" else 1 + self.data.config["negative_ratio"])
@@ -110,13 +126,45 @@ class _EpochPipe:
             s, p = torch.empty((max(n, 1), 3), dtype=torch.int64), torch.empty(max(n, 1), dtype=torch.int64)
             if cuda:
                 s, p = s.pin_memory(), p.pin_memory()
-            self.bufs[slot] = (s, p)
+            self.bufs[slot] = (s, p, ops.host_empty(max(n, 1), np.uint32))
         return self.bufs[slot]
 
-    def _draw(self, key, pos, slot, cuda):
-        s, p = self._buffers(slot, cuda)
-        S, perm = self.data._draw_epoch(key, pos, (s.numpy(), p.numpy()))
-        return s[:len(S)], p[:len(perm)]
+    def _free_slot(self):
+        used = {j.slot for j in self.queue} | {self.last_slot}
+        return next(k for k in range(self.DEPTH + 1) if k not in used)
+
+    def _run(self, job, cuda):
+        try:
+            if job.prev is not None:
+                job.prev.rng_done.wait()
+                if job.prev.error is not None:
+                    raise RuntimeError("the previous prefetched epoch failed")
+                job.start_key, job.start_pos = job.prev.end_key.copy(), int(job.prev.end_pos)
+                job.prev = None
+            key, pos = job.start_key.copy(), [int(job.start_pos)]
+            s, p, jb = self._buffers(job.slot, cuda)
+            S = self.data._draw_samples(key, pos, s.numpy())
+            j = ops.mt_permutation_draw_raw(key, pos, len(S), jb)
+            job.end_key, job.end_pos = key, int(pos[0])
+            job.rng_done.set()                                  # the next epoch's sampler may start now
+            perm = ops.permutation_apply(j, p.numpy())
+            job.out = (s[:len(S)], p[:len(perm)])
+        except BaseException as e:   # noqa: BLE001 -- reported by falling back to the synchronous draw
+            job.error = e
+        finally:
+            job.rng_done.set()
+            job.done.set()
+
+    def _spawn(self, cuda, prev=None, key=None, pos=None):
+        import threading
+        job = _EpochJob(self._free_slot(), prev, key, pos)
+        self.queue.append(job)
+        threading.Thread(target=self._run, args=(job, cuda), daemon=True).start()
+
+    def _flush(self):
+        for job in self.queue:
+            job.done.wait()
+        self.queue.clear()
 
     def next(self, device):
         cuda = device.type == "cuda"
@@ -124,34 +172,34 @@ class _EpochPipe:
         if st[0] != "MT19937":
             raise ops.RecadError("np.random global state is not MT19937")
         got = None
-        if self.pending is not None:
-            thread, k0, p0, res = self.pending
-            thread.join()
-            self.pending = None
-            if p0 == int(st[2]) and np.array_equal(k0, st[1]) and "out" in res:
-                got = res["out"]
-                key, pos = res["key"], res["pos"]
+        if self.queue:
+            head = self.queue[0]
+            head.rng_done.wait()
+            if head.error is None and head.start_pos == int(st[2]) and np.array_equal(head.start_key, st[1]):
+                head.done.wait()
+                if head.error is None:
+                    self.queue.popleft()
+                    got, key, pos, self.last_slot = head.out, head.end_key, [head.end_pos], head.slot
+            if got is None:
+                self._flush()
         if got is None:
             key, pos = np.ascontiguousarray(st[1], dtype=np.uint32).copy(), [int(st[2])]
-            got = self._draw(key, pos, self.turn, cuda)
+            slot = self._free_slot()
+            s, p, jb = self._buffers(slot, cuda)
+            S, perm = self.data._draw_epoch(key, pos, (s.numpy(), p.numpy()))
+            got, self.last_slot = (s[:len(S)], p[:len(perm)]), slot
         np.random.set_state((st[0], key, int(pos[0]), st[3], st[4]))
-        self.turn ^= 1
         if cuda:
             s_dev = got[0].to(device, non_blocking=True)
             p_dev = got[1].to(device, non_blocking=True)
         else:                                   # host "device" (CPU-only tests): detach from the reusable buffers
             s_dev, p_dev = got[0].clone(), got[1].clone()
         if self.prefetch:
-            k2, p2, res = key.copy(), [int(pos[0])], {}
-            slot = self.turn
-
-            def work():
-                kk, pp = k2.copy(), [p2[0]]
-                res["out"] = self._draw(kk, pp, slot, cuda)
-                res["key"], res["pos"] = kk, pp
-            t = self.threading.Thread(target=work, daemon=True)
-            t.start()
-            self.pending = (t, k2, p2[0], res)
+            while len(self.queue) < self.DEPTH:
+                if self.queue:
+                    self._spawn(cuda, prev=self.queue[-1])
+                else:
+                    self._spawn(cuda, key=key.copy(), pos=int(pos[0]))
         return s_dev, p_dev
 
 
@@ -326,16 +374,17 @@ class ImplicitData:
             self._pipe = _EpochPipe(self)
         return self._pipe.next(torch.device(device or self.config["device"]))
 
+    def _draw_samples(self, key, pos, out=None):
+        """The sampler from an EXPLICIT MT19937 state (key, pos are advanced in place)."""
+        if self.config["sample"] == "pairwise":
+            return ops.mt_pairwise_raw(key, pos, self.n_users, self.n_items, self.traindataSize, *self._allpos, out=out)
+        if self.config["sample"] == "pointwise":
+            return ops.mt_pointwise_raw(key, pos, *self._tr, self.n_items, self.config["negative_ratio"], out=out)
+        raise NotImplementedError("Not implemented yet")
+
     def _draw_epoch(self, key, pos, buf=None):
         """Sampler + shuffle from an EXPLICIT MT19937 state (key, pos are advanced in place)."""
-        if self.config["sample"] == "pairwise":
-            S = ops.mt_pairwise_raw(key, pos, self.n_users, self.n_items, self.traindataSize, *self._allpos,
-                                    out=None if buf is None else buf[0])
-        elif self.config["sample"] == "pointwise":
-            S = ops.mt_pointwise_raw(key, pos, *self._tr, self.n_items, self.config["negative_ratio"],
-                                     out=None if buf is None else buf[0])
-        else:
-            raise NotImplementedError("Not implemented yet")
+        S = self._draw_samples(key, pos, None if buf is None else buf[0])
         perm = ops.mt_permutation_raw(key, pos, len(S), out=None if buf is None else buf[1])
         return S, perm
 
@@ -467,6 +516,7 @@ class ArrayImplicitData:
     mode = ImplicitData.mode
     switch_mode = ImplicitData.switch_mode
     epoch_samples = ImplicitData.epoch_samples
+    _draw_samples = ImplicitData._draw_samples
     _draw_epoch = ImplicitData._draw_epoch
     generate_batch = ImplicitData.generate_batch
 

@@ -454,6 +454,25 @@ def mt_permutation_raw(key, pos, n, out=None):
     return perm[:n]
 
 
+def mt_permutation_draw_raw(key, pos, n, j_out=None):
+    """The stream-consuming half of the shuffle: j[i] = random_interval(i), i = n-1 .. 1 (uint32 [n])."""
+    j = host_empty(max(n, 1), np.uint32) if j_out is None else j_out
+    assert j.dtype == np.uint32 and j.flags.c_contiguous and j.shape[0] >= n
+    cpos = C.c_int32(pos[0])
+    check(_lib.lib().recad_mt19937_permutation_draw(key.ctypes.data, C.byref(cpos), n, j.ctypes.data), "recad_mt19937_permutation_draw")
+    pos[0] = cpos.value
+    return j[:n]
+
+
+def permutation_apply(j, out=None):
+    """The generator-free half: perm = arange(n) with swap(perm[i], perm[j[i]]) applied for i = n-1 .. 1."""
+    n = int(j.shape[0])
+    perm = np.empty(max(n, 1), dtype=np.int64) if out is None else out
+    assert perm.dtype == np.int64 and perm.flags.c_contiguous and perm.shape[0] >= n
+    check(_lib.lib().recad_permutation_apply(n, j.ctypes.data, perm.ctypes.data), "recad_permutation_apply")
+    return perm[:n]
+
+
 def mt_pairwise(n_users, n_items, train_size, allpos_rowptr, allpos_col, out=None):
     """== pairwise_sample (implicit.py:50-74) on the global np.random stream."""
     st, key, pos = _np_state()

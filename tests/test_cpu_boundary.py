@@ -196,3 +196,36 @@ def test_workflow_registry_mirrors_reference():
         workflow.from_config("defense", victim_data=None, attack_data=None, victim=None, attacker=None)
     with pytest.raises(TypeError):
         workflow.from_config("no defense", victim_data=None)
+
+
+def test_prefetched_epochs_equal_synchronous_epochs():
+    """The depth-2 prefetch queue (sampler chained epoch to epoch, swaps applied on the side) hands out exactly the
+    epochs a synchronous draw produces, leaves np.random where the reference would, and steps aside (same stream!)
+    when somebody else consumes np.random between two epochs."""
+    tr, va, te = util.dicts("game")
+    mk = lambda pf: dataset.from_config("implicit", "game", train_dict=tr, valid_dict=va, test_dict=te, need_graph=False,  # noqa: E731
+                                        device=CPU, prefetch=pf)
+    runs = []
+    for pf in (False, True):
+        d = mk(pf)
+        np.random.seed(11)
+        seq = []
+        for e in range(5):
+            if e == 3:
+                np.random.randint(0, 10, 7)          # a foreign consumer: queued epochs no longer match the stream
+            s, p = d.epoch_samples(CPU)
+            seq.append((s.numpy().copy(), p.numpy().copy(), np.random.get_state()[1].copy(), int(np.random.get_state()[2])))
+        if pf:
+            assert d._pipe.prefetch and len(d._pipe.queue) == d._pipe.DEPTH
+            d._pipe._flush()
+        runs.append(seq)
+    for a, b in zip(*runs):
+        assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3] == b[3]
+    # and the synchronous epoch is the reference's: sampler then np.random.shuffle on the same stream
+    np.random.seed(11)
+    S, P = runs[0][0][0], runs[0][0][1]
+    ptr, col = mk(False)._allpos
+    ref = ops.mt_pairwise(META["game"]["n_users"], META["game"]["n_items"], mk(False).traindataSize, ptr, col)
+    idx = np.arange(len(ref))
+    np.random.shuffle(idx)
+    assert np.array_equal(S, ref) and np.array_equal(P, idx)
