@@ -89,7 +89,20 @@ struct MT {
   }
   inline uint64_t masked(uint64_t r) {
     if (r == 0) return 0;
-    const uint32_t mask = mask_of(r);
+    return masked_with((uint32_t)r, mask_of(r));
+  }
+  // rejection loop with the first TWO candidates examined without a branch between them: the loop exit of the
+  // plain do/while is mispredicted on every rejection (20-50 % of the draws), this form only when both fail
+  inline uint32_t masked_with(uint32_t r, uint32_t mask) {
+    if (__builtin_expect(pos + 2 <= 624, 1)) {
+      const uint32_t v0 = buf[pos] & mask, v1 = buf[pos + 1] & mask;
+      const bool ok0 = v0 <= r, ok1 = v1 <= r;
+      if (__builtin_expect(ok0 | ok1, 1)) {
+        pos += ok0 ? 1 : 2;
+        return ok0 ? v0 : v1;
+      }
+      pos += 2;
+    }
     uint32_t v;
     do { v = next() & mask; } while (v > r);
     return v;
@@ -307,11 +320,7 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
     if (r == 0) {
       memset(users, 0, (size_t)train_size * sizeof(uint32_t));
     } else {
-      for (int64_t k = 0; k < train_size; ++k) {
-        uint32_t v;
-        do { v = mt.next() & mask; } while (v > r);
-        users[k] = v;
-      }
+      for (int64_t k = 0; k < train_size; ++k) users[k] = mt.masked_with(r, mask);
     }
   }
   lap("draw users");
@@ -322,7 +331,7 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
     if (k + kAhead < train_size) __builtin_prefetch(filter + (int64_t)users[k + kAhead] * kFilterWords);
     if (k + kAhead2 < train_size) {      // second stage: line 0 of that user has arrived; fetch line 1 if it will be consulted
       const uint64_t* f2 = filter + (int64_t)users[k + kAhead2] * kFilterWords;
-      if ((int64_t)(f2[0] >> 40) > kLight) __builtin_prefetch(f2 + 8);
+      __builtin_prefetch(f2 + ((int64_t)(f2[0] >> 40) > kLight ? 8 : 0));     // select, not branch: the outcome is a coin flip
     }
     const int64_t u = users[k];
     const uint64_t* f = filter + u * kFilterWords;
@@ -336,8 +345,7 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
     const int64_t pidx = lo + (int64_t)mt.masked((uint64_t)len - 1);
     uint32_t neg;
     for (;;) {
-      if (neg_r == 0) neg = 0;
-      else do { neg = mt.next() & neg_mask; } while (neg > neg_r);
+      neg = neg_r == 0 ? 0u : mt.masked_with(neg_r, neg_mask);
       const uint32_t a = probe_a(neg);
       if (!((f[a >> 6] >> (a & 63)) & 1ull)) break;                                            // definitely not a positive
       uint32_t b, c;
@@ -455,10 +463,17 @@ int recad_mt19937_permutation_draw(uint32_t* key, int32_t* pos, int64_t n, uint3
     recad::set_error("mt19937_permutation_draw: bad argument");
     return RECAD_ERR_ARG;
   }
+  const auto t0 = std::chrono::steady_clock::now();
   MT mt(key, *pos);
-  for (int64_t i = n - 1; i > 0; --i) j_out[i] = (uint32_t)mt.masked((uint64_t)i);
+  for (int64_t i = n - 1; i > 0;) {
+    const uint32_t mask = MT::mask_of((uint64_t)i);
+    const int64_t band_lo = (int64_t)(mask >> 1) + 1;        // every i in [band_lo, i] has this mask
+    for (; i >= band_lo && i > 0; --i) j_out[i] = mt.masked_with((uint32_t)i, mask);
+  }
   if (n > 0) j_out[0] = 0;
   *pos = mt.pos;
+  if (getenv("RECAD_SAMPLER_TRACE"))
+    fprintf(stderr, "[sampler] shuffle draws %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   return RECAD_OK;
 }
 
@@ -467,12 +482,15 @@ int recad_permutation_apply(int64_t n, const uint32_t* j, int64_t* perm) {
     recad::set_error("permutation_apply: bad argument");
     return RECAD_ERR_ARG;
   }
+  const auto t0 = std::chrono::steady_clock::now();
   for (int64_t i = 0; i < n; ++i) perm[i] = i;
   constexpr int64_t kAhead = 48;
   for (int64_t i = n - 1; i > 0; --i) {
     if (i > kAhead) __builtin_prefetch(perm + j[i - kAhead], 1);
     std::swap(perm[i], perm[j[i]]);
   }
+  if (getenv("RECAD_SAMPLER_TRACE"))
+    fprintf(stderr, "[sampler] shuffle swaps %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
   return RECAD_OK;
 }
 
