@@ -228,6 +228,7 @@ def run_b200(args, w):
         if k >= prime:
             e2e.append(time.time() - t0)
         metrics = {"loss": loss_e2e, "recall@20": sums[0] / max(sums[2], 1), "ndcg@20": sums[1] / max(sums[2], 1), "HR@20(target 0)": hr20}
+    data._pipe._flush()        # let the speculative epochs finish before their buffers go away
     h2d = n * 4 * 8            # samples [n, 3] + perm [n], int64
     d2h = 4 * 8 + 3 * 8 + 4
 

@@ -13,7 +13,9 @@
 #include <sys/mman.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <climits>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -82,6 +84,7 @@ struct MT {
     if (__builtin_expect(pos >= 624, 0)) { mt_refill(key, buf); pos = 0; }
     return buf[pos++];
   }
+  void reset(int p) { mt_temper_only(key, buf); pos = p; }   // after the caller restored `key` from a checkpoint
   static inline uint32_t mask_of(uint64_t r) {
     uint64_t mask = r;
     mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
@@ -126,7 +129,8 @@ struct Scratch {
     }
     return p;
   }
-  ~Scratch() { free(p); }
+  // no destructor on purpose: the instances are function-local statics, and a daemon prefetch thread may still be
+  // inside a sampler call when the process exits (static destructors would pull the memory from under it)
 };
 
 }  // namespace
@@ -306,12 +310,10 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
   static std::mutex scratch_mutex;
   static Scratch<uint32_t> users_buf;
   static Scratch<uint32_t> neg_buf;
-  static Scratch<int64_t> pidx_buf;
   std::lock_guard<std::mutex> scratch_lock(scratch_mutex);
   uint32_t* users = users_buf.get(train_size);
   uint32_t* negs = neg_buf.get(train_size);
-  int64_t* pidxs = pidx_buf.get(train_size);
-  if (!users || !negs || !pidxs) {
+  if (!users || !negs) {
     recad::set_error("mt19937_pairwise_fast: out of host memory");
     return RECAD_ERR_ARG;
   }
@@ -324,56 +326,182 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
     }
   }
   lap("draw users");
-  constexpr int64_t kAhead = 24, kAhead2 = 12;
+  // The stream is parsed block by block (kBlock samples) in two decoupled steps:
+  //  DRAW (this thread, cache resident): every sample of the block is drawn OPTIMISTICALLY -- position of the positive,
+  //    then the first negative candidate the mask accepts, assuming the candidate is not one of the user's positives
+  //    (true for all but ~deg/I of the samples).  It touches only the row pointer (8 MB).
+  //  CHECK (a pool of spinning helper threads): the assumption is verified against the per-user filter lines -- the
+  //    DRAM-bound part, which one core can only do at ~75 M random lines/s (line-fill buffers), spread over several.
+  //  When a candidate IS a positive (about one block in four) the generator is rewound to the checkpoint, the draws
+  //  up to that sample are replayed (same outputs), the sample is finished with the exact inline loop, the checkpoint
+  //  moves behind it and the rest of the block is drawn and checked again.  Result and stream consumption are exactly
+  //  those of the plain loop (tests/test_cpu_boundary.py).
+  constexpr int64_t kBlock = 2048, kAhead = 16, kAheadLen = 32;
+  constexpr uint32_t kDropped = 0xffffffffu;
+  constexpr int64_t kNoFail = INT64_MAX;
   const uint32_t neg_r = (uint32_t)(n_items - 1), neg_mask = MT::mask_of(neg_r);
-  int64_t w = 0;
-  for (int64_t k = 0; k < train_size; ++k) {
-    if (k + kAhead < train_size) __builtin_prefetch(filter + (int64_t)users[k + kAhead] * kFilterWords);
-    if (k + kAhead2 < train_size) {      // second stage: line 0 of that user has arrived; fetch line 1 if it will be consulted
-      const uint64_t* f2 = filter + (int64_t)users[k + kAhead2] * kFilterWords;
-      __builtin_prefetch(f2 + ((int64_t)(f2[0] >> 40) > kLight ? 8 : 0));     // select, not branch: the outcome is a coin flip
-    }
-    const int64_t u = users[k];
-    const uint64_t* f = filter + u * kFilterWords;
-    const int64_t lo = (int64_t)(f[0] & (((uint64_t)1 << 40) - 1)), len = (int64_t)(f[0] >> 40);
-    if (len == 0) continue;
-    if (len >= n_items) {
-      recad::set_error("mt19937_pairwise_fast: user %lld interacted with every item; negative sampling cannot terminate",
-                       (long long)u);
-      return RECAD_ERR_ARG;
-    }
-    const int64_t pidx = lo + (int64_t)mt.masked((uint64_t)len - 1);
-    uint32_t neg;
-    for (;;) {
-      neg = neg_r == 0 ? 0u : mt.masked_with(neg_r, neg_mask);
-      const uint32_t a = probe_a(neg);
-      if (!((f[a >> 6] >> (a & 63)) & 1ull)) break;                                            // definitely not a positive
-      uint32_t b, c;
-      probes_bc(neg, len <= kLight, b, c);
-      if (!((f[b >> 6] >> (b & 63)) & (f[c >> 6] >> (c & 63)) & 1ull)) break;
-      if (len > kHeavy) {                                                                      // heavy user: second level
-        const uint64_t nbits = (uint64_t)len * 32;
-        const uint64_t p0 = ext_probe(neg, 0, nbits), p1 = ext_probe(neg, 1, nbits), p2 = ext_probe(neg, 2, nbits);
-        if (!((ext[lo + (p0 >> 5)] >> (p0 & 31)) & (ext[lo + (p1 >> 5)] >> (p1 & 31)) & (ext[lo + (p2 >> 5)] >> (p2 & 31)) & 1u))
-          break;
-      }
-      if (!std::binary_search(allpos_col + lo, allpos_col + lo + len, (int32_t)neg)) break;    // filter false positive
-    }
-    users[w] = (uint32_t)u;      // w <= k: compaction in place (users without positives are dropped, implicit.py:63-64)
-    pidxs[w] = pidx;
-    negs[w] = neg;
-    ++w;
+  static Scratch<uint32_t> rel_buf;
+  uint32_t* rel = rel_buf.get(train_size);           // index of the positive inside the user's row, or kDropped
+  if (!rel) {
+    recad::set_error("mt19937_pairwise_fast: out of host memory");
+    return RECAD_ERR_ARG;
   }
-  lap("parse stream");
-  parallel_for(w, n_threads, [&](int64_t a, int64_t b) {
-    constexpr int64_t kAhead = 16;
-    for (int64_t k = a; k < b; ++k) {
-      if (k + kAhead < b) __builtin_prefetch(allpos_col + pidxs[k + kAhead]);
-      out[3 * k] = users[k];
-      out[3 * k + 1] = allpos_col[pidxs[k]];
-      out[3 * k + 2] = negs[k];
+  auto is_positive = [&](const uint64_t* f, int64_t lo, int64_t len, uint32_t neg) -> bool {
+    const uint32_t a = probe_a(neg);
+    if (!((f[a >> 6] >> (a & 63)) & 1ull)) return false;                                       // definitely not a positive
+    uint32_t b, c;
+    probes_bc(neg, len <= kLight, b, c);
+    if (!((f[b >> 6] >> (b & 63)) & (f[c >> 6] >> (c & 63)) & 1ull)) return false;
+    if (len > kHeavy) {                                                                        // heavy user: second level
+      const uint64_t nbits = (uint64_t)len * 32;
+      const uint64_t p0 = ext_probe(neg, 0, nbits), p1 = ext_probe(neg, 1, nbits), p2 = ext_probe(neg, 2, nbits);
+      if (!((ext[lo + (p0 >> 5)] >> (p0 & 31)) & (ext[lo + (p1 >> 5)] >> (p1 & 31)) & (ext[lo + (p2 >> 5)] >> (p2 & 31)) & 1u))
+        return false;
     }
-  });
+    return std::binary_search(allpos_col + lo, allpos_col + lo + len, (int32_t)neg);           // filter false positive?
+  };
+  // first sample of [a0, a1) whose candidate is one of its user's positives
+  auto check = [&](int64_t a0, int64_t a1) -> int64_t {
+    for (int64_t k = a0; k < std::min(a1, a0 + kAhead); ++k) __builtin_prefetch(filter + (int64_t)users[k] * kFilterWords);
+    for (int64_t k = a0; k < a1; ++k) {
+      if (k + kAhead < a1) __builtin_prefetch(filter + (int64_t)users[k + kAhead] * kFilterWords);
+      if (rel[k] == kDropped) continue;
+      const uint64_t* f = filter + (int64_t)users[k] * kFilterWords;
+      if (__builtin_expect(is_positive(f, (int64_t)(f[0] & (((uint64_t)1 << 40) - 1)), (int64_t)(f[0] >> 40), negs[k]), 0)) return k;
+    }
+    return kNoFail;
+  };
+  // helper pool: spins on `go`, checks its slice of [job_lo, job_hi), reports the first failure, bumps `done`
+  struct alignas(64) Slot { std::atomic<int64_t> fail; };
+  const int n_help = getenv("RECAD_SAMPLER_HELPERS") ? atoi(getenv("RECAD_SAMPLER_HELPERS")) : (int)std::max(0, std::min(n_threads - 1, 7));
+  std::vector<Slot> slots((size_t)n_help + 1);
+  std::atomic<int64_t> go{0}, done{0};
+  std::atomic<bool> quit{false};
+  int64_t job_lo = 0, job_hi = 0;
+  auto slice = [&](int t, int64_t& a0, int64_t& a1) {
+    const int64_t n = job_hi - job_lo, per = (n + n_help) / (n_help + 1);
+    a0 = std::min(job_hi, job_lo + t * per);
+    a1 = std::min(job_hi, a0 + per);
+  };
+  std::vector<std::thread> helpers;
+  for (int t = 1; t <= n_help; ++t)
+    helpers.emplace_back([&, t]() {
+      int64_t seen = 0;
+      for (;;) {
+        int spins = 0;
+        while (go.load(std::memory_order_acquire) == seen) {
+          if (quit.load(std::memory_order_relaxed)) return;
+          if (++spins > 2000) { std::this_thread::yield(); spins = 0; } else { __builtin_ia32_pause(); }
+        }
+        ++seen;
+        int64_t a0, a1;
+        slice(t, a0, a1);
+        slots[(size_t)t].fail.store(check(a0, a1), std::memory_order_relaxed);
+        done.fetch_add(1, std::memory_order_release);
+      }
+    });
+  auto check_parallel = [&](int64_t lo_, int64_t hi_) -> int64_t {
+    if (n_help == 0 || hi_ - lo_ < 256) return check(lo_, hi_);
+    job_lo = lo_; job_hi = hi_;
+    done.store(0, std::memory_order_relaxed);
+    go.fetch_add(1, std::memory_order_release);
+    int64_t a0, a1;
+    slice(0, a0, a1);
+    int64_t first = check(a0, a1);
+    while (done.load(std::memory_order_acquire) < n_help) __builtin_ia32_pause();
+    for (int t = 1; t <= n_help; ++t) first = std::min(first, slots[(size_t)t].fail.load(std::memory_order_relaxed));
+    return first;
+  };
+  // DRAW for samples [k0, k1)
+  auto draw = [&](int64_t k0, int64_t k1) -> int {
+    for (int64_t k = k0; k < k1; ++k) {
+      if (k + kAheadLen < train_size) __builtin_prefetch(allpos_rowptr + users[k + kAheadLen]);
+      const int64_t u = users[k];
+      const int64_t len = allpos_rowptr[u + 1] - allpos_rowptr[u];
+      if (len == 0) { rel[k] = kDropped; continue; }                     // implicit.py:63-64
+      if (len >= n_items) {
+        recad::set_error("mt19937_pairwise_fast: user %lld interacted with every item; negative sampling cannot terminate",
+                         (long long)u);
+        return RECAD_ERR_ARG;
+      }
+      rel[k] = (uint32_t)mt.masked((uint64_t)len - 1);
+      negs[k] = neg_r == 0 ? 0u : mt.masked_with(neg_r, neg_mask);
+    }
+    return RECAD_OK;
+  };
+  int rc = RECAD_OK;
+  int64_t n_rewind = 0;
+  double t_draw = 0;
+  uint32_t ck_key[624];
+  for (int64_t b0 = 0; b0 < train_size && rc == RECAD_OK; b0 += kBlock) {
+    const int64_t b1 = std::min(train_size, b0 + kBlock);
+    memcpy(ck_key, key, sizeof(ck_key));                   // checkpoint: generator state in front of sample ck_from
+    int ck_pos = mt.pos;
+    int64_t ck_from = b0;
+    const auto tA = std::chrono::steady_clock::now();
+    if ((rc = draw(b0, b1))) break;
+    t_draw += std::chrono::duration<double>(std::chrono::steady_clock::now() - tA).count();
+    for (;;) {
+      const int64_t k = check_parallel(ck_from, b1);
+      if (k == kNoFail) break;
+      // rewind, replay the draws up to and including sample k (same outputs), finish it with the exact loop, move the
+      // checkpoint behind it, redraw the rest of the block
+      memcpy(key, ck_key, sizeof(ck_key));
+      mt.reset(ck_pos);
+      if ((rc = draw(ck_from, k + 1))) break;
+      const int64_t u = users[k];
+      const int64_t lo = allpos_rowptr[u], len = allpos_rowptr[u + 1] - lo;
+      const uint64_t* f = filter + u * kFilterWords;
+      uint32_t neg;
+      do { neg = neg_r == 0 ? 0u : mt.masked_with(neg_r, neg_mask); } while (is_positive(f, lo, len, neg));
+      negs[k] = neg;
+      memcpy(ck_key, key, sizeof(ck_key));
+      ck_pos = mt.pos;
+      ck_from = k + 1;
+      if ((rc = draw(k + 1, b1))) break;
+      ++n_rewind;
+    }
+  }
+  quit.store(true, std::memory_order_relaxed);
+  for (auto& h : helpers) h.join();
+  if (rc) return rc;
+  if (trace) fprintf(stderr, "[sampler] %lld rewinds, %d helper threads, first draws %.3f s\n", (long long)n_rewind, n_help, t_draw);
+  lap("parse stream");
+  // ---- compaction (users without positives are dropped) + gather of the positive items + 64-bit rows, all threads
+  int64_t w = 0;
+  {
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, (train_size + 65535) / 65536));
+    const int64_t per = (train_size + nt - 1) / nt;
+    std::vector<int64_t> cnt((size_t)nt + 1, 0);
+    parallel_for(nt, nt, [&](int64_t t0, int64_t t1) {
+      for (int64_t t = t0; t < t1; ++t) {
+        int64_t c = 0;
+        for (int64_t k = t * per; k < std::min(train_size, (t + 1) * per); ++k) c += rel[k] != kDropped;
+        cnt[(size_t)t + 1] = c;
+      }
+    });
+    for (int t = 0; t < nt; ++t) cnt[(size_t)t + 1] += cnt[(size_t)t];
+    w = cnt[(size_t)nt];
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) {
+      th.emplace_back([&, t]() {
+        int64_t o = cnt[(size_t)t];
+        const int64_t a1 = std::min(train_size, (t + 1) * per);
+        constexpr int64_t kAheadG = 16;
+        for (int64_t k = t * per; k < a1; ++k) {
+          if (k + kAheadG < a1 && rel[k + kAheadG] != kDropped)
+            __builtin_prefetch(allpos_col + allpos_rowptr[users[k + kAheadG]] + rel[k + kAheadG]);
+          if (rel[k] == kDropped) continue;
+          const int64_t u = users[k];
+          out[3 * o] = u;
+          out[3 * o + 1] = allpos_col[allpos_rowptr[u] + rel[k]];
+          out[3 * o + 2] = negs[k];
+          ++o;
+        }
+      });
+    }
+    for (auto& x : th) x.join();
+  }
   lap("gather positives");
   *n_out = w;
   *pos = mt.pos;

@@ -119,6 +119,12 @@ class _EpochPipe:
         self.last_slot = -1          # its buffers may still be the source of an asynchronous H2D copy
         pf = data.config.get("prefetch")
         self.prefetch = bool(pf) if pf is not None else data.traindataSize >= (1 << 21)
+        # speculative epochs still being drawn at interpreter exit write into pinned buffers that the CUDA runtime
+        # frees during its own teardown: wait for them first
+        import atexit
+        import weakref
+        ref = weakref.ref(self)
+        atexit.register(lambda: ref() is not None and ref()._flush())
 
     def _buffers(self, slot, cuda):
         n = self.data.traindataSize * (1 if self.data.config["sample"] == "pairwise" else 1 + self.data.config["negative_ratio"])
