@@ -85,6 +85,39 @@ struct MT {
     return buf[pos++];
   }
   void reset(int p) { mt_temper_only(key, buf); pos = p; }   // after the caller restored `key` from a checkpoint
+  // n draws of random_interval(r) with ONE mask, written to dst[0..n): every output is stored at the cursor and the
+  // cursor advances only if it is accepted -- no branch on the (random) acceptance, a 2-cycle dependency per output
+  void fill_masked(uint32_t* dst, int64_t n, uint32_t r, uint32_t mask) {
+    int64_t k = 0;
+    while (k < n) {
+      if (pos >= 624) { mt_refill(key, buf); pos = 0; }
+      int p = pos;
+      // the cursor can advance at most once per output: stay inside dst for the whole buffer pass
+      const int stop = (int)std::min<int64_t>(624, p + (n - k));
+      for (; p < stop; ++p) {
+        const uint32_t v = buf[p] & mask;
+        dst[k] = v;
+        k += v <= r;
+      }
+      pos = p;
+    }
+  }
+  // the draws of a Fisher-Yates pass over one power-of-two band: j[i] = random_interval(i) for i = hi, hi-1, .., lo
+  // (all share `mask`); same branchless cursor, moving down
+  void fill_band_desc(uint32_t* j, int64_t hi, int64_t lo, uint32_t mask) {
+    int64_t i = hi;
+    while (i >= lo) {
+      if (pos >= 624) { mt_refill(key, buf); pos = 0; }
+      int p = pos;
+      const int stop = (int)std::min<int64_t>(624, p + (i - lo + 1));
+      for (; p < stop; ++p) {
+        const uint32_t v = buf[p] & mask;
+        j[i] = v;
+        i -= (int64_t)v <= i;
+      }
+      pos = p;
+    }
+  }
   static inline uint32_t mask_of(uint64_t r) {
     uint64_t mask = r;
     mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
@@ -322,7 +355,7 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
     if (r == 0) {
       memset(users, 0, (size_t)train_size * sizeof(uint32_t));
     } else {
-      for (int64_t k = 0; k < train_size; ++k) users[k] = mt.masked_with(r, mask);
+      mt.fill_masked(users, train_size, r, mask);
     }
   }
   lap("draw users");
@@ -331,12 +364,13 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
   //    then the first negative candidate the mask accepts, assuming the candidate is not one of the user's positives
   //    (true for all but ~deg/I of the samples).  It touches only the row pointer (8 MB).
   //  CHECK (a pool of spinning helper threads): the assumption is verified against the per-user filter lines -- the
-  //    DRAM-bound part, which one core can only do at ~75 M random lines/s (line-fill buffers), spread over several.
-  //  When a candidate IS a positive (about one block in four) the generator is rewound to the checkpoint, the draws
+  //    DRAM-bound part, which one core can only do at ~75 M random lines/s (line-fill buffers), spread over several,
+  //    and it runs WHILE this thread already draws the next block.
+  //  When a candidate IS a positive (about one block in eight) the generator is rewound to the checkpoint, the draws
   //  up to that sample are replayed (same outputs), the sample is finished with the exact inline loop, the checkpoint
-  //  moves behind it and the rest of the block is drawn and checked again.  Result and stream consumption are exactly
+  //  moves behind it and everything drawn behind it (rest of the block, the speculative next block) is drawn again.  Result and stream consumption are exactly
   //  those of the plain loop (tests/test_cpu_boundary.py).
-  constexpr int64_t kBlock = 2048, kAhead = 16, kAheadLen = 32;
+  constexpr int64_t kBlock = 512, kAhead = 16, kAheadLen = 32;
   constexpr uint32_t kDropped = 0xffffffffu;
   constexpr int64_t kNoFail = INT64_MAX;
   const uint32_t neg_r = (uint32_t)(n_items - 1), neg_mask = MT::mask_of(neg_r);
@@ -378,9 +412,9 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
   std::atomic<int64_t> go{0}, done{0};
   std::atomic<bool> quit{false};
   int64_t job_lo = 0, job_hi = 0;
-  auto slice = [&](int t, int64_t& a0, int64_t& a1) {
-    const int64_t n = job_hi - job_lo, per = (n + n_help) / (n_help + 1);
-    a0 = std::min(job_hi, job_lo + t * per);
+  auto slice = [&](int t, int64_t& a0, int64_t& a1) {      // helper t = 1 .. n_help
+    const int64_t n = job_hi - job_lo, per = (n + n_help - 1) / n_help;
+    a0 = std::min(job_hi, job_lo + (t - 1) * per);
     a1 = std::min(job_hi, a0 + per);
   };
   std::vector<std::thread> helpers;
@@ -400,16 +434,22 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
         done.fetch_add(1, std::memory_order_release);
       }
     });
-  auto check_parallel = [&](int64_t lo_, int64_t hi_) -> int64_t {
-    if (n_help == 0 || hi_ - lo_ < 256) return check(lo_, hi_);
+  // the check of [lo_, hi_) runs on the helpers while this thread goes on drawing; finish_check() collects the result
+  int64_t inline_result = kNoFail;
+  bool pool_busy = false;
+  auto start_check = [&](int64_t lo_, int64_t hi_) {
+    if (n_help == 0 || hi_ - lo_ < 64) { inline_result = check(lo_, hi_); pool_busy = false; return; }
     job_lo = lo_; job_hi = hi_;
     done.store(0, std::memory_order_relaxed);
     go.fetch_add(1, std::memory_order_release);
-    int64_t a0, a1;
-    slice(0, a0, a1);
-    int64_t first = check(a0, a1);
+    pool_busy = true;
+  };
+  auto finish_check = [&]() -> int64_t {
+    if (!pool_busy) return inline_result;
     while (done.load(std::memory_order_acquire) < n_help) __builtin_ia32_pause();
+    int64_t first = kNoFail;
     for (int t = 1; t <= n_help; ++t) first = std::min(first, slots[(size_t)t].fail.load(std::memory_order_relaxed));
+    pool_busy = false;
     return first;
   };
   // DRAW for samples [k0, k1)
@@ -431,21 +471,29 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
   };
   int rc = RECAD_OK;
   int64_t n_rewind = 0;
-  double t_draw = 0;
-  uint32_t ck_key[624];
+  uint32_t ck_key[624], nx_key[624];
+  int ck_pos = mt.pos, nx_pos = 0;
+  memcpy(ck_key, key, sizeof(ck_key));                     // checkpoint: generator state in front of sample ck_from
+  int64_t ck_from = 0;
+  rc = draw(0, std::min(train_size, kBlock));
   for (int64_t b0 = 0; b0 < train_size && rc == RECAD_OK; b0 += kBlock) {
-    const int64_t b1 = std::min(train_size, b0 + kBlock);
-    memcpy(ck_key, key, sizeof(ck_key));                   // checkpoint: generator state in front of sample ck_from
-    int ck_pos = mt.pos;
-    int64_t ck_from = b0;
-    const auto tA = std::chrono::steady_clock::now();
-    if ((rc = draw(b0, b1))) break;
-    t_draw += std::chrono::duration<double>(std::chrono::steady_clock::now() - tA).count();
-    for (;;) {
-      const int64_t k = check_parallel(ck_from, b1);
-      if (k == kNoFail) break;
+    // invariant: block [b0, b1) is drawn (optimistically) from the checkpoint at ck_from = b0
+    const int64_t b1 = std::min(train_size, b0 + kBlock), n1 = std::min(train_size, b1 + kBlock);
+    start_check(b0, b1);
+    memcpy(nx_key, key, sizeof(nx_key));                   // state behind block b = checkpoint of block b + 1
+    nx_pos = mt.pos;
+    if (b1 < train_size && (rc = draw(b1, n1))) { finish_check(); break; }   // speculative: runs under the check of block b
+    int64_t k = finish_check();
+    if (k == kNoFail) {
+      memcpy(ck_key, nx_key, sizeof(ck_key));
+      ck_pos = nx_pos;
+      ck_from = b1;
+      continue;
+    }
+    // a candidate of block b is a positive: what was drawn behind it (rest of b, all of b + 1) is void
+    while (k != kNoFail) {
       // rewind, replay the draws up to and including sample k (same outputs), finish it with the exact loop, move the
-      // checkpoint behind it, redraw the rest of the block
+      // checkpoint behind it, redraw and recheck the rest of the block
       memcpy(key, ck_key, sizeof(ck_key));
       mt.reset(ck_pos);
       if ((rc = draw(ck_from, k + 1))) break;
@@ -460,12 +508,19 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
       ck_from = k + 1;
       if ((rc = draw(k + 1, b1))) break;
       ++n_rewind;
+      start_check(ck_from, b1);
+      k = finish_check();
     }
+    if (rc) break;
+    memcpy(ck_key, key, sizeof(ck_key));                   // block b is final; block b + 1 is drawn again from here
+    ck_pos = mt.pos;
+    ck_from = b1;
+    if (b1 < train_size) rc = draw(b1, n1);
   }
   quit.store(true, std::memory_order_relaxed);
   for (auto& h : helpers) h.join();
   if (rc) return rc;
-  if (trace) fprintf(stderr, "[sampler] %lld rewinds, %d helper threads, first draws %.3f s\n", (long long)n_rewind, n_help, t_draw);
+  if (trace) fprintf(stderr, "[sampler] %lld rewinds, %d helper threads\n", (long long)n_rewind, n_help);
   lap("parse stream");
   // ---- compaction (users without positives are dropped) + gather of the positive items + 64-bit rows, all threads
   int64_t w = 0;
@@ -595,8 +650,9 @@ int recad_mt19937_permutation_draw(uint32_t* key, int32_t* pos, int64_t n, uint3
   MT mt(key, *pos);
   for (int64_t i = n - 1; i > 0;) {
     const uint32_t mask = MT::mask_of((uint64_t)i);
-    const int64_t band_lo = (int64_t)(mask >> 1) + 1;        // every i in [band_lo, i] has this mask
-    for (; i >= band_lo && i > 0; --i) j_out[i] = mt.masked_with((uint32_t)i, mask);
+    const int64_t band_lo = std::max<int64_t>((int64_t)(mask >> 1) + 1, 1);        // every i in [band_lo, i] has this mask
+    mt.fill_band_desc(j_out, i, band_lo, mask);
+    i = band_lo - 1;
   }
   if (n > 0) j_out[0] = 0;
   *pos = mt.pos;

@@ -229,3 +229,37 @@ def test_prefetched_epochs_equal_synchronous_epochs():
     idx = np.arange(len(ref))
     np.random.shuffle(idx)
     assert np.array_equal(S, ref) and np.array_equal(P, idx)
+
+
+def test_fast_sampler_rewinds_are_exact_on_a_dense_dataset():
+    """Worst case for the optimistic block parser: 64 items, users holding 0..40 of them -- a third of the first
+    negative candidates ARE positives, so nearly every block is rewound several times (and users without positives
+    are dropped).  Samples and generator state must still equal the plain loop's, with and without helper threads."""
+    import os
+    rng = np.random.default_rng(3)
+    U, I, n = 5000, 64, 300_000
+    lens = rng.integers(0, 41, size=U)
+    lens[rng.integers(0, U, 200)] = 0
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    col = np.concatenate([np.sort(rng.choice(I, size=k, replace=False)) for k in lens] + [np.zeros(0, np.int64)]).astype(np.int32)
+    old = ops.FAST_SAMPLER_MIN
+    outs = []
+    try:
+        for thr, helpers in ((1 << 60, None), (0, "0"), (0, "3"), (0, None)):
+            ops.FAST_SAMPLER_MIN = thr
+            if helpers is None:
+                os.environ.pop("RECAD_SAMPLER_HELPERS", None)
+            else:
+                os.environ["RECAD_SAMPLER_HELPERS"] = helpers
+            np.random.seed(21)
+            S = ops.mt_pairwise(U, I, n, ptr, col)
+            outs.append((S.copy(), np.random.get_state()[1].copy(), int(np.random.get_state()[2])))
+    finally:
+        ops.FAST_SAMPLER_MIN = old
+        os.environ.pop("RECAD_SAMPLER_HELPERS", None)
+    assert len(outs[0][0]) < n                                   # the users without positives were dropped
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]) and o[2] == outs[0][2]
+    pos_sets = [set(col[ptr[u]:ptr[u + 1]].tolist()) for u in range(U)]
+    S = outs[0][0]
+    assert all(int(p) in pos_sets[int(u)] and int(q) not in pos_sets[int(u)] for u, p, q in S[:5000])
