@@ -85,6 +85,25 @@ struct MT {
     return buf[pos++];
   }
   void reset(int p) { mt_temper_only(key, buf); pos = p; }   // after the caller restored `key` from a checkpoint
+  // Both draws of a pairwise sample -- random_interval(r1) (skipped, as numpy does, when r1 == 0) then
+  // random_interval(r2) -- from a four-output window: all loads and compares are issued at once and the only
+  // loop-carried dependency is pos -> selects -> pos.  Returns false, consuming nothing, when the window does not
+  // settle both draws (a double rejection, ~10 %, or the end of the buffer): the caller then uses masked_with().
+  inline bool draw_pair(uint32_t r1, uint32_t m1, uint32_t r2, uint32_t m2, uint32_t& v1, uint32_t& v2) {
+    if (__builtin_expect(pos + 4 > 624, 0)) return false;
+    const uint32_t o0 = buf[pos], o1 = buf[pos + 1], o2 = buf[pos + 2], o3 = buf[pos + 3];
+    const uint32_t a0 = o0 & m1, a1 = o1 & m1;
+    const bool none = r1 == 0, okA0 = a0 <= r1, okA1 = a1 <= r1;
+    const int cA = none ? 0 : (okA0 ? 1 : 2);
+    const uint32_t x0 = cA == 0 ? o0 : (cA == 1 ? o1 : o2), x1 = cA == 0 ? o1 : (cA == 1 ? o2 : o3);
+    const uint32_t b0 = x0 & m2, b1 = x1 & m2;
+    const bool okB0 = b0 <= r2, okB1 = b1 <= r2;
+    if (__builtin_expect(!((none | okA0 | okA1) & (okB0 | okB1)), 0)) return false;
+    v1 = none ? 0u : (okA0 ? a0 : a1);
+    v2 = okB0 ? b0 : b1;
+    pos += cA + (okB0 ? 1 : 2);
+    return true;
+  }
   // n draws of random_interval(r) with ONE mask, written to dst[0..n): every output is stored at the cursor and the
   // cursor advances only if it is accepted -- no branch on the (random) acceptance, a 2-cycle dependency per output
   void fill_masked(uint32_t* dst, int64_t n, uint32_t r, uint32_t mask) {
@@ -464,7 +483,9 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
                          (long long)u);
         return RECAD_ERR_ARG;
       }
-      rel[k] = (uint32_t)mt.masked((uint64_t)len - 1);
+      const uint32_t r1 = (uint32_t)(len - 1), m1 = r1 ? 0xffffffffu >> __builtin_clz(r1) : 0u;
+      if (__builtin_expect(neg_r != 0 && mt.draw_pair(r1, m1, neg_r, neg_mask, rel[k], negs[k]), 1)) continue;
+      rel[k] = r1 ? mt.masked_with(r1, m1) : 0u;
       negs[k] = neg_r == 0 ? 0u : mt.masked_with(neg_r, neg_mask);
     }
     return RECAD_OK;
