@@ -607,13 +607,21 @@ int recad_mt19937_pointwise(uint32_t* key, int32_t* pos, int64_t n_dict_users, c
       recad::set_error("mt19937_pointwise: user %lld has no negative item to draw", (long long)uid);
       return RECAD_ERR_ARG;
     }
+    const uint32_t rr = (uint32_t)(n_left - 1), mask = MT::mask_of(rr);
     for (int64_t c = 0; c < n_neg; ++c) {
-      const int64_t r = (int64_t)mt.masked((uint64_t)n_left - 1);
+      const int64_t r = rr ? (int64_t)mt.masked_with(rr, mask) : 0;
       // r-th element of the ascending complement: r + #{distinct positives p_j with p_j - j <= r}
       int64_t t = 0, j_distinct = 0;
       if (n_distinct == n) {
-        int64_t a = 0, b = n;  // binary search on the non-decreasing sequence sp[j] - j
-        while (a < b) { int64_t mid = (a + b) >> 1; if (sp[mid] - mid <= r) a = mid + 1; else b = mid; }
+        // count of the non-decreasing sequence sp[j] - j that is <= r: binary search with selects instead of branches
+        // (the outcome of every step is a coin flip)
+        int64_t a = 0, len = n;
+        while (len > 0) {
+          const int64_t half = len >> 1, mid = a + half;
+          const bool le = sp[mid] - mid <= r;
+          a = le ? mid + 1 : a;
+          len = le ? len - half - 1 : half;
+        }
         t = a;
       } else {
         for (int64_t j = 0; j < n; ++j) {

@@ -118,7 +118,9 @@ class _EpochPipe:
         self.queue = deque()
         self.last_slot = -1          # its buffers may still be the source of an asynchronous H2D copy
         pf = data.config.get("prefetch")
-        self.prefetch = bool(pf) if pf is not None else data.traindataSize >= (1 << 21)
+        # default: on from ~10^5 interactions (ml1m-sized), where an epoch draw costs 0.05-0.2 s -- as much as the device
+        # epoch of MF or LightGCN at that size
+        self.prefetch = bool(pf) if pf is not None else data.traindataSize >= (1 << 17)
         # speculative epochs still being drawn at interpreter exit write into pinned buffers that the CUDA runtime
         # frees during its own teardown: wait for them first
         import atexit

@@ -429,10 +429,16 @@ def pairwise_filter(allpos_rowptr, allpos_col, n_users):
     return _filters[key]
 
 
+_sorted_lists = {}              # cache of mt_pointwise_raw: the per-user sorted positives of the last dataset seen
+
+
 def mt_pointwise_raw(key, pos, user_ids, pos_rowptr, pos_items, n_items, ratio, out=None):
     uid, rp, items = _np(user_ids), _np(pos_rowptr), _np(pos_items)
-    rows = np.repeat(np.arange(len(uid), dtype=np.int64), np.diff(rp))
-    srt = items[np.lexsort((items, rows))]      # each user's list sorted ascending, lists kept in place
+    ck = (items.ctypes.data, len(items), rp.ctypes.data)
+    if _sorted_lists.get("key") != ck:          # once per dataset, not once per epoch (a 0.1 s lexsort at ml1m size)
+        rows = np.repeat(np.arange(len(uid), dtype=np.int64), np.diff(rp))
+        _sorted_lists.update(key=ck, srt=items[np.lexsort((items, rows))], keep=(items, rp))   # lists sorted ascending, in place
+    srt = _sorted_lists["srt"]
     n = len(items) * (1 + ratio)
     if out is None:
         out = np.empty((max(n, 1), 3), dtype=np.int64)
