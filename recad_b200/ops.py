@@ -412,33 +412,55 @@ def to_host(t, dtype=None):
 
 
 FAST_SAMPLER_MIN = 1 << 20      # samples per epoch from which the filter-based parser pays off
-_filters = {}                   # id(allpos_col array) -> (weakref-free cache key, filter)
+
+
+class _DerivedCache:
+    """Per-dataset host structures derived from the positives (filter blocks, sorted lists), keyed by the identity of
+    the source arrays.  The entry keeps those arrays alive, so an address can never be reused by another dataset while
+    its derived data is cached; a lock makes lookup-or-build atomic (the epochs of two datasets -- the clean one's
+    speculative prefetch and the attacked one's first draw -- do run concurrently)."""
+
+    def __init__(self, capacity):
+        import threading
+        from collections import OrderedDict
+        self.capacity, self.lock, self.entries = capacity, threading.Lock(), OrderedDict()
+
+    def get(self, key, keepalive, build):
+        with self.lock:
+            if key in self.entries:
+                self.entries.move_to_end(key)
+                return self.entries[key][0]
+            value = build()
+            self.entries[key] = (value, keepalive)
+            while len(self.entries) > self.capacity:
+                self.entries.popitem(last=False)
+            return value
+
+
+_filters = _DerivedCache(3)
+_sorted_lists = _DerivedCache(4)
 
 
 def pairwise_filter(allpos_rowptr, allpos_col, n_users):
     """Per-user 128-byte blocks (row bounds + two-level membership filter, first line decisive) for mt_pairwise_raw(fast); built once per positives array."""
-    key = (allpos_col.ctypes.data, len(allpos_col), int(n_users))
-    if key not in _filters:
-        _filters.clear()
+    def build():
         filt = host_empty(int(n_users) * 16, np.uint64)
         ext = host_empty(max(len(allpos_col), 1), np.uint32)
         check(_lib.lib().recad_pairwise_filter_build(allpos_rowptr.ctypes.data, allpos_col.ctypes.data, n_users,
                                                      filt.ctypes.data, ext.ctypes.data, os.cpu_count() or 1),
               "recad_pairwise_filter_build")
-        _filters[key] = (filt, ext)
-    return _filters[key]
-
-
-_sorted_lists = {}              # cache of mt_pointwise_raw: the per-user sorted positives of the last dataset seen
+        return filt, ext
+    return _filters.get((allpos_col.ctypes.data, allpos_rowptr.ctypes.data, len(allpos_col), int(n_users)),
+                        (allpos_rowptr, allpos_col), build)
 
 
 def mt_pointwise_raw(key, pos, user_ids, pos_rowptr, pos_items, n_items, ratio, out=None):
     uid, rp, items = _np(user_ids), _np(pos_rowptr), _np(pos_items)
-    ck = (items.ctypes.data, len(items), rp.ctypes.data)
-    if _sorted_lists.get("key") != ck:          # once per dataset, not once per epoch (a 0.1 s lexsort at ml1m size)
+
+    def build():                                # once per dataset, not once per epoch (a 0.1 s lexsort at ml1m size)
         rows = np.repeat(np.arange(len(uid), dtype=np.int64), np.diff(rp))
-        _sorted_lists.update(key=ck, srt=items[np.lexsort((items, rows))], keep=(items, rp))   # lists sorted ascending, in place
-    srt = _sorted_lists["srt"]
+        return items[np.lexsort((items, rows))]   # each user's list sorted ascending, lists kept in place
+    srt = _sorted_lists.get((items.ctypes.data, rp.ctypes.data, len(items)), (items, rp), build)
     n = len(items) * (1 + ratio)
     if out is None:
         out = np.empty((max(n, 1), 3), dtype=np.int64)

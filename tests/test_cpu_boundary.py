@@ -263,3 +263,41 @@ def test_fast_sampler_rewinds_are_exact_on_a_dense_dataset():
     pos_sets = [set(col[ptr[u]:ptr[u + 1]].tolist()) for u in range(U)]
     S = outs[0][0]
     assert all(int(p) in pos_sets[int(u)] and int(q) not in pos_sets[int(u)] for u, p, q in S[:5000])
+
+
+def test_sampler_caches_do_not_mix_datasets():
+    """The filter blocks / sorted lists derived from a dataset's positives are cached per dataset: alternating between
+    two datasets of identical shape (the clean and the attacked one of a workflow, whose epochs are drawn by different
+    threads) must give each its own results."""
+    rng = np.random.default_rng(8)
+    U, I, n = 400, 300, 20_000
+
+    def make():
+        lens = rng.integers(1, 30, size=U)
+        ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        col = np.concatenate([np.sort(rng.choice(I, size=k, replace=False)) for k in lens]).astype(np.int32)
+        return ptr, col
+    sets = [make(), make()]
+    old = ops.FAST_SAMPLER_MIN
+    try:
+        want = []
+        ops.FAST_SAMPLER_MIN = 1 << 60
+        for ptr, col in sets:
+            np.random.seed(4)
+            want.append(ops.mt_pairwise(U, I, n, ptr, col).copy())
+        ops.FAST_SAMPLER_MIN = 0
+        for _ in range(2):
+            for k, (ptr, col) in enumerate(sets):
+                np.random.seed(4)
+                assert np.array_equal(ops.mt_pairwise(U, I, n, ptr, col), want[k])
+    finally:
+        ops.FAST_SAMPLER_MIN = old
+    # pointwise: per-user sorted lists are cached per (items, rowptr) pair
+    keys = np.arange(U, dtype=np.int64)
+    outs = []
+    for rnd in range(2):
+        for ptr, col in sets:
+            np.random.seed(9)
+            st, key, pos = ops._np_state()
+            outs.append(ops.mt_pointwise_raw(key, pos, keys, ptr, col.astype(np.int64), I, 2).copy())
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3]) and not np.array_equal(outs[0], outs[1])
