@@ -117,6 +117,7 @@ class _EpochPipe:
         self.bufs = [None] * (self.DEPTH + 1)
         self.queue = deque()
         self.last_slot = -1          # its buffers may still be the source of an asynchronous H2D copy
+        self.calls = 0
         pf = data.config.get("prefetch")
         # default: on from ~10^5 interactions (ml1m-sized), where an epoch draw costs 0.05-0.2 s -- as much as the device
         # epoch of MF or LightGCN at that size
@@ -202,7 +203,11 @@ class _EpochPipe:
             p_dev = got[1].to(device, non_blocking=True)
         else:                                   # host "device" (CPU-only tests): detach from the reusable buffers
             s_dev, p_dev = got[0].clone(), got[1].clone()
-        if self.prefetch:
+        self.calls += 1
+        # speculate only once the caller has come back for a second epoch: a dataset that lives for ONE epoch (the
+        # attacked copy of an attack iteration) would otherwise leave two useless epochs running in the background,
+        # and the next dataset's sampler queues up behind them
+        if self.prefetch and self.calls >= 2:
             while len(self.queue) < self.DEPTH:
                 if self.queue:
                     self._spawn(cuda, prev=self.queue[-1])

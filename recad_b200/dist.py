@@ -444,7 +444,7 @@ def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, 
     if rank == 0:
         from .dataset import _EpochPipe
         pipe = _EpochPipe(_Rank0Epochs(U, I, *ap))
-    prime = 3                                               # untimed: fill the prefetch queue (steady state of an epoch loop)
+    prime = 4                                               # untimed: fill the prefetch queue (steady state of an epoch loop)
     for it in range(prime + max(1, min(args.steps, 4))):
         dist.barrier()
         torch.cuda.synchronize()
