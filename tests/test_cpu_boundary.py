@@ -44,6 +44,15 @@ def test_host_error_paths_report_through_last_error():
     assert rc == -1 and b"bad argument" in lib.recad_last_error()
     with pytest.raises(_lib.RecadError):
         _lib.check(rc, "recad_mt19937_permutation")
+    # argument validation of the device entry points happens before any launch, so it is testable without a GPU
+    assert lib.recad_spmm_scatter(None, None, None, 2, 10, 64, None) < 0 and b"spmm_scatter" in lib.recad_last_error()
+    assert lib.recad_peer_reduce_bcast(None, 2, 8, 8, None, 2, 0, None) < 0 and b"peer_reduce_bcast" in lib.recad_last_error()
+    assert lib.recad_mf_grad(None, None, None, 4, 4, None) < 0 and b"mf" in lib.recad_last_error()
+    assert lib.recad_ncf_grad(None, None, None, 4, 4, None) < 0
+    assert lib.recad_mt19937_permutation_draw(None, None, 5, None) < 0 and b"permutation_draw" in lib.recad_last_error()
+    assert lib.recad_permutation_apply(5, None, None) < 0 and b"permutation_apply" in lib.recad_last_error()
+    assert lib.recad_fullrank_eval_tc(None, None, 10, 64, None, 4, None, None, None, 0, 20, None, None, None, None, None, None, 0,
+                                      None) < 0 and b"fullrank_tc" in lib.recad_last_error()
 
 
 def test_no_cpu_fallback_anywhere():
