@@ -121,7 +121,7 @@ def peaks():
 # ----------------------------------------------------------------------------------------------
 def run_b200(args, w):
     import torch.distributed as dist
-    from recad_b200 import dataset, evaluate, model, ops
+    from recad_b200 import dataset, model, ops
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))

@@ -1,7 +1,6 @@
 """Time the full-rank kernels in isolation: python tools/eval_probe.py [n_users] [n_items] [precision ...]"""
 import os
 import sys
-import time
 
 import torch
 

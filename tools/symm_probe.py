@@ -1,6 +1,5 @@
 """Probe what the box offers for peer-memory kernels: torchrun --nproc-per-node N tools/symm_probe.py"""
 import os
-import time
 
 import torch
 import torch.distributed as dist
@@ -39,8 +38,8 @@ try:
     t = symm.empty((I, D), dtype=torch.float32, device=dev)
     hdl = symm.rendezvous(t, dist.group.WORLD)
     if rank == 0:
-        print("symm ok: multicast", hdl.has_multicast_support(dev.type, dev.index) if hasattr(hdl, "has_multicast_support") else None,
-              "mc_ptr", hex(hdl.multicast_ptr), "bufs", [hex(p) for p in hdl.buffer_ptrs], "signal pad", hdl.signal_pad_size, flush=True)
+        print("symm ok: multicast ptr", hex(int(getattr(hdl, "multicast_ptr", 0) or 0)), "bufs", [hex(p) for p in hdl.buffer_ptrs],
+              "signal pad", getattr(hdl, "signal_pad_size", None), flush=True)
     t.normal_()
     tb = timeit(lambda: hdl.barrier(channel=0))
     if rank == 0:
