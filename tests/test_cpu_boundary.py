@@ -310,3 +310,37 @@ def test_sampler_caches_do_not_mix_datasets():
             st, key, pos = ops._np_state()
             outs.append(ops.mt_pointwise_raw(key, pos, keys, ptr, col.astype(np.int64), I, 2).copy())
     assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3]) and not np.array_equal(outs[0], outs[1])
+
+
+def test_csv_loader_and_dict_cache(tmp_path):
+    """csv2dict (implicit.py:94-104): time order, rating >= filter, first occurrence kept; the .npy dict cache of
+    implicit.py:153-164 is written and read back under the reference's file names."""
+    import os
+    from recad_b200.dataset import csv2dict
+    rows = [(0, 7, 3, 5, 50), (1, 7, 9, 4, 10), (2, 7, 3, 5, 60), (3, 2, 1, 3, 5), (4, 2, 8, 5, 7), (5, 7, 4, 2, 20), (6, 5, 0, 4, 1)]
+    for split in ("train", "valid", "test"):
+        with open(tmp_path / f"toy_{split}.csv", "w") as f:
+            f.write(",user_id,item_id,rating,timestamp\n" + "".join(f"{a},{u},{i},{r},{t}\n" for a, u, i, r, t in rows))
+    d = csv2dict(str(tmp_path / "toy_train.csv"), filter=4)
+    assert d == {5: [0], 2: [8], 7: [9, 3]} and list(d) == [5, 2, 7]          # dict order = first appearance in time
+    kw = dict(path_train=str(tmp_path / "toy_train.csv"), path_valid=str(tmp_path / "toy_valid.csv"),
+              path_test=str(tmp_path / "toy_test.csv"), need_graph=False, device=CPU, if_cache=True, cache_dir=str(tmp_path / "gen"))
+    a = dataset.from_config("implicit", "toy", **kw)
+    assert sorted(os.listdir(tmp_path / "gen")) == [f"toy_implicit_{s}_dict.npy" for s in ("test", "train", "valid")]
+    for split in ("train", "valid", "test"):
+        os.remove(tmp_path / f"toy_{split}.csv")                                  # second load must come from the cache
+    b = dataset.from_config("implicit", "toy", **kw)
+    assert b.train_dict == a.train_dict == d and (b.n_users, b.n_items) == (8, 10)
+
+
+@pytest.mark.reference
+def test_csv_loader_reproduces_the_golden_dev_dicts():
+    import os
+    from recad_b200.dataset import csv2dict
+    root = "/root/reference/data/dev"
+    if not os.path.isdir(root):
+        pytest.skip("reference checkout not present")
+    tr, va, te = util.dicts("dev")
+    for split, want in (("train", tr), ("valid", va), ("test", te)):
+        got = csv2dict(os.path.join(root, f"dev_{split}.csv"), filter=4)
+        assert got == want and list(got) == list(want)
