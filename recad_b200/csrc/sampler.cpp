@@ -27,6 +27,14 @@ namespace recad { void set_error(const char* fmt, ...); }
 
 namespace {
 
+static inline void cpu_relax() {        // spin-wait hint
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#elif defined(__aarch64__)
+  asm volatile("yield" ::: "memory");
+#endif
+}
+
 // numpy's legacy generator, state-compatible (key[624] + pos).  The 624 outputs of a twist are tempered in one
 // vectorisable pass into `buf`, so that next() -- called 2-3 times per sample by the sequential stream parsers --
 // is a load and an increment.
@@ -444,7 +452,7 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
         int spins = 0;
         while (go.load(std::memory_order_acquire) == seen) {
           if (quit.load(std::memory_order_relaxed)) return;
-          if (++spins > 2000) { std::this_thread::yield(); spins = 0; } else { __builtin_ia32_pause(); }
+          if (++spins > 2000) { std::this_thread::yield(); spins = 0; } else { cpu_relax(); }
         }
         ++seen;
         int64_t a0, a1;
@@ -465,7 +473,7 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
   };
   auto finish_check = [&]() -> int64_t {
     if (!pool_busy) return inline_result;
-    while (done.load(std::memory_order_acquire) < n_help) __builtin_ia32_pause();
+    while (done.load(std::memory_order_acquire) < n_help) cpu_relax();
     int64_t first = kNoFail;
     for (int t = 1; t <= n_help; ++t) first = std::min(first, slots[(size_t)t].fail.load(std::memory_order_relaxed));
     pool_busy = false;
