@@ -396,6 +396,13 @@ int recad_mt19937_permutation(uint32_t* key, int32_t* pos, int64_t n, int64_t* p
  * consumes the stream (j_out [host] uint32[n], j_out[i] = random_interval(i) for i = n-1 .. 1), _apply turns
  * the draws into the permutation without touching the generator -- so the caller can start drawing the next
  * epoch while another thread applies the swaps of this one. */
+/* recad_mt19937_pairwise_fast followed by recad_mt19937_permutation_draw over its *n_out rows, as ONE call: the shuffle
+ * draws (j_out [host] uint32[train_size]) are made on the calling thread right behind the parse while the other
+ * threads still gather the positive items and write `out` -- same results, same stream consumption. */
+int recad_mt19937_pairwise_epoch(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items, int64_t train_size,
+                                 const int64_t* allpos_rowptr, const int32_t* allpos_col, const uint64_t* filter,
+                                 const uint32_t* ext, int32_t n_threads, int64_t* out, int64_t* n_out,
+                                 uint32_t* j_out);
 int recad_mt19937_permutation_draw(uint32_t* key, int32_t* pos, int64_t n, uint32_t* j_out);
 int recad_permutation_apply(int64_t n, const uint32_t* j, int64_t* perm);
 

@@ -98,6 +98,7 @@ SIGNATURES = {
     "recad_host_advise_huge": (C.c_int, [vp, i64]),
     "recad_pairwise_filter_build": (C.c_int, [vp, vp, i64, vp, vp, i32]),
     "recad_mt19937_pairwise_fast": (C.c_int, [vp, C.POINTER(i32), i64, i64, i64, vp, vp, vp, vp, i32, vp, C.POINTER(i64)]),
+    "recad_mt19937_pairwise_epoch": (C.c_int, [vp, C.POINTER(i32), i64, i64, i64, vp, vp, vp, vp, i32, vp, C.POINTER(i64), vp]),
     "recad_mt19937_pointwise": (C.c_int, [vp, C.POINTER(i32), i64, vp, vp, vp, vp, i64, i32, vp]),
     "recad_mt19937_permutation": (C.c_int, [vp, C.POINTER(i32), i64, vp]),
     "recad_mt19937_permutation_draw": (C.c_int, [vp, C.POINTER(i32), i64, vp]),

@@ -193,6 +193,17 @@ struct Scratch {
   // inside a sampler call when the process exits (static destructors would pull the memory from under it)
 };
 
+// the draws of np.random.shuffle(arange(n)): j[i] = random_interval(i) for i = n-1 .. 1, one power-of-two band at a time
+static void shuffle_draws(MT& mt, int64_t n, uint32_t* j_out) {
+  for (int64_t i = n - 1; i > 0;) {
+    const uint32_t mask = MT::mask_of((uint64_t)i);
+    const int64_t band_lo = std::max<int64_t>((int64_t)(mask >> 1) + 1, 1);        // every i in [band_lo, i] has this mask
+    mt.fill_band_desc(j_out, i, band_lo, mask);
+    i = band_lo - 1;
+  }
+  if (n > 0) j_out[0] = 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -346,9 +357,11 @@ int recad_pairwise_filter_build(const int64_t* allpos_rowptr, const int32_t* all
   return RECAD_OK;
 }
 
-int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items, int64_t train_size,
-                                const int64_t* allpos_rowptr, const int32_t* allpos_col, const uint64_t* filter,
-                                const uint32_t* ext, int32_t n_threads, int64_t* out, int64_t* n_out) {
+// j_out != NULL: the draws of the epoch shuffle (recad_mt19937_permutation_draw over the *n_out rows) are made right
+// behind the parse, on this thread, WHILE the other threads gather the positive items and write the 64-bit rows
+static int pairwise_fast_impl(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items, int64_t train_size,
+                              const int64_t* allpos_rowptr, const int32_t* allpos_col, const uint64_t* filter,
+                              const uint32_t* ext, int32_t n_threads, int64_t* out, int64_t* n_out, uint32_t* j_out) {
   if (!key || !pos || !allpos_rowptr || !filter || !ext || !out || !n_out || n_users <= 0 || n_items <= 0 || train_size < 0 ||
       n_users > 0xffffffffLL || n_items > 0xffffffffLL) {
     recad::set_error("mt19937_pairwise_fast: bad argument");
@@ -584,12 +597,34 @@ int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, in
         }
       });
     }
+    if (j_out) {                       // the stream goes on while the rows are being written
+      shuffle_draws(mt, w, j_out);
+      lap("shuffle draws (under the gather)");
+    }
     for (auto& x : th) x.join();
   }
   lap("gather positives");
   *n_out = w;
   *pos = mt.pos;
   return RECAD_OK;
+}
+
+int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items, int64_t train_size,
+                                const int64_t* allpos_rowptr, const int32_t* allpos_col, const uint64_t* filter,
+                                const uint32_t* ext, int32_t n_threads, int64_t* out, int64_t* n_out) {
+  return pairwise_fast_impl(key, pos, n_users, n_items, train_size, allpos_rowptr, allpos_col, filter, ext, n_threads, out,
+                            n_out, nullptr);
+}
+
+int recad_mt19937_pairwise_epoch(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items, int64_t train_size,
+                                 const int64_t* allpos_rowptr, const int32_t* allpos_col, const uint64_t* filter,
+                                 const uint32_t* ext, int32_t n_threads, int64_t* out, int64_t* n_out, uint32_t* j_out) {
+  if (!j_out) {
+    recad::set_error("mt19937_pairwise_epoch: bad argument");
+    return RECAD_ERR_ARG;
+  }
+  return pairwise_fast_impl(key, pos, n_users, n_items, train_size, allpos_rowptr, allpos_col, filter, ext, n_threads, out,
+                            n_out, j_out);
 }
 
 int recad_mt19937_pointwise(uint32_t* key, int32_t* pos, int64_t n_dict_users, const int64_t* user_ids,
@@ -685,13 +720,7 @@ int recad_mt19937_permutation_draw(uint32_t* key, int32_t* pos, int64_t n, uint3
   }
   const auto t0 = std::chrono::steady_clock::now();
   MT mt(key, *pos);
-  for (int64_t i = n - 1; i > 0;) {
-    const uint32_t mask = MT::mask_of((uint64_t)i);
-    const int64_t band_lo = std::max<int64_t>((int64_t)(mask >> 1) + 1, 1);        // every i in [band_lo, i] has this mask
-    mt.fill_band_desc(j_out, i, band_lo, mask);
-    i = band_lo - 1;
-  }
-  if (n > 0) j_out[0] = 0;
+  shuffle_draws(mt, n, j_out);
   *pos = mt.pos;
   if (getenv("RECAD_SAMPLER_TRACE"))
     fprintf(stderr, "[sampler] shuffle draws %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());

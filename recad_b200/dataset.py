@@ -152,8 +152,12 @@ class _EpochPipe:
                 job.prev = None
             key, pos = job.start_key.copy(), [int(job.start_pos)]
             s, p, jb = self._buffers(job.slot, cuda)
-            S = self.data._draw_samples(key, pos, s.numpy())
-            j = ops.mt_permutation_draw_raw(key, pos, len(S), jb)
+            d = self.data
+            if d.config["sample"] == "pairwise":          # sampler + shuffle draws in one call (draws under the row gather)
+                S, j = ops.mt_pairwise_epoch_raw(key, pos, d.n_users, d.n_items, d.traindataSize, *d._allpos, out=s.numpy(), j_out=jb)
+            else:
+                S = d._draw_samples(key, pos, s.numpy())
+                j = ops.mt_permutation_draw_raw(key, pos, len(S), jb)
             job.end_key, job.end_pos = key, int(pos[0])
             job.rng_done.set()                                  # the next epoch's sampler may start now
             perm = ops.permutation_apply(j, p.numpy())

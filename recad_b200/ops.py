@@ -396,6 +396,25 @@ def mt_pairwise_raw(key, pos, n_users, n_items, train_size, allpos_rowptr, allpo
     return out[:n_out.value]
 
 
+def mt_pairwise_epoch_raw(key, pos, n_users, n_items, train_size, allpos_rowptr, allpos_col, out, j_out):
+    """Sampler + the draws of the epoch shuffle as one call (large epochs only): -> (samples [n, 3], j [n]); the draws run
+    on the calling thread while the other threads still write the rows.  Same stream consumption as
+    mt_pairwise_raw followed by mt_permutation_draw_raw."""
+    if train_size < FAST_SAMPLER_MIN:
+        S = mt_pairwise_raw(key, pos, n_users, n_items, train_size, allpos_rowptr, allpos_col, out=out)
+        return S, mt_permutation_draw_raw(key, pos, len(S), j_out)
+    rp, col = _np(allpos_rowptr), _np(allpos_col, np.int32)
+    assert out.dtype == np.int64 and out.flags.c_contiguous and out.shape[0] >= train_size
+    assert j_out.dtype == np.uint32 and j_out.flags.c_contiguous and j_out.shape[0] >= train_size
+    filt, ext = pairwise_filter(rp, col, n_users)
+    n_out, cpos = C.c_int64(), C.c_int32(pos[0])
+    check(_lib.lib().recad_mt19937_pairwise_epoch(key.ctypes.data, C.byref(cpos), n_users, n_items, train_size, rp.ctypes.data,
+                                                  col.ctypes.data, filt.ctypes.data, ext.ctypes.data, min(os.cpu_count() or 1, 32),
+                                                  out.ctypes.data, C.byref(n_out), j_out.ctypes.data), "recad_mt19937_pairwise_epoch")
+    pos[0] = cpos.value
+    return out[:n_out.value], j_out[:n_out.value]
+
+
 def host_empty(shape, dtype):
     """np.empty whose pages are requested as transparent huge pages (must be called before first touch)."""
     a = np.empty(shape, dtype=dtype)

@@ -344,3 +344,29 @@ def test_csv_loader_reproduces_the_golden_dev_dicts():
     for split, want in (("train", tr), ("valid", va), ("test", te)):
         got = csv2dict(os.path.join(root, f"dev_{split}.csv"), filter=4)
         assert got == want and list(got) == list(want)
+
+
+def test_pairwise_epoch_call_equals_sampler_then_shuffle_draws():
+    """recad_mt19937_pairwise_epoch (sampler + the shuffle's draws in one call, the draws made while other threads still
+    write the rows) == recad_mt19937_pairwise_fast followed by recad_mt19937_permutation_draw: rows, draws, generator."""
+    rng = np.random.default_rng(12)
+    U, I, n = 3000, 500, 150_000
+    lens = rng.integers(0, 60, size=U)                        # some users without positives: dropped rows, n_out < n
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    col = np.concatenate([np.sort(rng.choice(I, size=k, replace=False)) for k in lens] + [np.zeros(0, np.int64)]).astype(np.int32)
+    old = ops.FAST_SAMPLER_MIN
+    ops.FAST_SAMPLER_MIN = 0
+    try:
+        np.random.seed(33)
+        st, key, pos = ops._np_state()
+        S = ops.mt_pairwise_raw(key, pos, U, I, n, ptr, col).copy()
+        j = ops.mt_permutation_draw_raw(key, pos, len(S)).copy()
+        np.random.seed(33)
+        st, key2, pos2 = ops._np_state()
+        out, jb = np.empty((n, 3), np.int64), np.empty(n, np.uint32)
+        S2, j2 = ops.mt_pairwise_epoch_raw(key2, pos2, U, I, n, ptr, col, out, jb)
+    finally:
+        ops.FAST_SAMPLER_MIN = old
+    assert len(S) < n and np.array_equal(S, S2) and np.array_equal(j, j2)
+    assert np.array_equal(key, key2) and pos == pos2
+    assert sorted(ops.permutation_apply(j2).tolist()) == list(range(len(S)))
