@@ -447,7 +447,7 @@ static int pairwise_fast_impl(uint32_t* key, int32_t* pos, int64_t n_users, int6
   };
   // helper pool: spins on `go`, checks its slice of [job_lo, job_hi), reports the first failure, bumps `done`
   struct alignas(64) Slot { std::atomic<int64_t> fail; };
-  const int n_help = getenv("RECAD_SAMPLER_HELPERS") ? atoi(getenv("RECAD_SAMPLER_HELPERS")) : (int)std::max(0, std::min(n_threads - 1, 7));
+  const int n_help = getenv("RECAD_SAMPLER_HELPERS") ? atoi(getenv("RECAD_SAMPLER_HELPERS")) : (int)std::max(0, std::min(n_threads / 2 - 1, 7));   // half the cores at most: the swaps of the previous epoch and the caller run too
   std::vector<Slot> slots((size_t)n_help + 1);
   std::atomic<int64_t> go{0}, done{0};
   std::atomic<bool> quit{false};
