@@ -160,14 +160,9 @@ def run_b200(args, w):
     n = int(sets[0][0].shape[0])
     n_batches = (n + B - 1) // B
     gt_ptr, gt_col = data.ground_truth_csr("test", dev)
-    import ctypes as C
-    from recad_b200 import _lib
-    lib = _lib.lib()
-
     def epoch(samples):
         rows, perm = samples
-        _lib.check(lib.recad_lightgcn_train_epoch(C.byref(m._st), m._vp(rows), m._vp(perm), int(rows.shape[0]), B, m._steps,
-                                                  ops._stream(dev)), "recad_lightgcn_train_epoch")
+        m.run_epoch(rows, perm, B)
         m._steps += (int(rows.shape[0]) + B - 1) // B
         m._O_valid = False
 
@@ -229,7 +224,7 @@ def run_b200(args, w):
             e2e.append(time.time() - t0)
         metrics = {"loss": loss_e2e, "recall@20": sums[0] / max(sums[2], 1), "ndcg@20": sums[1] / max(sums[2], 1), "HR@20(target 0)": hr20}
     data._pipe._flush()        # let the speculative epochs finish before their buffers go away
-    h2d = n * 4 * 8            # samples [n, 3] + perm [n], int64
+    h2d = sum(int(t.numel()) * t.element_size() for t in sets[0]) + (n * 4 if sets[0][0].dtype == torch.int32 else 0)   # users, rel, negs, perm (int32) or rows + perm (int64)
     d2h = 4 * 8 + 3 * 8 + 4
 
     out = {

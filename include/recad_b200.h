@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RECAD_ABI_VERSION 1
+#define RECAD_ABI_VERSION 2
 
 enum {
   RECAD_OK = 0,
@@ -94,36 +94,34 @@ int64_t recad_csr_append_scratch_bytes(int64_t n_users, int64_t n_items, int64_t
  * backward is the same product because A_hat is symmetric)
  * ------------------------------------------------------------------------ */
 
-/* A CSR matrix plus its load-balancing plan: rows longer than seg_len are cut
- * into segments; a segment is the unit of work of one warp.  Rectangular
- * matrices are allowed (colidx indexes rows of X), which is what the user-row
- * shards of the multi-GPU path use. */
+/* A CSR matrix plus its work plan.  rowptr / colidx / vals are the canonical arrays (bit-exact against the
+ * reference's coalesced graph, implicit.py:295-296); the kernels read two derived arrays:
+ *   cv       [dev] int32[nnz, 2]   interleaved (colidx, bits of vals) pairs (recad_spmm_pack_cv)
+ *   seg_meta [dev] int32[n_seg, 4] the PLAN: one entry per segment = at most 1024 consecutive entries of one row,
+ *            {first entry low 32 bits, high 32 bits, row, (slot + 1) << 11 | count}; a segment is the unit of work
+ *            of one warp.  Rows cut into several segments (long rows, or item rows cut at L2-sized column blocks)
+ *            own consecutive partial-sum slots; slot = -1 (field 0) for single-segment rows.  Built by
+ *            recad_b200.ops.PackedPlan (index arithmetic, once per graph).
+ * Rectangular matrices are allowed (colidx indexes rows of X), which is what the shards of the multi-GPU path use.
+ * A matrix must not be used by two launches at the same time (row_cnt / partials are per-matrix scratch). */
 typedef struct recad_csr {
   int64_t n_rows;
+  int64_t n_cols;
   int64_t nnz;
   const int64_t* rowptr;   /* [dev] int64[n_rows + 1] */
   const int32_t* colidx;   /* [dev] int32[nnz] */
   const float* vals;       /* [dev] float[nnz] */
+  const void* cv;          /* [dev] int32[nnz, 2] */
   int64_t n_seg;           /* plan: number of segments (>= n_rows) */
-  int32_t seg_len;         /* plan: max entries per segment */
-  int32_t _pad;
-  const int32_t* seg_row;  /* [dev] int32[n_seg] */
-  const int64_t* seg_lo;   /* [dev] int64[n_seg] first entry of the segment */
-  const int32_t* seg_slot; /* [dev] int32[n_seg] -1 = the row has one segment, else partial slot */
+  const void* seg_meta;    /* [dev] int32[n_seg, 4] */
   int64_t n_mrow;          /* rows with > 1 segment */
-  const int32_t* mrow;     /* [dev] int32[n_mrow] row id */
-  const int32_t* mrow_lo;  /* [dev] int32[n_mrow + 1] first partial slot of the row */
+  const void* row_mseg;    /* [dev] int32[n_rows, 2] (first partial slot, number of segments) of multi-segment rows */
+  int32_t* row_cnt;        /* [dev] int32[n_rows] arrival counters, zero between launches */
   float* partials;         /* [dev] float[n_slot * D] scratch for multi-segment rows */
 } recad_csr;
 
-/* Upper bounds for the plan arrays of a matrix with n_rows / nnz. */
-int64_t recad_spmm_plan_max_segments(int64_t n_rows, int64_t nnz, int32_t seg_len);
-int64_t recad_spmm_plan_scratch_bytes(int64_t n_rows);
-/* Build the plan on the device.  counts_out [host] int64[3] = {n_seg, n_mrow,
- * n_slot}.  Synchronises the stream. */
-int recad_spmm_plan(const int64_t* rowptr, int64_t n_rows, int32_t seg_len, int32_t* seg_row,
-                    int64_t* seg_lo, int32_t* seg_slot, int32_t* mrow, int32_t* mrow_lo,
-                    int64_t* counts_out, void* scratch, int64_t scratch_bytes, void* stream);
+/* cv[e] = (colidx[e], bits of vals[e]). */
+int recad_spmm_pack_cv(const int32_t* colidx, const float* vals, int64_t nnz, void* cv, void* stream);
 
 /* Y = A X (written if Y != NULL) and Z = alpha * (C + A X) (written if Z != NULL;
  * C == NULL means 0; Z may alias C).  X, Y, C, Z: [dev] float[rows, D] row-major,
@@ -215,6 +213,15 @@ int recad_lightgcn_propagate(const recad_lightgcn* st, void* stream);
  * the epoch (the reference syncs once per batch, lightgcn.py:169). */
 int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* samples, const int64_t* perm,
                                int64_t n_samples, int64_t batch, int64_t step0, void* stream);
+
+/* 32-bit forms of the two calls above (samples [dev] int32[*, 3], perm [dev] int32[*]): what the large-epoch path
+ * uses -- the host sampler emits 32-bit arrays (recad_mt19937_pairwise_soa + recad_samples_expand), halving the
+ * host->device traffic of an epoch. */
+int recad_bpr_fwd_bwd_i32(const float* O, const float* E, int64_t n_users, int64_t n_items,
+                          const int32_t* samples, const int32_t* perm, int64_t B, int64_t B_norm,
+                          float grad_scale, float* gO, float* cnt, double* loss_acc, int32_t D, void* stream);
+int recad_lightgcn_train_epoch_i32(const recad_lightgcn* st, const int32_t* samples, const int32_t* perm,
+                                   int64_t n_samples, int64_t batch, int64_t step0, void* stream);
 
 /* scores[b] = <O[users[b]], O[n_users + items[b]]> (lightgcn.py:174-183 after a
  * propagate; O must be current). */
@@ -404,6 +411,22 @@ int recad_mt19937_pairwise_epoch(uint32_t* key, int32_t* pos, int64_t n_users, i
                                  const uint32_t* ext, int32_t n_threads, int64_t* out, int64_t* n_out,
                                  uint32_t* j_out);
 int recad_mt19937_permutation_draw(uint32_t* key, int32_t* pos, int64_t n, uint32_t* j_out);
+/* Second-generation epoch sampler for 10^7..10^8 samples: same samples and stream consumption as
+ * recad_mt19937_pairwise (+ recad_mt19937_permutation_draw when j_out != NULL), in 32-bit structure-of-arrays form:
+ *   users / rel / negs [host] uint32[train_size]: user id, INDEX of the positive inside the user's row of allPos,
+ *   negative item; the positive ITEM is looked up on the device by recad_samples_expand.
+ * A producer thread generates the MT19937 stream into a ring, helper threads gather row lengths and verify the
+ * optimistically drawn negatives; the calling thread runs the sequential parse (csrc/sampler.cpp). */
+int recad_mt19937_pairwise_soa(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items, int64_t train_size,
+                               const int64_t* allpos_rowptr, const int32_t* allpos_col, const uint64_t* filter,
+                               const uint32_t* ext, int32_t n_threads, uint32_t* users, uint32_t* rel, uint32_t* negs,
+                               int64_t* n_out, uint32_t* j_out);
+int recad_permutation_apply32(int64_t n, const uint32_t* j, int32_t* perm);
+/* rows[k] = (users[k], allpos_col[allpos_rowptr[users[k]] + rel[k]], negs[k]) as int32[n, 3] on the device
+ * (the positive-item gather of implicit.py:66-67, done where the CSR lives).
+ * users / rel / negs [dev] uint32[n], allpos_rowptr [dev] int64[n_users + 1], allpos_col [dev] int32[]. */
+int recad_samples_expand(const int64_t* allpos_rowptr, const int32_t* allpos_col, const uint32_t* users,
+                         const uint32_t* rel, const uint32_t* negs, int64_t n, int32_t* rows, void* stream);
 int recad_permutation_apply(int64_t n, const uint32_t* j, int64_t* perm);
 
 #ifdef __cplusplus

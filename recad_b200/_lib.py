@@ -19,9 +19,8 @@ class RecadError(RuntimeError):
 class CSR(C.Structure):
     """struct recad_csr"""
     _fields_ = [
-        ("n_rows", i64), ("nnz", i64), ("rowptr", vp), ("colidx", vp), ("vals", vp),
-        ("n_seg", i64), ("seg_len", i32), ("_pad", i32), ("seg_row", vp), ("seg_lo", vp), ("seg_slot", vp),
-        ("n_mrow", i64), ("mrow", vp), ("mrow_lo", vp), ("partials", vp),
+        ("n_rows", i64), ("n_cols", i64), ("nnz", i64), ("rowptr", vp), ("colidx", vp), ("vals", vp), ("cv", vp),
+        ("n_seg", i64), ("seg_meta", vp), ("n_mrow", i64), ("row_mseg", vp), ("row_cnt", vp), ("partials", vp),
     ]
 
 
@@ -67,10 +66,8 @@ SIGNATURES = {
     "recad_csr_normalize": (C.c_int, [vp, vp, vp, vp, i64, vp, vp]),
     "recad_csr_append_users": (C.c_int, [vp, vp, vp, i64, i64, i64, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
     "recad_csr_append_scratch_bytes": (i64, [i64, i64, i64, i64]),
-    "recad_spmm_plan_max_segments": (i64, [i64, i64, i32]),
-    "recad_spmm_plan_scratch_bytes": (i64, [i64]),
-    "recad_spmm_plan": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp, C.POINTER(i64), vp, i64, vp]),
     "recad_spmm": (C.c_int, [C.POINTER(CSR), vp, vp, vp, vp, f32, i32, vp]),
+    "recad_spmm_pack_cv": (C.c_int, [vp, vp, i64, vp, vp]),
     "recad_spmm_scatter": (C.c_int, [C.POINTER(CSR), vp, C.POINTER(vp), i32, i64, i32, vp]),
     "recad_peer_reduce_bcast": (C.c_int, [vp, i32, i64, i64, C.POINTER(vp), i32, i32, vp]),
     "recad_bpr_fwd_bwd": (C.c_int, [vp, vp, i64, i64, vp, vp, i64, i64, f32, vp, vp, vp, i32, vp]),
@@ -78,6 +75,8 @@ SIGNATURES = {
     "recad_adam": (C.c_int, [vp, vp, vp, f32, vp, vp, i64, i32, f32, f32, f32, f32, i64, vp]),
     "recad_lightgcn_propagate": (C.c_int, [C.POINTER(LightGCN), vp]),
     "recad_lightgcn_train_epoch": (C.c_int, [C.POINTER(LightGCN), vp, vp, i64, i64, i64, vp]),
+    "recad_bpr_fwd_bwd_i32": (C.c_int, [vp, vp, i64, i64, vp, vp, i64, i64, f32, vp, vp, vp, i32, vp]),
+    "recad_lightgcn_train_epoch_i32": (C.c_int, [C.POINTER(LightGCN), vp, vp, i64, i64, i64, vp]),
     "recad_dot_scores": (C.c_int, [vp, i64, vp, vp, i64, i32, vp, vp]),
     "recad_mf_forward": (C.c_int, [C.POINTER(MF), vp, vp, i64, vp, vp]),
     "recad_mf_train_epoch": (C.c_int, [C.POINTER(MF), vp, vp, i64, i64, i64, vp]),
@@ -103,6 +102,9 @@ SIGNATURES = {
     "recad_mt19937_permutation": (C.c_int, [vp, C.POINTER(i32), i64, vp]),
     "recad_mt19937_permutation_draw": (C.c_int, [vp, C.POINTER(i32), i64, vp]),
     "recad_permutation_apply": (C.c_int, [i64, vp, vp]),
+    "recad_mt19937_pairwise_soa": (C.c_int, [vp, C.POINTER(i32), i64, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, C.POINTER(i64), vp]),
+    "recad_permutation_apply32": (C.c_int, [i64, vp, vp]),
+    "recad_samples_expand": (C.c_int, [vp, vp, vp, vp, vp, i64, vp, vp]),
 }
 
 _lib = None
@@ -120,7 +122,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)   # AttributeError if the library lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if handle.recad_abi_version() != 1:
+        if handle.recad_abi_version() != 2:
             raise RecadError("librecad_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

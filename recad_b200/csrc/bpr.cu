@@ -13,10 +13,10 @@ namespace recad {
 // BPR forward + backward.  A group of LPR lanes owns one sample; each lane holds VPL float4 columns
 // of the six rows (O_u, O_p, O_n, E_u, E_p, E_n).  Gradients leave through 128-bit vector REDs.
 // ------------------------------------------------------------------------------------------
-template <int LPR, int VPL>
+template <int LPR, int VPL, typename IdxT>
 __global__ void __launch_bounds__(256)
 bpr_kernel(const float* __restrict__ O, const float* __restrict__ E, int64_t n_users, int64_t n_items,
-           const int64_t* __restrict__ samples, const int64_t* __restrict__ perm,
+           const IdxT* __restrict__ samples, const IdxT* __restrict__ perm,
            int64_t B, int64_t B_norm, float grad_scale, float* __restrict__ gO, float* __restrict__ cnt,
            double* __restrict__ loss_acc, int nvec, int* __restrict__ bad) {
   constexpr int GPW = 32 / LPR;  // sample groups per warp
@@ -180,28 +180,29 @@ int launch_adam(float* p, const float* g, const float* cnt, float reg_scale, flo
   return RECAD_OK;
 }
 
-template <int LPR, int VPL>
-static int launch_bpr_t(const float* O, const float* E, int64_t U, int64_t I, const int64_t* samples,
-                        const int64_t* perm, int64_t B, int64_t B_norm, float gs, float* gO, float* cnt, double* loss, int nvec,
+template <int LPR, int VPL, typename IdxT>
+static int launch_bpr_t(const float* O, const float* E, int64_t U, int64_t I, const IdxT* samples,
+                        const IdxT* perm, int64_t B, int64_t B_norm, float gs, float* gO, float* cnt, double* loss, int nvec,
                         int* bad, cudaStream_t s) {
   const int64_t groups_per_block = 256 / LPR;
   const int64_t want = (B + groups_per_block - 1) / groups_per_block;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 32));
-  bpr_kernel<LPR, VPL><<<grid, 256, 0, s>>>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad);
+  bpr_kernel<LPR, VPL, IdxT><<<grid, 256, 0, s>>>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad);
   RECAD_LAUNCH_CHECK();
   return RECAD_OK;
 }
 
-int launch_bpr(const float* O, const float* E, int64_t U, int64_t I, const int64_t* samples, const int64_t* perm,
+template <typename IdxT>
+static int launch_bpr(const float* O, const float* E, int64_t U, int64_t I, const IdxT* samples, const IdxT* perm,
                int64_t B, int64_t B_norm, float gs, float* gO, float* cnt, double* loss, int D, int* bad,
                cudaStream_t s) {
   const int nvec = D / 4;
-  if (nvec <= 8) return launch_bpr_t<8, 1>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 16) return launch_bpr_t<16, 1>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 32) return launch_bpr_t<32, 1>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 64) return launch_bpr_t<32, 2>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 128) return launch_bpr_t<32, 4>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
-  return launch_bpr_t<32, 8>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 8) return launch_bpr_t<8, 1, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 16) return launch_bpr_t<16, 1, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 32) return launch_bpr_t<32, 1, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 64) return launch_bpr_t<32, 2, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 128) return launch_bpr_t<32, 4, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  return launch_bpr_t<32, 8, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
 }
 
 // z = a * x + b * y (float4 grid-stride); z may alias x or y
@@ -253,8 +254,8 @@ int recad_bpr_fwd_bwd(const float* O, const float* E, int64_t n_users, int64_t n
   RECAD_REQUIRE(B >= 0 && B_norm >= B && B_norm > 0 && D >= 4 && D % 4 == 0 && D <= 1024, RECAD_ERR_UNSUPPORTED, "bpr: bad B or D");
   if (B == 0) return RECAD_OK;
   // loss_acc[3] doubles as the out-of-range flag (stays 0.0 when all ids are valid)
-  return launch_bpr(O, E, n_users, n_items, samples, perm, B, B_norm, grad_scale, gO, cnt, loss_acc, D,
-                    reinterpret_cast<int*>(loss_acc + 3), as_stream(stream));
+  return launch_bpr<int64_t>(O, E, n_users, n_items, samples, perm, B, B_norm, grad_scale, gO, cnt, loss_acc, D,
+                             reinterpret_cast<int*>(loss_acc + 3), as_stream(stream));
 }
 
 int recad_adam(float* p, const float* g, const float* cnt, float reg_scale, float* m, float* v, int64_t n, int32_t D,
@@ -286,8 +287,11 @@ int recad_lightgcn_propagate(const recad_lightgcn* st, void* stream) {
   return RECAD_OK;
 }
 
-int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* samples, const int64_t* perm,
-                               int64_t n_samples, int64_t batch, int64_t step0, void* stream) {
+}  // extern "C"
+
+template <typename IdxT>
+static int lightgcn_train_epoch_t(const recad_lightgcn* st, const IdxT* samples, const IdxT* perm,
+                                  int64_t n_samples, int64_t batch, int64_t step0, void* stream) {
   int rc = check_lightgcn(st);
   if (rc) return rc;
   RECAD_REQUIRE(st->m && st->v && st->g && st->cnt && st->loss_acc && st->X0 && st->X1, RECAD_ERR_ARG,
@@ -305,7 +309,7 @@ int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* samples,
     if (rc) return rc;
     RECAD_CUDA_CHECK(cudaMemsetAsync(st->g, 0, N * D * sizeof(float), s));
     RECAD_CUDA_CHECK(cudaMemsetAsync(st->cnt, 0, N * sizeof(float), s));
-    rc = launch_bpr(st->O, st->E, st->n_users, st->n_items, perm ? samples : samples + 3 * b0, perm ? perm + b0 : nullptr, B, B,
+    rc = launch_bpr(st->O, st->E, st->n_users, st->n_items, perm ? samples : samples + 3 * b0, perm ? perm + b0 : (const IdxT*)nullptr, B, B,
                     1.0f / (float)(L + 1), st->g, st->cnt, st->loss_acc, D, reinterpret_cast<int*>(st->loss_acc + 3), s);
     if (rc) return rc;
     // Horner: t <- g + A t, L times, so that t = (I + A + ... + A^L) g
@@ -321,6 +325,55 @@ int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* samples,
                      adam_scalars(st->lr, st->beta1, st->beta2, st->eps, step), fold, s);
     if (rc) return rc;
   }
+  return RECAD_OK;
+}
+
+extern "C" {
+
+int recad_lightgcn_train_epoch(const recad_lightgcn* st, const int64_t* samples, const int64_t* perm,
+                               int64_t n_samples, int64_t batch, int64_t step0, void* stream) {
+  return lightgcn_train_epoch_t<int64_t>(st, samples, perm, n_samples, batch, step0, stream);
+}
+
+int recad_lightgcn_train_epoch_i32(const recad_lightgcn* st, const int32_t* samples, const int32_t* perm,
+                                   int64_t n_samples, int64_t batch, int64_t step0, void* stream) {
+  return lightgcn_train_epoch_t<int32_t>(st, samples, perm, n_samples, batch, step0, stream);
+}
+
+int recad_bpr_fwd_bwd_i32(const float* O, const float* E, int64_t n_users, int64_t n_items, const int32_t* samples,
+                          const int32_t* perm, int64_t B, int64_t B_norm, float grad_scale, float* gO, float* cnt,
+                          double* loss_acc, int32_t D, void* stream) {
+  RECAD_REQUIRE(O && E && samples && gO && cnt && loss_acc, RECAD_ERR_ARG, "bpr: null pointer");
+  RECAD_REQUIRE(B >= 0 && B_norm >= B && B_norm > 0 && D >= 4 && D % 4 == 0 && D <= 1024, RECAD_ERR_UNSUPPORTED, "bpr: bad B or D");
+  if (B == 0) return RECAD_OK;
+  return launch_bpr<int32_t>(O, E, n_users, n_items, samples, perm, B, B_norm, grad_scale, gO, cnt, loss_acc, D,
+                             reinterpret_cast<int*>(loss_acc + 3), as_stream(stream));
+}
+
+}  // extern "C"
+
+// rows[k] = (users[k], allpos_col[allpos_rowptr[users[k]] + rel[k]], negs[k])
+__global__ void __launch_bounds__(256)
+samples_expand_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const uint32_t* __restrict__ users,
+                      const uint32_t* __restrict__ rel, const uint32_t* __restrict__ negs, int64_t n, int32_t* __restrict__ rows) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t u = users[k];
+    rows[3 * k] = (int32_t)u;
+    rows[3 * k + 1] = col[rowptr[u] + rel[k]];
+    rows[3 * k + 2] = (int32_t)negs[k];
+  }
+}
+
+extern "C" {
+
+int recad_samples_expand(const int64_t* allpos_rowptr, const int32_t* allpos_col, const uint32_t* users, const uint32_t* rel,
+                         const uint32_t* negs, int64_t n, int32_t* rows, void* stream) {
+  RECAD_REQUIRE(n >= 0 && (n == 0 || (allpos_rowptr && allpos_col && users && rel && negs && rows)), RECAD_ERR_ARG,
+                "samples_expand: bad argument");
+  if (n == 0) return RECAD_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 16);
+  samples_expand_kernel<<<grid, 256, 0, as_stream(stream)>>>(allpos_rowptr, allpos_col, users, rel, negs, n, rows);
+  RECAD_LAUNCH_CHECK();
   return RECAD_OK;
 }
 

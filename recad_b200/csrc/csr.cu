@@ -194,49 +194,6 @@ __global__ void append_item_tails_kernel(const uint64_t* __restrict__ item_keys,
   new_mult[p] = 1.0f;
 }
 
-// ------------------------------------------------------------------------------------------
-// SpMM plan
-// ------------------------------------------------------------------------------------------
-__global__ void plan_count_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int32_t seg_len,
-                                  uint32_t* __restrict__ nseg, uint32_t* __restrict__ multi,
-                                  uint32_t* __restrict__ slots) {
-  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_rows) return;
-  const int64_t len = rowptr[r + 1] - rowptr[r];
-  const uint32_t s = len <= seg_len ? 1u : (uint32_t)((len + seg_len - 1) / seg_len);
-  nseg[r] = s;
-  multi[r] = s > 1 ? 1u : 0u;
-  slots[r] = s > 1 ? s : 0u;
-}
-
-__global__ void plan_fill_kernel(const int64_t* __restrict__ rowptr, int64_t n_rows, int32_t seg_len,
-                                 const uint32_t* __restrict__ seg_off, const uint32_t* __restrict__ mrow_off,
-                                 const uint32_t* __restrict__ slot_off, const unsigned long long* __restrict__ totals,
-                                 int32_t* __restrict__ seg_row, int64_t* __restrict__ seg_lo,
-                                 int32_t* __restrict__ seg_slot, int32_t* __restrict__ mrow,
-                                 int32_t* __restrict__ mrow_lo) {
-  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r == 0) mrow_lo[totals[1]] = (int32_t)totals[2];
-  if (r >= n_rows) return;
-  const int64_t lo = rowptr[r], len = rowptr[r + 1] - lo;
-  const uint32_t s = len <= seg_len ? 1u : (uint32_t)((len + seg_len - 1) / seg_len);
-  const uint32_t so = seg_off[r];
-  if (s == 1) {
-    seg_row[so] = (int32_t)r;
-    seg_lo[so] = lo;
-    seg_slot[so] = -1;
-  } else {
-    const uint32_t sl = slot_off[r];
-    for (uint32_t k = 0; k < s; ++k) {
-      seg_row[so + k] = (int32_t)r;
-      seg_lo[so + k] = lo + (int64_t)k * seg_len;
-      seg_slot[so + k] = (int32_t)(sl + k);
-    }
-    mrow[mrow_off[r]] = (int32_t)r;
-    mrow_lo[mrow_off[r]] = (int32_t)sl;
-  }
-}
-
 }  // namespace recad
 
 using namespace recad;
@@ -386,46 +343,6 @@ int recad_csr_append_users(const int64_t* rowptr, const int32_t* colidx, const f
   RECAD_CUDA_CHECK(cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, s));
   RECAD_CUDA_CHECK(cudaStreamSynchronize(s));
   RECAD_REQUIRE(!h_bad, RECAD_ERR_ARG, "csr_append: fake item id out of range");
-  return RECAD_OK;
-}
-
-int64_t recad_spmm_plan_max_segments(int64_t n_rows, int64_t nnz, int32_t seg_len) {
-  return n_rows + (seg_len > 0 ? nnz / seg_len : 0) + 1;
-}
-
-int64_t recad_spmm_plan_scratch_bytes(int64_t n_rows) {
-  return 6 * align256(n_rows * 4) + 3 * scan_scratch_bytes(n_rows) + 1024;
-}
-
-int recad_spmm_plan(const int64_t* rowptr, int64_t n_rows, int32_t seg_len, int32_t* seg_row, int64_t* seg_lo,
-                    int32_t* seg_slot, int32_t* mrow, int32_t* mrow_lo, int64_t* counts_out, void* scratch,
-                    int64_t scratch_bytes, void* stream) {
-  cudaStream_t s = as_stream(stream);
-  RECAD_REQUIRE(rowptr && n_rows > 0 && seg_len >= 32 && seg_len % 32 == 0, RECAD_ERR_ARG,
-                "spmm_plan: bad argument (seg_len must be a positive multiple of 32)");
-  RECAD_REQUIRE(seg_row && seg_lo && seg_slot && mrow && mrow_lo && counts_out && scratch, RECAD_ERR_ARG,
-                "spmm_plan: null pointer");
-  RECAD_REQUIRE(scratch_bytes >= recad_spmm_plan_scratch_bytes(n_rows), RECAD_ERR_SCRATCH, "spmm_plan: scratch too small");
-  char* p = reinterpret_cast<char*>(scratch);
-  uint32_t* a[6];
-  for (int k = 0; k < 6; ++k) { a[k] = reinterpret_cast<uint32_t*>(p); p += align256(n_rows * 4); }
-  unsigned long long* totals = reinterpret_cast<unsigned long long*>(p); p += 256;
-  void* scan_scr = p;
-  const int T = 256;
-  const unsigned grid = (unsigned)((n_rows + T - 1) / T);
-  plan_count_kernel<<<grid, T, 0, s>>>(rowptr, n_rows, seg_len, a[0], a[1], a[2]);
-  RECAD_LAUNCH_CHECK();
-  for (int k = 0; k < 3; ++k) {
-    int rc = exclusive_scan_u32(a[k], a[3 + k], n_rows, totals + k, scan_scr, s);
-    if (rc) return rc;
-  }
-  plan_fill_kernel<<<grid, T, 0, s>>>(rowptr, n_rows, seg_len, a[3], a[4], a[5], totals, seg_row, seg_lo, seg_slot,
-                                     mrow, mrow_lo);
-  RECAD_LAUNCH_CHECK();
-  unsigned long long h[3];
-  RECAD_CUDA_CHECK(cudaMemcpyAsync(h, totals, 24, cudaMemcpyDeviceToHost, s));
-  RECAD_CUDA_CHECK(cudaStreamSynchronize(s));
-  for (int k = 0; k < 3; ++k) counts_out[k] = (int64_t)h[k];
   return RECAD_OK;
 }
 

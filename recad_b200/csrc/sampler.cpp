@@ -204,6 +204,48 @@ static void shuffle_draws(MT& mt, int64_t n, uint32_t* j_out) {
   if (n > 0) j_out[0] = 0;
 }
 
+
+// Iteration order of the CPython set built by inserting, in ascending order, every item of [0, n_items) that is not
+// in the sorted list sp[0..n) (duplicates allowed in sp) into an empty set -- what `set(range(n_items)) - set(iids)`
+// returns when it does not take the copy-and-discard path.  hash(int) == int for these values.
+static void cpython_set_order(const int64_t* sp, int64_t n, int64_t n_items, std::vector<int64_t>& order) {
+  constexpr int kLinearProbes = 9, kPerturbShift = 5;
+  std::vector<int64_t> table(8, -1), old;
+  size_t mask = 7, fill = 0;
+  auto insert_clean = [&](std::vector<int64_t>& t, size_t m, int64_t key) {
+    size_t perturb = (size_t)key, i = (size_t)key & m;
+    for (;;) {
+      if (t[i] < 0) { t[i] = key; return; }
+      if (i + kLinearProbes <= m) {
+        for (int j = 1; j <= kLinearProbes; ++j)
+          if (t[i + (size_t)j] < 0) { t[i + (size_t)j] = key; return; }
+      }
+      perturb >>= kPerturbShift;
+      i = (i * 5 + 1 + perturb) & m;
+    }
+  };
+  int64_t q = 0;
+  for (int64_t item = 0; item < n_items; ++item) {
+    while (q < n && sp[q] < item) ++q;
+    if (q < n && sp[q] == item) continue;
+    insert_clean(table, mask, item);          // no dummies, no equal keys: set_add_entry probes exactly like set_insert_clean
+    ++fill;
+    if (fill * 5 >= mask * 3) {
+      const size_t minused = fill > 50000 ? fill * 2 : fill * 4;
+      size_t newsize = 8;
+      while (newsize <= minused) newsize <<= 1;
+      old.swap(table);
+      table.assign(newsize, -1);
+      mask = newsize - 1;
+      for (int64_t key : old)
+        if (key >= 0) insert_clean(table, mask, key);
+    }
+  }
+  order.clear();
+  for (int64_t key : table)
+    if (key >= 0) order.push_back(key);
+}
+
 }  // namespace
 
 extern "C" {
@@ -627,6 +669,450 @@ int recad_mt19937_pairwise_epoch(uint32_t* key, int32_t* pos, int64_t n_users, i
                             n_out, j_out);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Second-generation epoch sampler (recad_mt19937_pairwise_soa).  Same samples, same stream consumption as
+// recad_mt19937_pairwise (implicit.py:50-74) + the shuffle draws (implicit.py:24-25); what changed is who does what:
+//   * a PRODUCER thread generates the MT19937 output stream into a ring -- the stream does not depend on the parse,
+//     so rewinding the parser is just resetting an index (no generator checkpoints), and the parser never runs a twist;
+//   * the users are drawn first (implicit.py:57); while they are drawn, helper threads already gather every sample's
+//     row LENGTH from a 4-byte-per-user table, so the sequential parser only streams sequential arrays;
+//   * the parser draws optimistically (first candidate the mask accepts) block by block; the helpers check block b's
+//     candidates against the per-user filter lines while the parser draws block b + 1; a candidate that IS a positive
+//     makes the parser redo that sample exactly and redraw ONLY until the new trajectory meets the old one again
+//     (same sample, same stream offset: typically a few samples later), bounded by the two blocks in flight;
+//   * outputs are three 32-bit arrays (user, index of the positive inside the user's row, negative): the positive
+//     ITEM is looked up on the device (recad_samples_expand), where the CSR already lives.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+struct StreamRing {
+  static constexpr uint64_t kWords = (uint64_t)1 << 21;        // 8 MB of outputs in flight
+  static constexpr uint64_t kMask = kWords - 1;
+  static constexpr int kPad = 64;                              // mirror of the first words behind the end: windows never wrap
+  static constexpr int64_t kSnapEvery = 1024;                  // generator snapshots, in twists
+  uint32_t* buf = nullptr;
+  alignas(64) std::atomic<uint64_t> head{0};                   // outputs produced
+  alignas(64) std::atomic<uint64_t> tail{0};                   // lowest output the consumer may still read
+  std::atomic<bool> stop{false};
+  uint32_t key[624];
+  int pos0 = 0;
+  std::vector<uint32_t> snaps;                                 // key after s * kSnapEvery twists
+  std::thread th;
+
+  bool start(const uint32_t* key_in, int pos_in) {
+    void* q = nullptr;
+    if (posix_memalign(&q, 4096, (kWords + kPad) * sizeof(uint32_t)) != 0) return false;
+    buf = static_cast<uint32_t*>(q);
+    memcpy(key, key_in, sizeof(key));
+    pos0 = pos_in;
+    snaps.assign(key, key + 624);
+    th = std::thread([this]() { run(); });
+    return true;
+  }
+  void put(const uint32_t* src, int n) {                       // append n outputs at head (the caller checked the room)
+    if (n <= 0 || n > 624) return;
+    const uint64_t h = head.load(std::memory_order_relaxed);
+    uint64_t i = h & kMask;
+    const uint64_t first = std::min<uint64_t>((uint64_t)n, kWords - i);
+    memcpy(buf + i, src, first * 4);
+    const uint64_t rest = (uint64_t)n - first;
+    if (rest > 0 && rest <= 624) memcpy(buf, src + first, rest * 4);
+    // mirror: ring words [0, kPad) also live at [kWords, kWords + kPad)
+    if (i < (uint64_t)kPad) {
+      const uint64_t m = std::min<uint64_t>((uint64_t)n, (uint64_t)kPad - i);
+      memcpy(buf + kWords + i, src, m * 4);
+    }
+    if (rest > 0 && rest <= 624) memcpy(buf + kWords, src + first, std::min<uint64_t>(rest, (uint64_t)kPad) * 4);
+    head.store(h + (uint64_t)n, std::memory_order_release);
+  }
+  void run() {
+    alignas(64) uint32_t out[624];
+    mt_temper_only(key, out);
+    if (pos0 < 624) put(out + pos0, 624 - pos0);
+    int64_t twists = 0;
+    for (;;) {
+      int spins = 0;
+      while (head.load(std::memory_order_relaxed) + 624 + kPad > tail.load(std::memory_order_acquire) + kWords) {
+        if (stop.load(std::memory_order_relaxed)) return;
+        if (++spins > 256) { std::this_thread::yield(); spins = 0; } else { cpu_relax(); }
+      }
+      if (stop.load(std::memory_order_relaxed)) return;
+      mt_refill(key, out);
+      ++twists;
+      if (twists % kSnapEvery == 0) snaps.insert(snaps.end(), key, key + 624);
+      put(out, 624);
+    }
+  }
+  // generator state after `consumed` outputs, in numpy's convention (pos in [0, 624])
+  void finish(uint64_t consumed, uint32_t* key_out, int32_t* pos_out) {
+    stop.store(true, std::memory_order_relaxed);
+    th.join();
+    const uint64_t q = (uint64_t)pos0 + consumed;
+    int64_t twists = q <= 624 ? 0 : (int64_t)((q - 1) / 624);
+    const int64_t s = twists / kSnapEvery;
+    memcpy(key_out, snaps.data() + (size_t)s * 624, 624 * sizeof(uint32_t));
+    alignas(64) uint32_t scratch[624];
+    for (int64_t k = s * kSnapEvery; k < twists; ++k) mt_refill(key_out, scratch);
+    *pos_out = (int32_t)(q - (uint64_t)twists * 624);
+    free(buf);
+    buf = nullptr;
+  }
+};
+
+// consumer view of the ring
+struct StreamReader {
+  StreamRing& r;
+  uint64_t t = 0;            // next output to consume
+  uint64_t avail = 0;        // cached head
+  explicit StreamReader(StreamRing& ring) : r(ring) {}
+  inline const uint32_t* at(uint64_t i) const { return r.buf + (i & StreamRing::kMask); }
+  inline void need(uint64_t n) {                     // outputs [t, t + n) produced?  (n <= kPad for window reads)
+    if (__builtin_expect(t + n <= avail, 1)) return;
+    for (;;) {
+      avail = r.head.load(std::memory_order_acquire);
+      if (t + n <= avail) return;
+      cpu_relax();
+    }
+  }
+  inline void release(uint64_t upto) { r.tail.store(upto, std::memory_order_release); }
+  inline uint32_t masked(uint32_t rr, uint32_t mask) {          // random_interval(rr), rr > 0
+    for (;;) {
+      need(1);
+      const uint32_t v = *at(t++) & mask;
+      if (v <= rr) return v;
+    }
+  }
+};
+
+}  // namespace
+
+int recad_mt19937_pairwise_soa(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items, int64_t train_size,
+                               const int64_t* allpos_rowptr, const int32_t* allpos_col, const uint64_t* filter,
+                               const uint32_t* ext, int32_t n_threads, uint32_t* users, uint32_t* rel, uint32_t* negs,
+                               int64_t* n_out, uint32_t* j_out) {
+  if (!key || !pos || !allpos_rowptr || !filter || !ext || !users || !rel || !negs || !n_out || n_users <= 0 || n_items <= 0 ||
+      train_size < 0 || n_users > 0x7fffffffLL || n_items > 0x7fffffffLL || train_size > 0x7fffffffLL || *pos < 0 || *pos > 624) {
+    recad::set_error("mt19937_pairwise_soa: bad argument");
+    return RECAD_ERR_ARG;
+  }
+  const bool trace = getenv("RECAD_SAMPLER_TRACE") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[sampler2] %s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  };
+  static std::mutex scratch_mutex;                           // one epoch of a stream at a time (they are chained anyway)
+  static Scratch<uint32_t> len_buf, deg_buf;
+  std::lock_guard<std::mutex> scratch_lock(scratch_mutex);
+  uint32_t* len32 = len_buf.get(train_size);
+  uint32_t* deg = deg_buf.get(n_users);
+  if (!len32 || !deg) {
+    recad::set_error("mt19937_pairwise_soa: out of host memory");
+    return RECAD_ERR_ARG;
+  }
+  StreamRing ring;
+  if (!ring.start(key, *pos)) {
+    recad::set_error("mt19937_pairwise_soa: out of host memory");
+    return RECAD_ERR_ARG;
+  }
+  StreamReader rd(ring);
+  auto fail = [&](int rc) { ring.finish(0, key, pos); return rc; };   // leaves key / pos as they were
+  // row lengths (4 MB at 10^6 users: cache resident for the gather below); the producer fills the ring meanwhile
+  for (int64_t u = 0; u < n_users; ++u) deg[u] = (uint32_t)(allpos_rowptr[u + 1] - allpos_rowptr[u]);
+  // ---- helper pool: first the length gather (chunks of the user array as they are drawn), then the block checks
+  const int n_help = getenv("RECAD_SAMPLER_HELPERS") ? std::max(1, atoi(getenv("RECAD_SAMPLER_HELPERS")))
+                                                     : (int)std::max(1, std::min(n_threads / 2 - 1, 7));
+  constexpr int64_t kChunk = 1 << 15;
+  const int64_t n_chunks = (train_size + kChunk - 1) / kChunk;
+  std::atomic<int64_t> users_ready{0};            // users [0, users_ready) are drawn
+  std::atomic<int64_t> next_chunk{0}, chunks_done{0};
+  std::vector<std::atomic<uint8_t>> chunk_done((size_t)std::max<int64_t>(n_chunks, 1));
+  for (auto& c : chunk_done) c.store(0, std::memory_order_relaxed);
+  const int64_t kBlock = getenv("RECAD_SAMPLER_BLOCK") ? atoll(getenv("RECAD_SAMPLER_BLOCK")) : 512;   // power of two
+  constexpr int64_t kAhead = 16;
+  const uint64_t kStreamAhead = getenv("RECAD_SAMPLER_PF") ? (uint64_t)atoll(getenv("RECAD_SAMPLER_PF")) : 512;
+  constexpr uint32_t kDropped = 0xffffffffu;
+  constexpr int64_t kNoFail = INT64_MAX;
+  const uint32_t neg_r = (uint32_t)(n_items - 1), neg_mask = MT::mask_of(neg_r);
+  auto is_positive = [&](const uint64_t* f, int64_t lo, int64_t len, uint32_t neg) -> bool {
+    const uint32_t a = probe_a(neg);
+    if (!((f[a >> 6] >> (a & 63)) & 1ull)) return false;
+    uint32_t b, c;
+    probes_bc(neg, len <= kLight, b, c);
+    if (!((f[b >> 6] >> (b & 63)) & (f[c >> 6] >> (c & 63)) & 1ull)) return false;
+    if (len > kHeavy) {
+      const uint64_t nbits = (uint64_t)len * 32;
+      const uint64_t p0 = ext_probe(neg, 0, nbits), p1 = ext_probe(neg, 1, nbits), p2 = ext_probe(neg, 2, nbits);
+      if (!((ext[lo + (p0 >> 5)] >> (p0 & 31)) & (ext[lo + (p1 >> 5)] >> (p1 & 31)) & (ext[lo + (p2 >> 5)] >> (p2 & 31)) & 1u))
+        return false;
+    }
+    return std::binary_search(allpos_col + lo, allpos_col + lo + len, (int32_t)neg);
+  };
+  auto check = [&](int64_t a0, int64_t a1) -> int64_t {     // first sample of [a0, a1) whose candidate is a positive
+    for (int64_t k = a0; k < std::min(a1, a0 + kAhead); ++k) __builtin_prefetch(filter + (int64_t)users[k] * kFilterWords);
+    for (int64_t k = a0; k < a1; ++k) {
+      if (k + kAhead < a1) __builtin_prefetch(filter + (int64_t)users[k + kAhead] * kFilterWords);
+      if (rel[k] == kDropped) continue;
+      const uint64_t* f = filter + (int64_t)users[k] * kFilterWords;
+      if (__builtin_expect(is_positive(f, (int64_t)(f[0] & (((uint64_t)1 << 40) - 1)), (int64_t)(f[0] >> 40), negs[k]), 0)) return k;
+    }
+    return kNoFail;
+  };
+  struct alignas(64) Slot { std::atomic<int64_t> fail; };
+  std::vector<Slot> slots((size_t)n_help + 1);
+  std::atomic<int64_t> go{0}, done{0};
+  std::atomic<bool> quit{false};
+  int64_t job_lo = 0, job_hi = 0;
+  std::vector<std::thread> helpers;
+  for (int t = 1; t <= n_help; ++t)
+    helpers.emplace_back([&, t]() {
+      // phase 1: lengths
+      for (;;) {
+        const int64_t c = next_chunk.load(std::memory_order_relaxed);
+        if (c >= n_chunks) break;
+        const int64_t hi = std::min(train_size, (c + 1) * kChunk);
+        if (users_ready.load(std::memory_order_acquire) < hi) {
+          if (quit.load(std::memory_order_relaxed)) return;
+          cpu_relax();
+          continue;
+        }
+        int64_t mine = c;
+        if (!next_chunk.compare_exchange_strong(mine, c + 1, std::memory_order_relaxed)) continue;
+        for (int64_t k = c * kChunk; k < hi; ++k) len32[k] = deg[users[k]];
+        chunk_done[(size_t)c].store(1, std::memory_order_release);
+        chunks_done.fetch_add(1, std::memory_order_release);
+      }
+      // phase 2: checks
+      int64_t seen = 0;
+      for (;;) {
+        int spins = 0;
+        while (go.load(std::memory_order_acquire) == seen) {
+          if (quit.load(std::memory_order_relaxed)) return;
+          if (++spins > 4000) { std::this_thread::yield(); spins = 0; } else { cpu_relax(); }
+        }
+        ++seen;
+        const int64_t n = job_hi - job_lo, per = (n + n_help - 1) / n_help;
+        const int64_t a0 = std::min(job_hi, job_lo + (t - 1) * per), a1 = std::min(job_hi, a0 + per);
+        slots[(size_t)t].fail.store(check(a0, a1), std::memory_order_relaxed);
+        done.fetch_add(1, std::memory_order_release);
+      }
+    });
+  auto stop_helpers = [&]() {
+    quit.store(true, std::memory_order_relaxed);
+    for (auto& h : helpers) h.join();
+  };
+  // ---- users: np.random.randint(0, n_users, train_size), one vector call (implicit.py:57); branch-free cursor
+  {
+    const uint32_t r = (uint32_t)(n_users - 1), mask = MT::mask_of(r);
+    if (r == 0) {
+      memset(users, 0, (size_t)train_size * sizeof(uint32_t));
+      users_ready.store(train_size, std::memory_order_release);
+    } else {
+      int64_t k = 0, published = 0;
+      while (k < train_size) {
+        rd.need(1);
+        uint64_t span = std::min<uint64_t>(rd.avail - rd.t, (uint64_t)(train_size - k));
+        span = std::min<uint64_t>(span, StreamRing::kWords - (rd.t & StreamRing::kMask));      // contiguous part
+        const uint32_t* src = rd.at(rd.t);
+        for (uint64_t q = 0; q < span; ++q) {
+          const uint32_t v = src[q] & mask;
+          users[k] = v;
+          k += v <= r;
+        }
+        rd.t += span;
+        rd.release(rd.t);
+        if (k - published >= kChunk || k == train_size) {
+          users_ready.store(k, std::memory_order_release);
+          published = k;
+        }
+      }
+    }
+  }
+  lap("draw users");
+  while (chunks_done.load(std::memory_order_acquire) < n_chunks) cpu_relax();
+  lap("wait for the length gather");
+  // ---- parse
+  std::vector<uint32_t> tst_v((size_t)4 * kBlock);            // stream offset in front of each sample (ring of 4 blocks)
+  uint32_t* tst = tst_v.data();
+  const int64_t kTstMask = 4 * kBlock - 1;
+  int rc = RECAD_OK;
+  // optimistic draw of samples [k0, k1): position of the positive, first candidate the mask accepts.  The stream
+  // cursor and every pointer live in locals: the loop-carried chain is cursor -> 4 loads -> compares -> selects -> cursor
+  auto draw = [&](int64_t k0, int64_t k1) -> int {
+    uint64_t t = rd.t, avail = rd.avail;
+    const uint32_t* __restrict__ ringbuf = ring.buf;
+    const uint32_t* __restrict__ lens = len32;
+    uint32_t* __restrict__ rel_ = rel;
+    uint32_t* __restrict__ negs_ = negs;
+    uint32_t* __restrict__ tst_ = tst;
+    const uint32_t nr = neg_r, nm = neg_mask;
+    const int64_t tmask = kTstMask;
+    int rc_ = RECAD_OK;
+    for (int64_t k = k0; k < k1; ++k) {
+      tst_[k & tmask] = (uint32_t)t;
+      const uint32_t len = lens[k];
+      if (__builtin_expect(len == 0, 0)) { rel_[k] = kDropped; continue; }               // implicit.py:63-64
+      if (__builtin_expect((int64_t)len >= n_items, 0)) {
+        recad::set_error("mt19937_pairwise_soa: user %lld interacted with every item; negative sampling cannot terminate",
+                         (long long)users[k]);
+        rc_ = RECAD_ERR_ARG;
+        break;
+      }
+      const uint32_t r1 = len - 1, m1 = r1 ? 0xffffffffu >> __builtin_clz(r1) : 0u;
+      if (__builtin_expect(t + 4 > avail, 0)) {
+        rd.t = t;
+        rd.need(4);
+        avail = rd.avail;
+      }
+      const uint32_t* w = ringbuf + (t & StreamRing::kMask);
+      const uint32_t o0 = w[0], o1 = w[1], o2 = w[2], o3 = w[3];
+      const uint32_t a0 = o0 & m1, a1 = o1 & m1;
+      const bool none = r1 == 0, okA0 = a0 <= r1, okA1 = a1 <= r1;
+      const int cA = none ? 0 : (okA0 ? 1 : 2);
+      const uint32_t x0 = cA == 0 ? o0 : (cA == 1 ? o1 : o2), x1 = cA == 0 ? o1 : (cA == 1 ? o2 : o3);
+      const uint32_t b0 = x0 & nm, b1 = x1 & nm;
+      const bool okB0 = b0 <= nr, okB1 = b1 <= nr;
+      if (__builtin_expect((none | okA0 | okA1) & (okB0 | okB1) & (nr != 0), 1)) {
+        rel_[k] = none ? 0u : (okA0 ? a0 : a1);
+        negs_[k] = okB0 ? b0 : b1;
+        t += (uint64_t)(cA + (okB0 ? 1 : 2));
+        continue;
+      }
+      rd.t = t;
+      rel_[k] = r1 ? rd.masked(r1, m1) : 0u;
+      negs_[k] = nr ? rd.masked(nr, nm) : 0u;
+      t = rd.t;
+      avail = rd.avail;
+    }
+    rd.t = t;
+    return rc_;
+  };
+  int64_t inline_result = kNoFail;
+  bool pool_busy = false;
+  const bool dbg_nocheck = getenv("RECAD_SAMPLER_DEBUG_NOCHECK") != nullptr;   // timing experiments only: WRONG samples
+  auto start_check = [&](int64_t lo_, int64_t hi_) {
+    if (dbg_nocheck) { inline_result = kNoFail; pool_busy = false; return; }
+    if (hi_ - lo_ < 64) { inline_result = check(lo_, hi_); pool_busy = false; return; }
+    job_lo = lo_; job_hi = hi_;
+    done.store(0, std::memory_order_relaxed);
+    go.fetch_add(1, std::memory_order_release);
+    pool_busy = true;
+  };
+  int64_t wait_spins = 0;
+  auto finish_check = [&]() -> int64_t {
+    if (!pool_busy) return inline_result;
+    while (done.load(std::memory_order_acquire) < n_help) { cpu_relax(); ++wait_spins; }
+    int64_t first = kNoFail;
+    for (int t = 1; t <= n_help; ++t) first = std::min(first, slots[(size_t)t].fail.load(std::memory_order_relaxed));
+    pool_busy = false;
+    return first;
+  };
+  int64_t n_fix = 0, n_redrawn = 0, n_dropped = 0;
+  rc = draw(0, std::min(train_size, kBlock));
+  for (int64_t b0 = 0; b0 < train_size && rc == RECAD_OK; b0 += kBlock) {
+    // invariant: [b0, b1) is drawn and rd.t is the offset behind it
+    const int64_t b1 = std::min(train_size, b0 + kBlock), n1 = std::min(train_size, b1 + kBlock);
+    rd.release(rd.t - (uint64_t)(uint32_t)((uint32_t)rd.t - tst[b0 & kTstMask]));   // block b may still be rewound into
+    start_check(b0, b1);
+    if (b1 < train_size && (rc = draw(b1, n1))) { finish_check(); break; }      // speculative, under the check of block b
+    int64_t k = finish_check();
+    while (k != kNoFail) {
+      // sample k's candidate is one of its user's positives: redo it exactly from its own offset, then redraw what
+      // follows until the new trajectory meets the old one (same sample, same offset) or the drawn region ends
+      const uint64_t t_end_old = rd.t;
+      rd.t = rd.t - (uint64_t)(uint32_t)((uint32_t)rd.t - tst[k & kTstMask]);
+      {
+        const int64_t u = users[k];
+        const int64_t lo = allpos_rowptr[u], len = allpos_rowptr[u + 1] - lo;
+        const uint64_t* f = filter + u * kFilterWords;
+        const uint32_t r1 = (uint32_t)(len - 1), m1 = r1 ? 0xffffffffu >> __builtin_clz(r1) : 0u;
+        rel[k] = r1 ? rd.masked(r1, m1) : 0u;
+        uint32_t neg;
+        do { neg = neg_r ? rd.masked(neg_r, neg_mask) : 0u; } while (is_positive(f, lo, len, neg));
+        negs[k] = neg;
+      }
+      ++n_fix;
+      int64_t j = k + 1;
+      bool met = false;
+      for (; j < n1; ++j) {
+        if ((uint32_t)rd.t == tst[j & kTstMask]) { met = true; break; }
+        if ((rc = draw(j, j + 1))) break;
+        ++n_redrawn;
+      }
+      if (rc) break;
+      if (met) rd.t = t_end_old;
+      if (k + 1 < b1) {
+        start_check(k + 1, b1);
+        k = finish_check();
+      } else {
+        k = kNoFail;
+      }
+    }
+  }
+  stop_helpers();
+  if (rc) return fail(rc);
+  if (trace) fprintf(stderr, "[sampler2] %lld exact redos, %lld samples redrawn, %d helper threads, %lld wait spins\n", (long long)n_fix,
+                     (long long)n_redrawn, n_help, (long long)wait_spins);
+  lap("parse stream");
+  // users without positives are dropped (implicit.py:63-64): compact in place (rare)
+  int64_t w = train_size;
+  for (int64_t k = 0; k < train_size; ++k) n_dropped += rel[k] == kDropped;
+  if (n_dropped) {
+    w = 0;
+    for (int64_t k = 0; k < train_size; ++k) {
+      if (rel[k] == kDropped) continue;
+      users[w] = users[k]; rel[w] = rel[k]; negs[w] = negs[k];
+      ++w;
+    }
+    lap("drop users without positives");
+  }
+  if (j_out) {
+    // the draws of np.random.shuffle(arange(w)): j[i] = random_interval(i) for i = w-1 .. 1, band by band
+    for (int64_t i = w - 1; i > 0;) {
+      const uint32_t mask = MT::mask_of((uint64_t)i);
+      const int64_t band_lo = std::max<int64_t>((int64_t)(mask >> 1) + 1, 1);
+      while (i >= band_lo) {
+        rd.need(1);
+        uint64_t span = std::min<uint64_t>(rd.avail - rd.t, (uint64_t)(i - band_lo + 1));
+        span = std::min<uint64_t>(span, StreamRing::kWords - (rd.t & StreamRing::kMask));
+        const uint32_t* src = rd.at(rd.t);
+        for (uint64_t q = 0; q < span; ++q) {
+          const uint32_t v = src[q] & mask;
+          j_out[i] = v;
+          i -= (int64_t)v <= i;
+        }
+        rd.t += span;
+        rd.release(rd.t);
+      }
+    }
+    if (w > 0) j_out[0] = 0;
+    lap("shuffle draws");
+  }
+  *n_out = w;
+  ring.finish(rd.t, key, pos);
+  return RECAD_OK;
+}
+
+// perm = arange(n) with swap(perm[i], perm[j[i]]) for i = n-1 .. 1, 32-bit (n < 2^31)
+int recad_permutation_apply32(int64_t n, const uint32_t* j, int32_t* perm) {
+  if (!j || !perm || n < 0 || n > 0x7fffffffLL) {
+    recad::set_error("permutation_apply32: bad argument");
+    return RECAD_ERR_ARG;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int64_t i = 0; i < n; ++i) perm[i] = (int32_t)i;
+  constexpr int64_t kAhead = 64;
+  for (int64_t i = n - 1; i > 0; --i) {
+    if (i > kAhead) __builtin_prefetch(perm + j[i - kAhead], 1);
+    std::swap(perm[i], perm[j[i]]);
+  }
+  if (getenv("RECAD_SAMPLER_TRACE"))
+    fprintf(stderr, "[sampler2] shuffle swaps %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  return RECAD_OK;
+}
+
 int recad_mt19937_pointwise(uint32_t* key, int32_t* pos, int64_t n_dict_users, const int64_t* user_ids,
                             const int64_t* pos_rowptr, const int64_t* pos_items, const int64_t* pos_sorted,
                             int64_t n_items, int32_t ratio, int64_t* out) {
@@ -636,6 +1122,7 @@ int recad_mt19937_pointwise(uint32_t* key, int32_t* pos, int64_t n_dict_users, c
   }
   MT mt(key, *pos);
   int64_t w = 0;
+  std::vector<int64_t> left_scratch;
   for (int64_t k = 0; k < n_dict_users; ++k) {
     const int64_t lo = pos_rowptr[k], hi = pos_rowptr[k + 1], n = hi - lo, uid = user_ids[k];
     for (int64_t j = lo; j < hi; ++j) { out[3 * w] = uid; out[3 * w + 1] = pos_items[j]; out[3 * w + 2] = 1; ++w; }
@@ -651,6 +1138,20 @@ int recad_mt19937_pointwise(uint32_t* key, int32_t* pos, int64_t n_dict_users, c
       return RECAD_ERR_ARG;
     }
     const uint32_t rr = (uint32_t)(n_left - 1), mask = MT::mask_of(rr);
+    // `list(full_items - set(iids))` (implicit.py:86) is ascending only while CPython takes the copy-and-discard path
+    // of set_difference, i.e. while len(full) / 4 > len(set(iids)).  For denser users the difference is BUILT by
+    // inserting the surviving items, in ascending order, into a fresh hash table; when that table ends up smaller than
+    // n_items the values wrap around it and the list order is the table's slot order (setobject.c, CPython 3.8-3.13:
+    // LINEAR_PROBES 9, PERTURB_SHIFT 5, growth to 4 x used (2 x above 50000) when fill * 5 >= mask * 3).
+    const bool table_order = !((n_items >> 2) > n_distinct);
+    if (table_order) {
+      cpython_set_order(sp, n, n_items, left_scratch);
+      for (int64_t c = 0; c < n_neg; ++c) {
+        const int64_t r = rr ? (int64_t)mt.masked_with(rr, mask) : 0;
+        out[3 * w] = uid; out[3 * w + 1] = left_scratch[(size_t)r]; out[3 * w + 2] = 0; ++w;
+      }
+      continue;
+    }
     for (int64_t c = 0; c < n_neg; ++c) {
       const int64_t r = rr ? (int64_t)mt.masked_with(rr, mask) : 0;
       // r-th element of the ascending complement: r + #{distinct positives p_j with p_j - j <= r}

@@ -1,16 +1,24 @@
 // CSR SpMM fused with the LightGCN layer mean:  Y = A X,  Z = alpha * (C + A X).
-// (reference: recad/model/victim/lightgcn.py:99-111 `torch.sparse.mm` + stack + mean; the
-// autograd backward of the same lines is this kernel again because A_hat is symmetric.)
+// (reference: recad/model/victim/lightgcn.py:99-111 `torch.sparse.mm` + stack + mean; the autograd backward of the
+// same lines is this kernel again because A_hat is symmetric.)
 //
-// HBM-bound gather: per stored entry 8 B of (col, val) streamed + one D*4-byte row of X gathered.
-// Work unit = one warp per SEGMENT of a row (plan built by recad_spmm_plan): short rows are one
-// segment and write their result directly through the fused epilogue; long rows (popular items)
-// are cut into <= seg_len pieces whose partial sums are combined in fixed order by a second tiny
-// kernel, so the result is deterministic and no warp ever walks a 10^5-entry row alone.
-//
-// Inside a warp: the segment's (col, val) pairs are staged 32 at a time with one coalesced load
-// per lane and broadcast with shuffles; a row of X is covered by D/4 lanes with 128-bit loads, so
-// a warp load instruction fetches 32/(D/4) neighbour rows at once and UNR of them are in flight.
+// The product is a gather: per stored entry 8 bytes of (col, val) are streamed and one D*4-byte row of X is fetched.
+// On B200 the rows come out of L2 (the item table fits, the user table is made to fit block by block), so the bound
+// is L2 -> SM delivery, and the kernel is organised around not wasting any of it:
+//   * work unit = one warp per SEGMENT (at most 1024 entries of one row) taken from a PACKED plan: one 16-byte entry
+//     {first entry (64 bit), row, (slot + 1) << 11 | count}, loaded one segment ahead, so a segment starts with its
+//     bounds in registers instead of a plan -> row pointer -> entries chain of dependent loads;
+//   * the matrix is streamed as interleaved (col, val) pairs (`cv`, 8 bytes): the lanes that gather neighbour k load
+//     pair k themselves (a broadcast load out of L1) -- no shuffles, which were a third of the L1 data-pipe
+//     wavefronts of the first version (profiles/ncu_spmm_r01.md); the pairs of the next round are requested before
+//     the gathers of the current round are consumed;
+//   * a row of X is covered by D/4 lanes with 128-bit loads, UNR independent gathers in flight per lane;
+//   * the plan orders segments longest-first inside each group (no straggler warps at the tail) and may cut the item
+//     rows at L2-sized blocks of the user table, processed block by block (recad_b200.ops.PackedPlan);
+//   * a row with several segments is finished by whichever of its warps arrives LAST: partial sums are parked in
+//     `partials`, a per-row counter elects the last arriver, and it adds the partials in slot order -- deterministic,
+//     no second kernel, no second pass.
+// The sharded path's epilogue stores a finished row into the owner's NVLink-mapped staging block instead (kScatter).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -21,12 +29,6 @@ namespace recad {
 
 constexpr int kSpmmWarps = 8;  // warps per CTA
 
-template <int D>
-struct RowLanes {
-  static constexpr int LPR = D / 4;      // lanes per row (float4 each)
-  static constexpr int NPL = 32 / LPR;   // neighbour rows per warp-wide load
-};
-
 // Peer-memory epilogue of the sharded path (recad_spmm_scatter): row i of the product is not stored in a local
 // Y but sent to the rank that OWNS item i -- dst[i / slice] is that rank's staging block for this sender, mapped
 // into this process over NVLink (torch symmetric memory), so the partial sums travel while the SpMM still runs.
@@ -36,326 +38,266 @@ struct RowScatter {
   int32_t slice;
 };
 
-template <int D, bool kScatter = false>
-__device__ __forceinline__ void spmm_epilogue(int64_t row, int slot, int l, float4 y, float* Y, const float* C,
-                                              float* Z, float alpha, float* partials, const RowScatter* sc = nullptr) {  // Z may alias C
-  constexpr int LPR = D / 4;
-  if (slot >= 0) {
-    reinterpret_cast<float4*>(partials)[(int64_t)slot * LPR + l] = y;
-    return;
-  }
+struct SpmmArgs {
+  const int4* seg_meta;
+  int64_t n_seg;
+  const int2* cv;
+  const int2* row_mseg;   // per row: (first partial slot, number of segments); only read for multi-segment rows
+  int* row_cnt;           // per row arrival counter, zero between launches
+  float* partials;
+  const float* X;
+  float* Y;
+  const float* C;
+  float* Z;
+  float alpha;
+};
+
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& x) {
+  a.x = fmaf(w, x.x, a.x); a.y = fmaf(w, x.y, a.y); a.z = fmaf(w, x.z, a.z); a.w = fmaf(w, x.w, a.w);
+}
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+template <bool kScatter>
+__device__ __forceinline__ void store_row(const SpmmArgs& a, const RowScatter& sc, int64_t row, int nvec, int c, float4 y) {  // Z may alias C
   if (kScatter) {
-    const int owner = (int)(row / sc->slice);
-    reinterpret_cast<float4*>(sc->dst[owner])[(row - (int64_t)owner * sc->slice) * LPR + l] = y;
+    const int owner = (int)(row / sc.slice);
+    reinterpret_cast<float4*>(sc.dst[owner])[(row - (int64_t)owner * sc.slice) * nvec + c] = y;
     return;
   }
-  const int64_t o = row * LPR + l;
-  if (Y) reinterpret_cast<float4*>(Y)[o] = y;
-  if (Z) {
-    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (C) c = reinterpret_cast<const float4*>(C)[o];
-    float4 z;
-    z.x = alpha * (c.x + y.x);
-    z.y = alpha * (c.y + y.y);
-    z.z = alpha * (c.z + y.z);
-    z.w = alpha * (c.w + y.w);
-    reinterpret_cast<float4*>(Z)[o] = z;
+  const int64_t o = row * nvec + c;
+  if (a.Y) reinterpret_cast<float4*>(a.Y)[o] = y;
+  if (a.Z) {
+    float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.C) cv = reinterpret_cast<const float4*>(a.C)[o];
+    reinterpret_cast<float4*>(a.Z)[o] = make_float4(a.alpha * (cv.x + y.x), a.alpha * (cv.y + y.y), a.alpha * (cv.z + y.z),
+                                                    a.alpha * (cv.w + y.w));
   }
 }
 
-template <int D, int UNR, int MINB, bool kStreamX, bool kScatter = false>
-__global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
-spmm_seg_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const float* __restrict__ vals,
-                int64_t n_seg, int32_t seg_len, const int32_t* __restrict__ seg_row,
-                const int64_t* __restrict__ seg_lo, const int32_t* __restrict__ seg_slot,
-                const float* __restrict__ X, float* Y, const float* C, float* Z, float alpha, float* partials,
-                const __grid_constant__ RowScatter sc) {
-  constexpr int LPR = RowLanes<D>::LPR, NPL = RowLanes<D>::NPL;
-  static_assert(32 % (NPL * UNR) == 0, "unroll must divide the staged chunk");
-  const int lane = threadIdx.x & 31;
-  const int sub = lane / LPR;  // which neighbour of the NPL fetched together
-  const int l = lane % LPR;    // which float4 of the row
-  // persistent launch: the grid is sized to the resident-CTA capacity of the chip and every warp
-  // strides over the segment list, so occupancy stays full until the list is exhausted (a warp
-  // per segment leaves a CTA's slots idle while its longest row finishes)
-  const int64_t n_warps = (int64_t)gridDim.x * kSpmmWarps;
-  for (int64_t seg = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5); seg < n_seg; seg += n_warps) {
-  const int64_t row = seg_row[seg];
-  const int64_t lo = seg_lo[seg];
-  const int64_t hi = min(lo + (int64_t)seg_len, rowptr[row + 1]);
-  const int slot = seg_slot[seg];
-  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
-
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  // software pipeline on the (col, val) stream: the next 32 pairs are requested before the
-  // current 32 are consumed
-  int c_next = 0;
-  float v_next = 0.f;
-  if (lo + lane < hi) {
-    c_next = ld_stream(colidx + lo + lane);
-    v_next = ld_stream(vals + lo + lane);
+// after a partial sum was stored: true in every lane of the warp that arrived last for `row`
+__device__ __forceinline__ bool last_arriver(const SpmmArgs& a, int row, int lane, int2& ms) {
+  __threadfence();
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    ms = __ldg(a.row_mseg + row);
+    const int old = atomicAdd(a.row_cnt + row, 1);
+    last = old == ms.y - 1;
+    if (last) a.row_cnt[row] = 0;                 // ready for the next launch
   }
-  for (int64_t base = lo; base < hi; base += 32) {
-    const int c = c_next;
-    const float v = v_next;
-    const int64_t nb = base + 32 + lane;
-    if (nb < hi) {
-      c_next = ld_stream(colidx + nb);
-      v_next = ld_stream(vals + nb);
-    }
-    const int cnt = (int)min((int64_t)32, hi - base);
-    for (int j = 0; j < cnt; j += NPL * UNR) {
+  last = __shfl_sync(kFull, last, 0);
+  if (last) {
+    ms.x = __shfl_sync(kFull, ms.x, 0);
+    ms.y = __shfl_sync(kFull, ms.y, 0);
+    __threadfence();
+  }
+  return last != 0;
+}
+
+template <int D, int UNR, int MINB, bool kScatter>
+__global__ void __launch_bounds__(kSpmmWarps * 32, MINB)
+spmm_kernel(const __grid_constant__ SpmmArgs a, const __grid_constant__ RowScatter sc) {
+  constexpr int LPR = D / 4;               // lanes per row (float4 each)
+  constexpr int NPL = 32 / LPR;            // neighbour rows per warp-wide load
+  constexpr int R = NPL * UNR;             // entries per round
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int64_t n_warps = (int64_t)gridDim.x * kSpmmWarps;
+  int64_t seg = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5);
+  if (seg >= a.n_seg) return;
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(a.X);
+  int4 meta = __ldg(a.seg_meta + seg);
+  while (true) {
+    const int64_t next = seg + n_warps;
+    int4 meta_n = make_int4(0, 0, 0, 0);
+    if (next < a.n_seg) meta_n = __ldg(a.seg_meta + next);      // one segment ahead
+    const int64_t lo = (int64_t)(uint32_t)meta.x | ((int64_t)meta.y << 32);
+    const int row = meta.z;
+    const int cnt = meta.w & 2047;
+    const int slot = (int)((uint32_t)meta.w >> 11) - 1;
+    const int2* __restrict__ p = a.cv + lo + sub;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int2 nx[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) nx[u] = (u * NPL + sub < cnt) ? __ldg(p + u * NPL) : make_int2(0, 0);
+    for (int j = 0; j < cnt; j += R) {
       float4 x[UNR];
       float w[UNR];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
-        const int k = j + u * NPL + sub;
-        const int cc = __shfl_sync(kFull, c, k & 31);
-        w[u] = __shfl_sync(kFull, v, k & 31);
-        if (k < cnt) {
-          const uint32_t off = (uint32_t)cc * (uint32_t)LPR + (uint32_t)l;   // float4 units; checked < 2^32 on the host
-          x[u] = kStreamX ? ld_stream4(X4 + off) : __ldg(X4 + off);
-        } else {
-          x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          w[u] = 0.f;
+        w[u] = __int_as_float(nx[u].y);
+        x[u] = (j + u * NPL + sub < cnt) ? __ldg(X4 + ((uint32_t)nx[u].x * (uint32_t)LPR + (uint32_t)l))   // float4 units; < 2^32 checked on the host
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)                               // pairs of the next round, under the gathers
+        nx[u] = (j + R + u * NPL + sub < cnt) ? __ldg(p + j + R + u * NPL) : make_int2(0, 0);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) fma4(acc, w[u], x[u]);
+    }
+#pragma unroll
+    for (int o = 16; o >= LPR; o >>= 1) {
+      acc.x += __shfl_xor_sync(kFull, acc.x, o); acc.y += __shfl_xor_sync(kFull, acc.y, o);
+      acc.z += __shfl_xor_sync(kFull, acc.z, o); acc.w += __shfl_xor_sync(kFull, acc.w, o);
+    }
+    if (slot < 0) {
+      if (sub == 0) store_row<kScatter>(a, sc, row, LPR, l, acc);
+    } else {
+      if (sub == 0) reinterpret_cast<float4*>(a.partials)[(int64_t)slot * LPR + l] = acc;
+      int2 ms;
+      if (last_arriver(a, row, lane, ms)) {
+        // partial slots of the row in slot order (fixed association => deterministic), 4 loads in flight per lane
+        const float4* __restrict__ P4 = reinterpret_cast<const float4*>(a.partials);
+        const int s1 = ms.x + ms.y;
+        float4 a4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int s = ms.x + sub;
+        for (; s + 3 * NPL < s1; s += 4 * NPL) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) add4(a4[q], __ldcg(P4 + (int64_t)(s + q * NPL) * LPR + l));
         }
-      }
+        for (; s < s1; s += NPL) add4(a4[0], __ldcg(P4 + (int64_t)s * LPR + l));
+        float4 t = make_float4((a4[0].x + a4[1].x) + (a4[2].x + a4[3].x), (a4[0].y + a4[1].y) + (a4[2].y + a4[3].y),
+                               (a4[0].z + a4[1].z) + (a4[2].z + a4[3].z), (a4[0].w + a4[1].w) + (a4[2].w + a4[3].w));
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        acc.x = fmaf(w[u], x[u].x, acc.x);
-        acc.y = fmaf(w[u], x[u].y, acc.y);
-        acc.z = fmaf(w[u], x[u].z, acc.z);
-        acc.w = fmaf(w[u], x[u].w, acc.w);
+        for (int o = 16; o >= LPR; o >>= 1) {
+          t.x += __shfl_xor_sync(kFull, t.x, o); t.y += __shfl_xor_sync(kFull, t.y, o);
+          t.z += __shfl_xor_sync(kFull, t.z, o); t.w += __shfl_xor_sync(kFull, t.w, o);
+        }
+        if (sub == 0) store_row<kScatter>(a, sc, row, LPR, l, t);
       }
     }
-  }
-#pragma unroll
-  for (int o = 16; o >= LPR; o >>= 1) {
-    acc.x += __shfl_xor_sync(kFull, acc.x, o);
-    acc.y += __shfl_xor_sync(kFull, acc.y, o);
-    acc.z += __shfl_xor_sync(kFull, acc.z, o);
-    acc.w += __shfl_xor_sync(kFull, acc.w, o);
-  }
-  if (sub == 0) spmm_epilogue<D, kScatter>(row, slot, l, acc, Y, C, Z, alpha, partials, &sc);
+    if (next >= a.n_seg) break;
+    seg = next;
+    meta = meta_n;
   }
 }
 
-// rows with more than one segment: sum their partial slots in slot order, then the same epilogue
-template <int D, bool kScatter = false>
-__global__ void __launch_bounds__(kSpmmWarps * 32)
-spmm_fixup_kernel(int64_t n_mrow, const int32_t* __restrict__ mrow, const int32_t* __restrict__ mrow_lo,
-                  const float* __restrict__ partials, float* Y, const float* C, float* Z, float alpha,
-                  const __grid_constant__ RowScatter sc) {
-  constexpr int LPR = RowLanes<D>::LPR, NPL = RowLanes<D>::NPL;
-  const int64_t j = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5);
-  if (j >= n_mrow) return;
-  const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
-  const int s0 = mrow_lo[j], s1 = mrow_lo[j + 1];
-  const float4* __restrict__ P4 = reinterpret_cast<const float4*>(partials);
-  // a hot item row has thousands of slots: keep 4 loads in flight per lane (fixed association => deterministic)
-  float4 a4[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) a4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  int s = s0 + sub;
-  for (; s + 3 * NPL < s1; s += 4 * NPL) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 p = P4[(int64_t)(s + q * NPL) * LPR + l];
-      a4[q].x += p.x; a4[q].y += p.y; a4[q].z += p.z; a4[q].w += p.w;
-    }
-  }
-  for (; s < s1; s += NPL) {
-    const float4 p = P4[(int64_t)s * LPR + l];
-    a4[0].x += p.x; a4[0].y += p.y; a4[0].z += p.z; a4[0].w += p.w;
-  }
-  float4 acc = make_float4((a4[0].x + a4[1].x) + (a4[2].x + a4[3].x), (a4[0].y + a4[1].y) + (a4[2].y + a4[3].y),
-                           (a4[0].z + a4[1].z) + (a4[2].z + a4[3].z), (a4[0].w + a4[1].w) + (a4[2].w + a4[3].w));
-#pragma unroll
-  for (int o = 16; o >= LPR; o >>= 1) {
-    acc.x += __shfl_xor_sync(kFull, acc.x, o);
-    acc.y += __shfl_xor_sync(kFull, acc.y, o);
-    acc.z += __shfl_xor_sync(kFull, acc.z, o);
-    acc.w += __shfl_xor_sync(kFull, acc.w, o);
-  }
-  if (sub == 0) spmm_epilogue<D, kScatter>(mrow[j], -1, l, acc, Y, C, Z, alpha, nullptr, &sc);
-}
-
-// any D that is a multiple of 4 (<= 1024): a lane owns float4 columns lane, lane+32, ...
+// any D that is a multiple of 4 (<= 1024): a lane owns float4 columns lane, lane + 32, ...
 constexpr int kGenericMaxVec = 8;
 __global__ void __launch_bounds__(kSpmmWarps * 32)
-spmm_generic_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                    const float* __restrict__ vals, int64_t n_seg, int32_t seg_len,
-                    const int32_t* __restrict__ seg_row, const int64_t* __restrict__ seg_lo,
-                    const int32_t* __restrict__ seg_slot, const float* __restrict__ X, float* Y, const float* C,
-                    float* Z, float alpha, float* partials, int D) {
-  const int64_t seg = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5);
-  if (seg >= n_seg) return;
+spmm_generic_kernel(const __grid_constant__ SpmmArgs a, int D) {
   const int lane = threadIdx.x & 31;
   const int nvec = D / 4;
-  const int64_t row = seg_row[seg], lo = seg_lo[seg];
-  const int64_t hi = min(lo + (int64_t)seg_len, rowptr[row + 1]);
-  const int slot = seg_slot[seg];
-  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(X);
-  float4 acc[kGenericMaxVec];
+  const int64_t n_warps = (int64_t)gridDim.x * kSpmmWarps;
+  const float4* __restrict__ X4 = reinterpret_cast<const float4*>(a.X);
+  const RowScatter none{};
+  for (int64_t seg = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5); seg < a.n_seg; seg += n_warps) {
+    const int4 meta = __ldg(a.seg_meta + seg);
+    const int64_t lo = (int64_t)(uint32_t)meta.x | ((int64_t)meta.y << 32);
+    const int row = meta.z, cnt = meta.w & 2047, slot = (int)((uint32_t)meta.w >> 11) - 1;
+    float4 acc[kGenericMaxVec];
 #pragma unroll
-  for (int q = 0; q < kGenericMaxVec; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t base = lo; base < hi; base += 32) {
-    int c = 0;
-    float v = 0.f;
-    if (base + lane < hi) { c = colidx[base + lane]; v = vals[base + lane]; }
-    const int cnt = (int)min((int64_t)32, hi - base);
+    for (int q = 0; q < kGenericMaxVec; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = 0; k < cnt; ++k) {
-      const int cc = __shfl_sync(kFull, c, k);
-      const float w = __shfl_sync(kFull, v, k);
+      const int2 e = __ldg(a.cv + lo + k);
+      const float w = __int_as_float(e.y);
 #pragma unroll
       for (int q = 0; q < kGenericMaxVec; ++q) {
-        const int col4 = lane + q * 32;
-        if (col4 < nvec) {
-          const float4 x = __ldg(X4 + (int64_t)cc * nvec + col4);
-          acc[q].x = fmaf(w, x.x, acc[q].x); acc[q].y = fmaf(w, x.y, acc[q].y);
-          acc[q].z = fmaf(w, x.z, acc[q].z); acc[q].w = fmaf(w, x.w, acc[q].w);
-        }
+        const int c = lane + q * 32;
+        if (c < nvec) fma4(acc[q], w, __ldg(X4 + (int64_t)e.x * nvec + c));
+      }
+    }
+    if (slot < 0) {
+#pragma unroll
+      for (int q = 0; q < kGenericMaxVec; ++q)
+        if (lane + q * 32 < nvec) store_row<false>(a, none, row, nvec, lane + q * 32, acc[q]);
+      continue;
+    }
+#pragma unroll
+    for (int q = 0; q < kGenericMaxVec; ++q)
+      if (lane + q * 32 < nvec) reinterpret_cast<float4*>(a.partials)[(int64_t)slot * nvec + lane + q * 32] = acc[q];
+    int2 ms;
+    if (last_arriver(a, row, lane, ms)) {
+      const float4* __restrict__ P4 = reinterpret_cast<const float4*>(a.partials);
+#pragma unroll
+      for (int q = 0; q < kGenericMaxVec; ++q) {
+        const int c = lane + q * 32;
+        if (c >= nvec) continue;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = ms.x; s < ms.x + ms.y; ++s) add4(t, __ldcg(P4 + (int64_t)s * nvec + c));
+        store_row<false>(a, none, row, nvec, c, t);
       }
     }
   }
-#pragma unroll
-  for (int q = 0; q < kGenericMaxVec; ++q) {
-    const int col4 = lane + q * 32;
-    if (col4 >= nvec) continue;
-    const float4 y = acc[q];
-    if (slot >= 0) { reinterpret_cast<float4*>(partials)[(int64_t)slot * nvec + col4] = y; continue; }
-    const int64_t o = row * nvec + col4;
-    if (Y) reinterpret_cast<float4*>(Y)[o] = y;
-    if (Z) {
-      float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (C) cv = reinterpret_cast<const float4*>(C)[o];
-      reinterpret_cast<float4*>(Z)[o] = make_float4(alpha * (cv.x + y.x), alpha * (cv.y + y.y),
-                                                    alpha * (cv.z + y.z), alpha * (cv.w + y.w));
-    }
-  }
 }
 
-__global__ void __launch_bounds__(kSpmmWarps * 32)
-spmm_generic_fixup_kernel(int64_t n_mrow, const int32_t* __restrict__ mrow, const int32_t* __restrict__ mrow_lo,
-                          const float* __restrict__ partials, float* Y, const float* C, float* Z, float alpha,
-                          int D) {
-  const int64_t j = (int64_t)blockIdx.x * kSpmmWarps + (threadIdx.x >> 5);
-  if (j >= n_mrow) return;
-  const int lane = threadIdx.x & 31, nvec = D / 4;
-  const int64_t row = mrow[j];
-  for (int col4 = lane; col4 < nvec; col4 += 32) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = mrow_lo[j]; s < mrow_lo[j + 1]; ++s) {
-      const float4 p = reinterpret_cast<const float4*>(partials)[(int64_t)s * nvec + col4];
-      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
-    }
-    const int64_t o = row * nvec + col4;
-    if (Y) reinterpret_cast<float4*>(Y)[o] = acc;
-    if (Z) {
-      float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (C) cv = reinterpret_cast<const float4*>(C)[o];
-      reinterpret_cast<float4*>(Z)[o] = make_float4(alpha * (cv.x + acc.x), alpha * (cv.y + acc.y),
-                                                    alpha * (cv.z + acc.z), alpha * (cv.w + acc.w));
-    }
-  }
+__global__ void pack_cv_kernel(const int32_t* __restrict__ col, const float* __restrict__ val, int64_t nnz, int2* __restrict__ cv) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
+    cv[e] = make_int2(col[e], __float_as_int(val[e]));
 }
 
-// tuning knob (RECAD_SPMM_VARIANT): bit0 = persistent grid, bits 1-2 = register cap (0: none, 1: 6 CTAs/SM,
-// 2: 5 CTAs/SM, 3: 4 CTAs/SM), bit3 = deeper unroll.  The default is the variant measured fastest on B200 (profiles/).
-static int spmm_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RECAD_SPMM_VARIANT");
-    v = e ? atoi(e) : 5;
-  }
-  return v;
-}
-
-template <int D, int UNR, int MINB, bool kStreamX, bool kScatter = false>
-static int launch_spmm_v(const recad_csr* A, const float* X, float* Y, const float* C, float* Z, float alpha,
-                         bool persistent, cudaStream_t s, const RowScatter& sc = RowScatter{}) {
-  auto kern = spmm_seg_kernel<D, UNR, MINB, kStreamX, kScatter>;
-  int64_t grid = (A->n_seg + kSpmmWarps - 1) / kSpmmWarps;
-  if (persistent) {
-    static int per_sm = 0;
-    if (!per_sm) RECAD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSpmmWarps * 32, 0));
-    grid = std::min<int64_t>(grid, (int64_t)sm_count() * std::max(per_sm, 1));
-  }
-  kern<<<(unsigned)grid, kSpmmWarps * 32, 0, s>>>(A->rowptr, A->colidx, A->vals, A->n_seg, A->seg_len, A->seg_row,
-                                                 A->seg_lo, A->seg_slot, X, Y, C, Z, alpha, A->partials, sc);
+// measured on B200 (profiles/spmm2_sweep_r02.jsonl): 4 gathers in flight per lane, up to 64 registers (4 CTAs / SM)
+template <int D, bool kScatter>
+static int launch_spmm(const SpmmArgs& a, const RowScatter& sc, cudaStream_t s) {
+  auto kern = spmm_kernel<D, 4, 4, kScatter>;
+  static int per_sm = 0;
+  if (!per_sm) RECAD_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSpmmWarps * 32, 0));
+  // persistent launch: the grid is the resident-CTA capacity of the chip and every warp strides over the segment list
+  const int64_t grid = std::min<int64_t>((a.n_seg + kSpmmWarps - 1) / kSpmmWarps, (int64_t)sm_count() * std::max(per_sm, 1));
+  kern<<<(unsigned)grid, kSpmmWarps * 32, 0, s>>>(a, sc);
   RECAD_LAUNCH_CHECK();
   return RECAD_OK;
 }
 
-// Y = A X with every finished row sent to its owner (see RowScatter)
-template <int D, int UNR>
-static int launch_spmm_scatter(const recad_csr* A, const float* X, const RowScatter& sc, cudaStream_t s) {
-  int rc = launch_spmm_v<D, UNR, 5, false, true>(A, X, nullptr, nullptr, nullptr, 1.f, true, s, sc);
-  if (rc) return rc;
-  if (A->n_mrow > 0) {
-    const unsigned g2 = (unsigned)((A->n_mrow + kSpmmWarps - 1) / kSpmmWarps);
-    spmm_fixup_kernel<D, true><<<g2, kSpmmWarps * 32, 0, s>>>(A->n_mrow, A->mrow, A->mrow_lo, A->partials, nullptr, nullptr,
-                                                             nullptr, 1.f, sc);
-    RECAD_LAUNCH_CHECK();
-  }
+static int check_csr(const recad_csr* A, const char* who) {
+  RECAD_REQUIRE(A, RECAD_ERR_ARG, "%s: null matrix", who);
+  RECAD_REQUIRE(A->n_rows > 0 && A->n_seg >= A->n_rows && A->seg_meta, RECAD_ERR_ARG, "%s: matrix has no plan (ops.PackedPlan)", who);
+  RECAD_REQUIRE(A->nnz == 0 || A->cv, RECAD_ERR_ARG, "%s: null (col, val) pairs (recad_spmm_pack_cv)", who);
+  RECAD_REQUIRE(A->n_mrow == 0 || (A->row_mseg && A->row_cnt && A->partials), RECAD_ERR_ARG, "%s: null multi-segment plan", who);
   return RECAD_OK;
 }
 
-template <int D, int UNR>
-static int launch_spmm(const recad_csr* A, const float* X, float* Y, const float* C, float* Z, float alpha,
-                       cudaStream_t s) {
-  const int v = spmm_variant();
-  const bool pers = v & 1;
-  int rc;
-  switch ((v >> 1) & 3) {
-    case 0: rc = launch_spmm_v<D, UNR, 1, false>(A, X, Y, C, Z, alpha, pers, s); break;
-    case 1: rc = launch_spmm_v<D, UNR, 6, false>(A, X, Y, C, Z, alpha, pers, s); break;
-    case 2: rc = launch_spmm_v<D, UNR, 5, false>(A, X, Y, C, Z, alpha, pers, s); break;
-    default: rc = launch_spmm_v<D, UNR, 4, false>(A, X, Y, C, Z, alpha, pers, s); break;
-  }
-  if (rc) return rc;
-  if (A->n_mrow > 0) {
-    const unsigned g2 = (unsigned)((A->n_mrow + kSpmmWarps - 1) / kSpmmWarps);
-    spmm_fixup_kernel<D><<<g2, kSpmmWarps * 32, 0, s>>>(A->n_mrow, A->mrow, A->mrow_lo, A->partials, Y, C, Z, alpha, RowScatter{});
-    RECAD_LAUNCH_CHECK();
-  }
-  return RECAD_OK;
+static SpmmArgs make_args(const recad_csr* A, const float* X, float* Y, const float* C, float* Z, float alpha) {
+  SpmmArgs a;
+  a.seg_meta = reinterpret_cast<const int4*>(A->seg_meta);
+  a.n_seg = A->n_seg;
+  a.cv = reinterpret_cast<const int2*>(A->cv);
+  a.row_mseg = reinterpret_cast<const int2*>(A->row_mseg);
+  a.row_cnt = A->row_cnt;
+  a.partials = A->partials;
+  a.X = X; a.Y = Y; a.C = C; a.Z = Z; a.alpha = alpha;
+  return a;
 }
 
 }  // namespace recad
 
 using namespace recad;
 
+extern "C" int recad_spmm_pack_cv(const int32_t* colidx, const float* vals, int64_t nnz, void* cv, void* stream) {
+  RECAD_REQUIRE(nnz == 0 || (colidx && vals && cv), RECAD_ERR_ARG, "spmm_pack_cv: null pointer");
+  if (nnz == 0) return RECAD_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>((nnz + 255) / 256, (int64_t)sm_count() * 16);
+  pack_cv_kernel<<<grid, 256, 0, as_stream(stream)>>>(colidx, vals, nnz, reinterpret_cast<int2*>(cv));
+  RECAD_LAUNCH_CHECK();
+  return RECAD_OK;
+}
+
 extern "C" int recad_spmm(const recad_csr* A, const float* X, float* Y, const float* C, float* Z, float alpha,
                           int32_t D, void* stream) {
   cudaStream_t s = as_stream(stream);
-  RECAD_REQUIRE(A && X, RECAD_ERR_ARG, "spmm: null matrix or X");
+  int rc = check_csr(A, "spmm");
+  if (rc) return rc;
+  RECAD_REQUIRE(X, RECAD_ERR_ARG, "spmm: null X");
   RECAD_REQUIRE(Y || Z, RECAD_ERR_ARG, "spmm: neither Y nor Z requested");
-  RECAD_REQUIRE(A->n_rows > 0 && A->n_seg >= A->n_rows && A->rowptr && A->seg_row && A->seg_lo && A->seg_slot,
-                RECAD_ERR_ARG, "spmm: matrix has no plan (call recad_spmm_plan)");
-  RECAD_REQUIRE(A->nnz == 0 || (A->colidx && A->vals), RECAD_ERR_ARG, "spmm: null colidx/vals");
-  RECAD_REQUIRE(A->n_mrow == 0 || (A->mrow && A->mrow_lo && A->partials), RECAD_ERR_ARG, "spmm: null multi-row plan");
-  RECAD_REQUIRE((int64_t)2147483647 / (D / 4 > 0 ? D / 4 : 1) > 0, RECAD_ERR_ARG, "spmm: bad D");
   RECAD_REQUIRE(D >= 4 && D % 4 == 0 && D <= 4 * 32 * kGenericMaxVec, RECAD_ERR_UNSUPPORTED,
                 "spmm: D = %d must be a multiple of 4 in [4, %d]", D, 4 * 32 * kGenericMaxVec);
+  RECAD_REQUIRE(A->n_cols > 0 && A->n_cols * (int64_t)(D / 4) < ((int64_t)1 << 32), RECAD_ERR_OVERFLOW,
+                "spmm: %lld columns x D = %d exceed the 32-bit gather offset", (long long)A->n_cols, D);
   RECAD_REQUIRE((((uintptr_t)X | (uintptr_t)Y | (uintptr_t)C | (uintptr_t)Z | (uintptr_t)A->partials) & 15) == 0,
                 RECAD_ERR_ARG, "spmm: buffers must be 16-byte aligned");
+  const SpmmArgs a = make_args(A, X, Y, C, Z, alpha);
+  const RowScatter none{};
   switch (D) {
-    case 32: return launch_spmm<32, 2>(A, X, Y, C, Z, alpha, s);
-    case 64: return (spmm_variant() & 8) ? launch_spmm<64, 8>(A, X, Y, C, Z, alpha, s) : launch_spmm<64, 4>(A, X, Y, C, Z, alpha, s);
-    case 128: return launch_spmm<128, 8>(A, X, Y, C, Z, alpha, s);
+    case 32: return launch_spmm<32, false>(a, none, s);
+    case 64: return launch_spmm<64, false>(a, none, s);
+    case 128: return launch_spmm<128, false>(a, none, s);
     default: break;
   }
-  const unsigned grid = (unsigned)((A->n_seg + kSpmmWarps - 1) / kSpmmWarps);
-  spmm_generic_kernel<<<grid, kSpmmWarps * 32, 0, s>>>(A->rowptr, A->colidx, A->vals, A->n_seg, A->seg_len, A->seg_row,
-                                                      A->seg_lo, A->seg_slot, X, Y, C, Z, alpha, A->partials, D);
+  const int64_t grid = std::min<int64_t>((A->n_seg + kSpmmWarps - 1) / kSpmmWarps, (int64_t)sm_count() * 8);
+  spmm_generic_kernel<<<(unsigned)grid, kSpmmWarps * 32, 0, s>>>(a, D);
   RECAD_LAUNCH_CHECK();
-  if (A->n_mrow > 0) {
-    const unsigned g2 = (unsigned)((A->n_mrow + kSpmmWarps - 1) / kSpmmWarps);
-    spmm_generic_fixup_kernel<<<g2, kSpmmWarps * 32, 0, s>>>(A->n_mrow, A->mrow, A->mrow_lo, A->partials, Y, C, Z,
-                                                            alpha, D);
-    RECAD_LAUNCH_CHECK();
-  }
   return RECAD_OK;
 }
 
@@ -395,14 +337,15 @@ peer_reduce_bcast_kernel(const float4* stage, int n_src, int64_t stride4, int64_
 extern "C" int recad_spmm_scatter(const recad_csr* A, const float* X, float* const* dst, int32_t n_dst, int64_t slice_rows,
                                   int32_t D, void* stream) {
   cudaStream_t s = as_stream(stream);
-  RECAD_REQUIRE(A && X && dst, RECAD_ERR_ARG, "spmm_scatter: null argument");
-  RECAD_REQUIRE(A->n_rows > 0 && A->n_seg >= A->n_rows && A->rowptr && A->seg_row && A->seg_lo && A->seg_slot,
-                RECAD_ERR_ARG, "spmm_scatter: matrix has no plan (call recad_spmm_plan)");
-  RECAD_REQUIRE(A->n_mrow == 0 || (A->mrow && A->mrow_lo && A->partials), RECAD_ERR_ARG, "spmm_scatter: null multi-row plan");
+  int rc = check_csr(A, "spmm_scatter");
+  if (rc) return rc;
+  RECAD_REQUIRE(X && dst, RECAD_ERR_ARG, "spmm_scatter: null argument");
   RECAD_REQUIRE(n_dst >= 1 && n_dst <= kMaxPeers && slice_rows > 0 && slice_rows < ((int64_t)1 << 31) &&
                     slice_rows * n_dst >= A->n_rows,
                 RECAD_ERR_ARG, "spmm_scatter: %d destinations of %lld rows do not cover %lld rows", n_dst,
                 (long long)slice_rows, (long long)A->n_rows);
+  RECAD_REQUIRE(A->n_cols > 0 && A->n_cols * (int64_t)(D / 4) < ((int64_t)1 << 32), RECAD_ERR_OVERFLOW,
+                "spmm_scatter: gather offset overflow");
   RowScatter sc{};
   sc.slice = (int32_t)slice_rows;
   for (int r = 0; r < n_dst; ++r) {
@@ -410,10 +353,11 @@ extern "C" int recad_spmm_scatter(const recad_csr* A, const float* X, float* con
     sc.dst[r] = dst[r];
   }
   RECAD_REQUIRE((((uintptr_t)X | (uintptr_t)A->partials) & 15) == 0, RECAD_ERR_ARG, "spmm_scatter: buffers must be 16-byte aligned");
+  const SpmmArgs a = make_args(A, X, nullptr, nullptr, nullptr, 1.f);
   switch (D) {
-    case 32: return launch_spmm_scatter<32, 2>(A, X, sc, s);
-    case 64: return launch_spmm_scatter<64, 4>(A, X, sc, s);
-    case 128: return launch_spmm_scatter<128, 8>(A, X, sc, s);
+    case 32: return launch_spmm<32, true>(a, sc, s);
+    case 64: return launch_spmm<64, true>(a, sc, s);
+    case 128: return launch_spmm<128, true>(a, sc, s);
     default: break;
   }
   RECAD_REQUIRE(false, RECAD_ERR_UNSUPPORTED, "spmm_scatter: D = %d (supported: 32, 64, 128)", D);

@@ -129,14 +129,61 @@ class _EpochPipe:
         ref = weakref.ref(self)
         atexit.register(lambda: ref() is not None and ref()._flush())
 
+    def _soa(self, cuda):
+        """Large pairwise epochs take the 32-bit structure-of-arrays path: the host sampler emits (user, index of the
+        positive, negative) as uint32, the positive ITEM is gathered on the device, rows and permutation stay int32."""
+        d = self.data
+        return (cuda and d.config["sample"] == "pairwise" and d.traindataSize >= ops.FAST_SAMPLER_MIN
+                and d.traindataSize < (1 << 31) and d.n_users < (1 << 31) and d.n_items < (1 << 31))
+
     def _buffers(self, slot, cuda):
         n = self.data.traindataSize * (1 if self.data.config["sample"] == "pairwise" else 1 + self.data.config["negative_ratio"])
-        if self.bufs[slot] is None or self.bufs[slot][0].shape[0] < n:
-            s, p = torch.empty((max(n, 1), 3), dtype=torch.int64), torch.empty(max(n, 1), dtype=torch.int64)
-            if cuda:
-                s, p = s.pin_memory(), p.pin_memory()
-            self.bufs[slot] = (s, p, ops.host_empty(max(n, 1), np.uint32))
+        soa = self._soa(cuda)
+        if self.bufs[slot] is None or self.bufs[slot][-1].shape[0] < n or self.bufs[slot][0] != soa:
+            if soa:
+                host = [torch.empty(max(n, 1), dtype=torch.int32).pin_memory() for _ in range(4)]   # users, rel, negs, perm
+                self.bufs[slot] = (True, *host, ops.host_empty(max(n, 1), np.uint32))
+            else:
+                s, p = torch.empty((max(n, 1), 3), dtype=torch.int64), torch.empty(max(n, 1), dtype=torch.int64)
+                if cuda:
+                    s, p = s.pin_memory(), p.pin_memory()
+                self.bufs[slot] = (False, s, p, ops.host_empty(max(n, 1), np.uint32))
         return self.bufs[slot]
+
+    def _draw_into(self, slot, cuda, key, pos, after_rng=None):
+        """Sampler + shuffle of one epoch from an explicit generator state into the slot's host buffers."""
+        d = self.data
+        buf = self._buffers(slot, cuda)
+        if buf[0]:
+            _, u, r, g, p, jb = buf
+            un, rn, gn = (t.numpy().view(np.uint32) for t in (u, r, g))
+            m = ops.mt_pairwise_soa_raw(key, pos, d.n_users, d.n_items, d.traindataSize, *d._allpos, un, rn, gn, jb)
+            if after_rng is not None:
+                after_rng()
+            ops.permutation_apply32(jb[:m], p.numpy())
+            return ("soa", u[:m], r[:m], g[:m], p[:m])
+        _, s, p, jb = buf
+        if d.config["sample"] == "pairwise":          # sampler + shuffle draws in one call (draws under the row gather)
+            S, j = ops.mt_pairwise_epoch_raw(key, pos, d.n_users, d.n_items, d.traindataSize, *d._allpos, out=s.numpy(), j_out=jb)
+        else:
+            S = d._draw_samples(key, pos, s.numpy())
+            j = ops.mt_permutation_draw_raw(key, pos, len(S), jb)
+        if after_rng is not None:
+            after_rng()
+        perm = ops.permutation_apply(j, p.numpy())
+        return ("rows", s[:len(S)], p[:len(perm)])
+
+    def _to_device(self, got, device):
+        if got[0] == "soa":
+            _, u, r, g, p = got
+            ud, rd, gd, pd = (t.to(device, non_blocking=True) for t in (u, r, g, p))
+            rows = torch.empty((int(u.shape[0]), 3), dtype=torch.int32, device=device)
+            ops.samples_expand(*self.data.allpos_device(device), ud, rd, gd, rows)
+            return rows, pd
+        _, s, p = got
+        if device.type == "cuda":
+            return s.to(device, non_blocking=True), p.to(device, non_blocking=True)
+        return s.clone(), p.clone()           # host "device" (CPU-only tests): detach from the reusable buffers
 
     def _free_slot(self):
         used = {j.slot for j in self.queue} | {self.last_slot}
@@ -151,17 +198,11 @@ class _EpochPipe:
                 job.start_key, job.start_pos = job.prev.end_key.copy(), int(job.prev.end_pos)
                 job.prev = None
             key, pos = job.start_key.copy(), [int(job.start_pos)]
-            s, p, jb = self._buffers(job.slot, cuda)
-            d = self.data
-            if d.config["sample"] == "pairwise":          # sampler + shuffle draws in one call (draws under the row gather)
-                S, j = ops.mt_pairwise_epoch_raw(key, pos, d.n_users, d.n_items, d.traindataSize, *d._allpos, out=s.numpy(), j_out=jb)
-            else:
-                S = d._draw_samples(key, pos, s.numpy())
-                j = ops.mt_permutation_draw_raw(key, pos, len(S), jb)
-            job.end_key, job.end_pos = key, int(pos[0])
-            job.rng_done.set()                                  # the next epoch's sampler may start now
-            perm = ops.permutation_apply(j, p.numpy())
-            job.out = (s[:len(S)], p[:len(perm)])
+
+            def rng_done():
+                job.end_key, job.end_pos = key, int(pos[0])
+                job.rng_done.set()                              # the next epoch's sampler may start now
+            job.out = self._draw_into(job.slot, cuda, key, pos, after_rng=rng_done)
         except BaseException as e:   # noqa: BLE001 -- reported by falling back to the synchronous draw
             job.error = e
         finally:
@@ -198,15 +239,9 @@ class _EpochPipe:
         if got is None:
             key, pos = np.ascontiguousarray(st[1], dtype=np.uint32).copy(), [int(st[2])]
             slot = self._free_slot()
-            s, p, jb = self._buffers(slot, cuda)
-            S, perm = self.data._draw_epoch(key, pos, (s.numpy(), p.numpy()))
-            got, self.last_slot = (s[:len(S)], p[:len(perm)]), slot
+            got, self.last_slot = self._draw_into(slot, cuda, key, pos), slot
         np.random.set_state((st[0], key, int(pos[0]), st[3], st[4]))
-        if cuda:
-            s_dev = got[0].to(device, non_blocking=True)
-            p_dev = got[1].to(device, non_blocking=True)
-        else:                                   # host "device" (CPU-only tests): detach from the reusable buffers
-            s_dev, p_dev = got[0].clone(), got[1].clone()
+        s_dev, p_dev = self._to_device(got, device)
         self.calls += 1
         # speculate only once the caller has come back for a second epoch: a dataset that lives for ONE epoch (the
         # attacked copy of an attack iteration) would otherwise leave two useless epochs running in the background,
@@ -327,6 +362,12 @@ class ImplicitData:
         ptr, idx = self._allpos
         return [idx[ptr[u]:ptr[u + 1]] for u in users]
 
+    def allpos_device(self, device):
+        """allPos (implicit.py:300-302) as a CSR on the device: (rowptr int64 [n_users + 1], col int32)."""
+        if getattr(self, "_allpos_dev", None) is None or self._allpos_dev[0].device != device:
+            self._allpos_dev = tuple(torch.from_numpy(np.ascontiguousarray(a)).to(device) for a in self._allpos)
+        return self._allpos_dev
+
     def train_csr(self, device=None):
         """Sorted distinct train items per user id (mask of normal_evaluate, normal.py:133-143):
         (rowptr int64 [n_users + 1], col int32) on `device`."""
@@ -409,7 +450,7 @@ class ImplicitData:
         c = self.config
         if self.mode() == "train":
             samples, perm = self.epoch_samples()
-            S = samples[perm]                              # compatibility path only: materialise the shuffle
+            S = samples[perm.long()].long()                # compatibility path only: materialise the shuffle
             if c["sample"] == "pairwise":
                 names, bs = ("users", "positive_items", "negative_items"), c["pairwise_batch_size"]
             else:
@@ -536,6 +577,9 @@ class ArrayImplicitData:
     _draw_samples = ImplicitData._draw_samples
     _draw_epoch = ImplicitData._draw_epoch
     generate_batch = ImplicitData.generate_batch
+
+    def allpos_device(self, device):
+        return tuple(t.to(device) for t in self._train_csr_dev)
 
     def train_csr(self, device=None):
         if device is None:

@@ -61,16 +61,123 @@ def d_inv_from_degree(degree):
     return d_inv
 
 
+def auto_col_blocks(n_cols, row_bytes=256):
+    """Column blocks for rows that gather from a table of n_cols rows: one block while the table fits the 126 MB L2
+    next to the streamed matrix, else ~80 MB blocks (measured on B200: 2-4 blocks of the 256 MB user table are equally
+    fast, profiles/spmm2_sweep_r02.jsonl)."""
+    nbytes = int(n_cols) * row_bytes
+    return 1 if nbytes <= 100e6 else max(2, int(round(nbytes / 80e6)))
+
+
+class PackedPlan:
+    """Work list of the SpMM (csrc/spmm.cu): one 16-byte entry per SEGMENT {lo (64 bit), row, (slot + 1) << 11 | count}.
+    `groups` = [(row_lo, row_hi, col_lo, col_hi, n_blocks)] partitions the rows; the rows of a group gather columns in
+    [col_lo, col_hi) and are cut at n_blocks equal column blocks, their segments ordered block by block, so that the
+    gathered slice of X (an L2-sized block of the user table) stays cache resident while it is in use; inside a
+    (group, block) the segments go longest first (no straggler warps at the tail of the persistent kernel).  A row
+    with more than one segment gets consecutive partial-sum slots in (row, first entry) order; its last-arriving warp
+    adds them in that order (deterministic).
+    Plain index arithmetic on torch tensors (runs wherever the row pointer lives): executed once per graph, the hot
+    path only reads its output."""
+
+    MAX_SEG = 1024
+
+    def __init__(self, meta, row_mseg, n_mrow, n_slot, group_segs):
+        self.meta, self.row_mseg, self.n_mrow, self.n_slot, self.group_segs = meta, row_mseg, int(n_mrow), int(n_slot), group_segs
+        self.n_seg = int(meta.shape[0])
+
+    @classmethod
+    def build(cls, rowptr, colidx, n_rows, seg_len, groups=None):
+        if not (0 < seg_len <= cls.MAX_SEG):
+            raise RecadError(f"PackedPlan: seg_len must be in (0, {cls.MAX_SEG}]")
+        dev = rowptr.device
+        i64 = dict(dtype=torch.int64, device=dev)
+        rowptr = rowptr.long()
+        if groups is None:
+            groups = [(0, n_rows, 0, 1 << 31, 1)]
+        assert groups[0][0] == 0 and groups[-1][1] == n_rows and all(a[1] == b[0] for a, b in zip(groups, groups[1:]))
+        # pieces = (row, lo, hi, order key): one piece per (row, column block)
+        p_row, p_lo, p_hi, p_grp = [], [], [], []
+        gkey = 0
+        for (r0, r1, c0, c1, nb) in groups:
+            rows = torch.arange(r0, r1, **i64)
+            if nb <= 1 or r1 == r0:
+                p_row.append(rows); p_lo.append(rowptr[r0:r1]); p_hi.append(rowptr[r0 + 1:r1 + 1])
+                p_grp.append(torch.full((r1 - r0,), gkey, **i64))
+                gkey += 1
+                continue
+            e0, e1 = int(rowptr[r0]), int(rowptr[r1])
+            erow = torch.repeat_interleave(rows, rowptr[r0 + 1:r1 + 1] - rowptr[r0:r1])
+            key = (erow << 32) | colidx[e0:e1].long()                       # ascending: CSR is (row, col) sorted
+            bounds = torch.tensor([c0 + (b * (c1 - c0)) // nb for b in range(1, nb)], **i64)
+            q = (rows[:, None] << 32) | bounds[None, :]
+            cut = torch.searchsorted(key, q.reshape(-1)).reshape(-1, nb - 1) + e0
+            edges = torch.cat([rowptr[r0:r1, None], cut, rowptr[r0 + 1:r1 + 1, None]], 1)   # [rows, nb + 1]
+            lo_b, hi_b = edges[:, :-1], edges[:, 1:]
+            keep = hi_b > lo_b
+            keep[:, 0] |= ~keep.any(1)                                       # an empty row is still written once
+            grp_b = (gkey + torch.arange(nb, **i64))[None, :].expand_as(lo_b)
+            p_row.append(rows[:, None].expand_as(lo_b)[keep]); p_lo.append(lo_b[keep]); p_hi.append(hi_b[keep])
+            p_grp.append(grp_b[keep])
+            gkey += nb
+        p_row, p_lo, p_hi, p_grp = (torch.cat(x) for x in (p_row, p_lo, p_hi, p_grp))
+        # pieces -> segments of at most seg_len entries
+        nch = torch.clamp((p_hi - p_lo + seg_len - 1) // seg_len, min=1)
+        first = torch.cumsum(nch, 0) - nch
+        n_seg = int(nch.sum())
+        piece = torch.repeat_interleave(torch.arange(p_row.numel(), **i64), nch)
+        k = torch.arange(n_seg, **i64) - first[piece]
+        s_row, s_grp = p_row[piece], p_grp[piece]
+        s_lo = p_lo[piece] + k * seg_len
+        s_cnt = torch.minimum(p_hi[piece] - s_lo, torch.full_like(s_lo, seg_len))
+        # partial-sum slots of the rows with more than one segment, in (row, lo) order
+        per_row = torch.bincount(s_row, minlength=n_rows)
+        multi = per_row > 1
+        slots_of = torch.where(multi, per_row, torch.zeros_like(per_row))
+        slot0 = torch.cumsum(slots_of, 0) - slots_of
+        n_slot, n_mrow = int(slots_of.sum()), int(multi.sum())
+        if n_slot + 1 >= (1 << 21):
+            raise RecadError(f"PackedPlan: {n_slot} partial slots exceed the packed field; use a longer seg_len")
+        by_row = torch.argsort(s_row * (1 << 40) + s_lo)                    # lo < 2^40
+        row_first = torch.cumsum(per_row, 0) - per_row
+        rank = torch.empty(n_seg, **i64)
+        rank[by_row] = torch.arange(n_seg, **i64) - row_first[s_row[by_row]]
+        s_slot = torch.where(multi[s_row], slot0[s_row] + rank, torch.full_like(rank, -1))
+        # execution order: group by group, block by block, longest first
+        ex = torch.argsort(s_grp * (1 << 44) + (cls.MAX_SEG - s_cnt) * (1 << 32) + s_row, stable=True)
+        meta = torch.stack([s_lo & 0xffffffff, s_lo >> 32, s_row, ((s_slot + 1) << 11) | s_cnt], 1)[ex]
+        meta = torch.where(meta >= (1 << 31), meta - (1 << 32), meta).to(torch.int32).contiguous()
+        row_mseg = torch.stack([slot0, per_row], 1).to(torch.int32).contiguous()
+        # segment ranges of the caller's groups (profiling tools time them separately)
+        g_of_key, gk = [], 0
+        for gi, (r0, r1, c0, c1, nb) in enumerate(groups):
+            n_keys = 1 if (nb <= 1 or r1 == r0) else nb
+            g_of_key += [gi] * n_keys
+            gk += n_keys
+        cnt_key = torch.bincount(s_grp, minlength=gk).tolist()
+        group_segs, at = [], 0
+        for gi in range(len(groups)):
+            n = sum(c for c, g in zip(cnt_key, g_of_key) if g == gi)
+            group_segs.append((at, at + n))
+            at += n
+        return cls(meta, row_mseg, n_mrow, n_slot, group_segs)
+
+
 class Graph:
     """Device-resident CSR of a (normalised) adjacency + its SpMM work plan."""
 
-    def __init__(self, n_rows, n_cols, rowptr, colidx, vals, mult=None, degree=None, seg_len=SEG_LEN):
+    def __init__(self, n_rows, n_cols, rowptr, colidx, vals, mult=None, degree=None, seg_len=SEG_LEN, split=None):
+        """split = n_users for the symmetric bipartite adjacency (rows < split gather item rows of X, rows >= split
+        gather user rows): the two halves become separate plan groups, each column-blocked when its gathered table
+        exceeds L2 (PackedPlan)."""
         self.n_rows, self.n_cols = int(n_rows), int(n_cols)
         self.rowptr, self.colidx, self.vals, self.mult, self.degree = rowptr, colidx, vals, mult, degree
         self.nnz = int(colidx.numel())
         self.device = rowptr.device
         self.seg_len = seg_len or auto_seg_len(self.nnz)
-        self._partials = None
+        self.split = None if split is None else int(split)
+        self._partials = {}
+        self._structs = {}
         self._plan()
 
     # -- construction ------------------------------------------------------ #
@@ -101,7 +208,7 @@ class Graph:
             if degree_hook is not None:
                 degree_hook(degree)
             vals = cls._normalize(rowptr, colidx, mult, degree, N)
-        return cls(N, N, rowptr, colidx, vals, mult, degree, seg_len)
+        return cls(N, N, rowptr, colidx, vals, mult, degree, seg_len, split=n_users)
 
     @staticmethod
     def _normalize(rowptr, colidx, mult, degree, N):
@@ -137,14 +244,14 @@ class Graph:
             if degree_hook is not None:
                 degree_hook(degree)
             vals = self._normalize(rowptr, colidx, mult, degree, Nn)
-        return Graph(Nn, Nn, rowptr, colidx, vals, mult, degree, self.seg_len)
+        return Graph(Nn, Nn, rowptr, colidx, vals, mult, degree, self.seg_len, split=n_users + F)
 
     def renormalized(self, degree):
         """The same structure with values recomputed from new degrees (a shard whose own rows did not
         change while fake users elsewhere changed the item degrees)."""
         with torch.cuda.device(self.device):
             vals = self._normalize(self.rowptr, self.colidx, self.mult, degree, self.n_rows)
-        return Graph(self.n_rows, self.n_cols, self.rowptr, self.colidx, vals, self.mult, degree, self.seg_len)
+        return Graph(self.n_rows, self.n_cols, self.rowptr, self.colidx, vals, self.mult, degree, self.seg_len, split=self.split)
 
     @classmethod
     def from_csr(cls, rowptr, colidx, vals, n_cols, seg_len=SEG_LEN):
@@ -155,42 +262,32 @@ class Graph:
 
     # -- plan ---------------------------------------------------------------- #
     def _plan(self):
-        L = _lib.lib()
-        dev = self.device
-        with torch.cuda.device(dev):
-            cap = L.recad_spmm_plan_max_segments(self.n_rows, self.nnz, self.seg_len)
-            seg_row = torch.empty(cap, dtype=torch.int32, device=dev)
-            seg_lo = torch.empty(cap, dtype=torch.int64, device=dev)
-            seg_slot = torch.empty(cap, dtype=torch.int32, device=dev)
-            mcap = self.nnz // self.seg_len + 2
-            mrow = torch.empty(mcap, dtype=torch.int32, device=dev)
-            mrow_lo = torch.empty(mcap + 1, dtype=torch.int32, device=dev)
-            nbytes = L.recad_spmm_plan_scratch_bytes(self.n_rows)
-            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            counts = (C.c_int64 * 3)()
-            check(L.recad_spmm_plan(_ptr(self.rowptr), self.n_rows, self.seg_len, _ptr(seg_row), _ptr(seg_lo), _ptr(seg_slot),
-                                    _ptr(mrow), _ptr(mrow_lo), counts, _ptr(scratch), nbytes, _stream(dev)), "recad_spmm_plan")
-        self.n_seg, self.n_mrow, self.n_slot = (int(c) for c in counts)
-        self.seg_row, self.seg_lo, self.seg_slot = seg_row[:self.n_seg], seg_lo[:self.n_seg], seg_slot[:self.n_seg]
-        self.mrow, self.mrow_lo = mrow[:max(self.n_mrow, 1)], mrow_lo[:self.n_mrow + 1]
-        self._struct = None
+        if self.split is not None and 0 < self.split < self.n_rows:
+            U = self.split
+            groups = [(0, U, U, self.n_cols, auto_col_blocks(self.n_cols - U)), (U, self.n_rows, 0, U, auto_col_blocks(U))]
+        else:
+            groups = [(0, self.n_rows, 0, self.n_cols, auto_col_blocks(self.n_cols))]
+        self.plan = PackedPlan.build(self.rowptr, self.colidx, self.n_rows, self.seg_len, groups)
+        self.n_seg, self.n_mrow, self.n_slot = self.plan.n_seg, self.plan.n_mrow, self.plan.n_slot
+        with torch.cuda.device(self.device):
+            self.cv = torch.empty((max(self.nnz, 1), 2), dtype=torch.int32, device=self.device)
+            check(_lib.lib().recad_spmm_pack_cv(_ptr(self.colidx), _ptr(self.vals), self.nnz, _ptr(self.cv), _stream(self.device)),
+                  "recad_spmm_pack_cv")
+            self.row_cnt = torch.zeros(self.n_rows, dtype=torch.int32, device=self.device)
 
     def struct(self, D):
-        """ctypes recad_csr for embedding width D (allocates the partial-sum scratch lazily)."""
-        need = max(self.n_slot, 1) * D
-        if self._partials is None or self._partials.numel() < need:
-            self._partials = torch.empty(need, dtype=torch.float32, device=self.device)
-            self._struct = None
-        if self._struct is None:
+        """ctypes recad_csr for embedding width D.  The partial-sum scratch is per D and is never freed while a
+        struct handed out for that D may still be referenced by a victim."""
+        if D not in self._structs:
+            self._partials[D] = torch.empty(max(self.n_slot, 1) * D, dtype=torch.float32, device=self.device)
             s = _lib.CSR()
-            s.n_rows, s.nnz = self.n_rows, self.nnz
-            s.rowptr, s.colidx, s.vals = self.rowptr.data_ptr(), self.colidx.data_ptr(), self.vals.data_ptr()
-            s.n_seg, s.seg_len = self.n_seg, self.seg_len
-            s.seg_row, s.seg_lo, s.seg_slot = self.seg_row.data_ptr(), self.seg_lo.data_ptr(), self.seg_slot.data_ptr()
-            s.n_mrow, s.mrow, s.mrow_lo = self.n_mrow, self.mrow.data_ptr(), self.mrow_lo.data_ptr()
-            s.partials = self._partials.data_ptr()
-            self._struct = s
-        return self._struct
+            s.n_rows, s.n_cols, s.nnz = self.n_rows, self.n_cols, self.nnz
+            s.rowptr, s.colidx, s.vals, s.cv = self.rowptr.data_ptr(), self.colidx.data_ptr(), self.vals.data_ptr(), self.cv.data_ptr()
+            s.n_seg, s.seg_meta = self.n_seg, self.plan.meta.data_ptr()
+            s.n_mrow, s.row_mseg, s.row_cnt = self.n_mrow, self.plan.row_mseg.data_ptr(), self.row_cnt.data_ptr()
+            s.partials = self._partials[D].data_ptr()
+            self._structs[D] = s
+        return self._structs[D]
 
     # -- export --------------------------------------------------------------- #
     def to_numpy(self):
@@ -413,6 +510,41 @@ def mt_pairwise_epoch_raw(key, pos, n_users, n_items, train_size, allpos_rowptr,
                                                   out.ctypes.data, C.byref(n_out), j_out.ctypes.data), "recad_mt19937_pairwise_epoch")
     pos[0] = cpos.value
     return out[:n_out.value], j_out[:n_out.value]
+
+
+def mt_pairwise_soa_raw(key, pos, n_users, n_items, train_size, allpos_rowptr, allpos_col, users, rel, negs, j_out=None):
+    """The large-epoch sampler (csrc/sampler.cpp, recad_mt19937_pairwise_soa): same samples and stream consumption as
+    mt_pairwise_raw (+ mt_permutation_draw_raw when j_out is given), written as three uint32 arrays
+    (user, index of the positive inside the user's row, negative).  -> number of samples."""
+    rp, col = _np(allpos_rowptr), _np(allpos_col, np.int32)
+    for a in (users, rel, negs) + ((j_out,) if j_out is not None else ()):
+        assert a.dtype == np.uint32 and a.flags.c_contiguous and a.shape[0] >= train_size
+    filt, ext = pairwise_filter(rp, col, n_users)
+    n_out, cpos = C.c_int64(), C.c_int32(pos[0])
+    check(_lib.lib().recad_mt19937_pairwise_soa(key.ctypes.data, C.byref(cpos), n_users, n_items, train_size, rp.ctypes.data,
+                                                col.ctypes.data, filt.ctypes.data, ext.ctypes.data, min(os.cpu_count() or 1, 32),
+                                                users.ctypes.data, rel.ctypes.data, negs.ctypes.data, C.byref(n_out),
+                                                j_out.ctypes.data if j_out is not None else None), "recad_mt19937_pairwise_soa")
+    pos[0] = cpos.value
+    return n_out.value
+
+
+def permutation_apply32(j, out):
+    n = int(j.shape[0])
+    assert out.dtype == np.int32 and out.flags.c_contiguous and out.shape[0] >= n
+    check(_lib.lib().recad_permutation_apply32(n, j.ctypes.data, out.ctypes.data), "recad_permutation_apply32")
+    return out[:n]
+
+
+def samples_expand(allpos_rowptr, allpos_col, users, rel, negs, rows):
+    """rows[k] = (users[k], allpos_col[allpos_rowptr[users[k]] + rel[k]], negs[k]) on the device (int32 [n, 3])."""
+    _need_cuda(allpos_rowptr, allpos_col, users, rel, negs, rows)
+    n = int(users.shape[0])
+    assert rows.dtype == torch.int32 and rows.shape[0] >= n and allpos_rowptr.dtype == torch.int64 and allpos_col.dtype == torch.int32
+    with torch.cuda.device(rows.device):
+        check(_lib.lib().recad_samples_expand(_ptr(allpos_rowptr), _ptr(allpos_col), _ptr(users), _ptr(rel), _ptr(negs), n,
+                                              _ptr(rows), _stream(rows.device)), "recad_samples_expand")
+    return rows
 
 
 def host_empty(shape, dtype):

@@ -66,6 +66,12 @@ class BaseVictim(LazyMixin, torch.nn.Module):
         on the device.  recad_b200 datasets hand over sampler-order rows + the shuffle permutation; for any
         other BaseData the reference-style batch generator is drained (its rows are already shuffled)."""
         ds = self.dataset
+        # a pairwise victim on a pointwise dataset (or the reverse) would read (user, item, label) rows as
+        # (user, pos, neg): the reference fails on the missing batch key, so does this
+        want = "pairwise" if names[1] == "positive_items" else "pointwise"
+        have = getattr(ds, "config", {}).get("sample") if isinstance(getattr(ds, "config", None), dict) else None
+        if have is not None and have != want:
+            raise KeyError(f"{names[1]}: {type(self).__name__} trains on {want} batches but the dataset samples {have}")
         if hasattr(ds, "epoch_samples"):
             return ds.epoch_samples(self._dev)
         cols = [[] for _ in names]

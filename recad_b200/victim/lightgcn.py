@@ -80,6 +80,18 @@ class LightGCN(BaseVictim):
         for k in ("E", "m", "v", "O", "X0", "X1", "g", "cnt", "loss_acc"):
             setattr(st, k, getattr(self, k).data_ptr())
         self._st = st
+        self._O_valid = False      # O was just (re)allocated: never score from it before a propagate
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._O_valid = False      # the tables changed under the cached propagation
+        return out
+
+    def invalidate(self):
+        """Call after editing embedding_*.weight.data in place: forward() / full_rank() reuse the cached propagation
+        until a train_step, load_state_dict or device move says the tables changed (the reference re-propagates on
+        every forward, lightgcn.py:174-176)."""
+        self._O_valid = False
 
     def _move(self, dev):
         if dev.index is None:
@@ -112,10 +124,7 @@ class LightGCN(BaseVictim):
         if n == 0:
             raise ops.RecadError("LightGCN.train_step: the sampler produced no training triple")
         B = int(self.dataset.config["pairwise_batch_size"]) if hasattr(self.dataset, "config") else 1024
-        with torch.cuda.device(self._dev):
-            self._check(_lib.lib().recad_lightgcn_train_epoch(
-                C.byref(self._st), self._vp(samples), self._vp(perm), n, B, self._steps,
-                ops._stream(self._dev)), "recad_lightgcn_train_epoch")
+        self.run_epoch(samples, perm, B)
         n_batches = (n + B - 1) // B
         self._steps += n_batches
         self._O_valid = False
@@ -124,6 +133,18 @@ class LightGCN(BaseVictim):
         if pbar:
             pbar.set_description(f"loss {out[0]:.5f}")
         return out
+
+    def run_epoch(self, samples, perm, B):
+        """Enqueue one epoch over device-resident rows (int64 or int32 [n, 3]) visited in the order perm (same dtype)."""
+        L = _lib.lib()
+        i32 = samples.dtype == torch.int32
+        if perm is not None and perm.dtype != samples.dtype:
+            perm = perm.to(samples.dtype)
+        fn, name = (L.recad_lightgcn_train_epoch_i32, "recad_lightgcn_train_epoch_i32") if i32 else \
+            (L.recad_lightgcn_train_epoch, "recad_lightgcn_train_epoch")
+        with torch.cuda.device(self._dev):
+            self._check(fn(C.byref(self._st), self._vp(samples), self._vp(perm), int(samples.shape[0]), B, self._steps,
+                           ops._stream(self._dev)), name)
 
     def forward(self, users, items):
         """lightgcn.py:174-183: <O_u, O_i>.  The propagation is redone only when the tables changed

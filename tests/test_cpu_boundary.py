@@ -26,13 +26,13 @@ def test_library_exports_every_header_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.recad_abi_version() == 1
+    assert lib.recad_abi_version() == 2
 
 
 def test_struct_layouts_match_header_sizes():
     # natural alignment, 8-byte pointers: catches a field added on one side only
     import ctypes as C
-    assert C.sizeof(_lib.CSR) == 14 * 8
+    assert C.sizeof(_lib.CSR) == 13 * 8
     assert C.sizeof(_lib.LightGCN) == 8 + 16 + 8 + 6 * 4 + 9 * 8
     assert C.sizeof(_lib.MF) == 16 + 6 * 4 + 17 * 8
     assert C.sizeof(_lib.NCF) == 16 + 8 + 16 + 8 + 4 * 8 + 8 + 8 + 8 + 8 + 8
@@ -370,3 +370,67 @@ def test_pairwise_epoch_call_equals_sampler_then_shuffle_draws():
     assert len(S) < n and np.array_equal(S, S2) and np.array_equal(j, j2)
     assert np.array_equal(key, key2) and pos == pos2
     assert sorted(ops.permutation_apply(j2).tolist()) == list(range(len(S)))
+
+
+def test_pointwise_sampler_dense_users_follow_cpython_set_order():
+    """implicit.py:86 `list(full_items - set(iids))` is ascending only while CPython copies the full set and discards;
+    from len(set(iids)) >= n_items / 4 the difference is rebuilt into a smaller hash table and the list follows its
+    slot order.  The C++ replay emulates that table: same negatives, same generator state as the reference's Python."""
+    def ref_pointwise(train_dict, n_items, ratio):          # implicit.py:77-91 verbatim in behaviour
+        data = []
+        full_items = set(range(n_items))
+        for uid, iids in train_dict.items():
+            data.extend([(uid, iid, 1) for iid in iids])
+            left_set = list(full_items - set(iids))
+            negs = np.random.choice(left_set, size=len(iids) * ratio)
+            data.extend([(uid, ni, 0) for ni in negs])
+        return np.array(data)
+    rng = np.random.default_rng(3)
+    for n_items, fracs in [(1000, [0.1, 0.24, 0.25, 0.26, 0.7, 0.99]), (3706, [0.2, 0.8]), (10000, [0.55]), (17, [0.5, 0.9])]:
+        d = {u: [int(x) for x in rng.permutation(n_items)[:max(1, min(n_items - 1, int(n_items * f)))]] for u, f in enumerate(fracs)}
+        d[len(fracs)] = [5, 5, 7, 5]                         # duplicated positives
+        np.random.seed(11)
+        ref = ref_pointwise(d, n_items, 2)
+        st_ref = np.random.get_state()
+        np.random.seed(11)
+        keys = np.array(list(d), np.int64)
+        ptr = np.concatenate([[0], np.cumsum([len(v) for v in d.values()])]).astype(np.int64)
+        items = np.concatenate([np.array(v, np.int64) for v in d.values()])
+        got = ops.mt_pointwise(keys, ptr, items, n_items, 2)
+        st = np.random.get_state()
+        assert np.array_equal(got, ref), n_items
+        assert np.array_equal(st[1], st_ref[1]) and st[2] == st_ref[2]
+
+
+def test_soa_epoch_sampler_equals_plain_sampler_and_shuffle():
+    """recad_mt19937_pairwise_soa (stream producer thread, pre-gathered lengths, optimistic parse with exact redo and
+    re-convergence, 32-bit arrays) == recad_mt19937_pairwise + recad_mt19937_permutation_draw: users, positives
+    (through the row index), negatives, shuffle draws, generator state -- including users without positives, a
+    one-user dataset and a dataset where nearly every optimistic candidate is a positive."""
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    for U, I, deg, n, empty in [(2000, 64, 20, 60000, 0.0), (3000, 3000, 40, 300000, 0.01), (1, 7, 3, 3000, 0.0), (40, 16, 15, 20000, 0.1)]:
+        ptr, cols = [0], []
+        for u in range(U):
+            d = 0 if rng.random() < empty else int(min(I - 1, max(1, rng.poisson(deg))))
+            cols.append(np.sort(rng.choice(I, d, replace=False)).astype(np.int32))
+            ptr.append(ptr[-1] + d)
+        ptr, col = np.array(ptr, np.int64), np.concatenate(cols)
+        for seed in (0, 5):
+            np.random.seed(seed)
+            _, key, pos = ops._np_state()
+            pos = [(pos[0] + seed * 100) % 625]
+            key2, pos2 = key.copy(), [pos[0]]
+            out, n_out, cpos = np.empty((n, 3), np.int64), C.c_int64(), C.c_int32(pos[0])
+            _lib.check(_lib.lib().recad_mt19937_pairwise(key.ctypes.data, C.byref(cpos), U, I, n, ptr.ctypes.data, col.ctypes.data,
+                                                         out.ctypes.data, C.byref(n_out)), "recad_mt19937_pairwise")
+            S, pos = out[:n_out.value], [cpos.value]
+            j_ref = ops.mt_permutation_draw_raw(key, pos, len(S))
+            users, rel, negs, j = (np.empty(n, np.uint32) for _ in range(4))
+            m = ops.mt_pairwise_soa_raw(key2, pos2, U, I, n, ptr, col, users, rel, negs, j)
+            assert m == len(S)
+            assert np.array_equal(users[:m], S[:, 0]) and np.array_equal(col[ptr[users[:m]] + rel[:m]], S[:, 1])
+            assert np.array_equal(negs[:m], S[:, 2]) and np.array_equal(j[:m], j_ref)
+            assert np.array_equal(key2, key) and pos2[0] == pos[0]
+            perm32 = ops.permutation_apply32(j[:m], np.empty(max(m, 1), np.int32))
+            assert np.array_equal(perm32, ops.permutation_apply(j_ref))
