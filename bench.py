@@ -34,7 +34,21 @@ WORKLOADS = {
     "tiny": dict(n_users=20_000, n_items=5_000, n_edges=400_000, D=64, L=3, batch=65_536),
 }
 METRIC = "lightgcn_bpr_epoch_plus_fullrank_eval_seconds"
-NCU_SPMM_DRAM_BYTES = 10_500_000_000   # measured per launch on the synthetic graph: 9.5 GB read + 1.0 GB written
+L2_CAP_BYTES_PER_CLK = 6300            # full-chip L2 -> SM throughput cap (B300_MICROARCH.md, "LTS throughput cap")
+
+
+def ncu_spmm_traffic(workload):
+    """DRAM / L2 bytes of ONE SpMM launch from the committed ncu capture -- valid only for the kernel source it was
+    taken from (profiles/ncu_spmm_r02.json records the hash of csrc/spmm.cu); None when the kernel changed since."""
+    import hashlib
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_spmm_r02.json")))
+        sha = hashlib.sha256(open(os.path.join(ROOT, "recad_b200", "csrc", "spmm.cu"), "rb").read()).hexdigest()[:16]
+    except OSError:
+        return None
+    if rec.get("workload") != workload or rec.get("spmm_cu_sha16") != sha:
+        return None
+    return rec
 
 
 def synth_edges(w, device, seed=0):
@@ -205,6 +219,8 @@ def run_b200(args, w):
     pk, pk_src = peaks()
     alg = graph.algorithmic_bytes(D) + graph.n_rows * 4 * D * 2       # + read C, write Z of the fused epilogue
     achieved = alg / (spmm_ms * 1e-3) / 1e9
+    ncu = ncu_spmm_traffic(args.workload)
+    traffic = (ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ncu else None
 
     # end to end through the public API: host sampler + pinned H2D + epoch + loss D2H, then evaluation + metric D2H
     # (the next epoch's samples are drawn on a background thread while the GPU works: dataset._EpochPipe)
@@ -227,6 +243,7 @@ def run_b200(args, w):
     h2d = sum(int(t.numel()) * t.element_size() for t in sets[0]) + (n * 4 if sets[0][0].dtype == torch.int32 else 0)   # users, rel, negs, perm (int32) or rows + perm (int64)
     d2h = 4 * 8 + 3 * 8 + 4
 
+    sm_mhz = clocks.summary()["sm_mhz"]
     out = {
         "metric": METRIC, "value": round(step_ms / 1e3, 6), "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(step_ms, 3), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -240,11 +257,18 @@ def run_b200(args, w):
         "graph_build_s": round(t_graph, 4), "edge_gen_s": round(t_gen, 3), "host_sampler_s": round(t_sampler, 3),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": round(achieved / pk["hbm_gbs"], 4),
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/ncu_spmm_r01.md)
-                     "traffic": NCU_SPMM_DRAM_BYTES if args.workload == "synthetic" else None,
-                     "kernel": "spmm_seg_kernel<64,4,5> + spmm_fixup_kernel<64>",
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/ncu_spmm_r02.md);
+                     # null when csrc/spmm.cu changed after the capture
+                     "traffic": traffic,
+                     "frac_dram": round(traffic / (spmm_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4) if traffic else None,
+                     "frac_l2": round(ncu["l2_to_sm_bytes"] / (spmm_ms * 1e-3) / (L2_CAP_BYTES_PER_CLK * sm_mhz * 1e6), 4)
+                     if ncu and sm_mhz else None,
+                     "kernel": f"spmm_kernel<{D},4,4,0>",
                      "ms_per_launch": round(spmm_ms, 4), "algorithmic_bytes": alg, "peak_source": pk_src,
-                     "model": "no-reuse gather: nnz*(8+4D) + 3*N*4D + (N+1)*4"},
+                     "model": "no-reuse gather: nnz*(8+4D) + 3*N*4D + (N+1)*4 (SURVEY 8d); the gathers are served by L2, so "
+                              "`frac` above 1 is NOT an HBM fraction: `frac_dram` = measured DRAM bytes / time / peak, `frac_l2` = "
+                              "measured L2->SM bytes / time / (6300 B/clk x SM clock), the bound this kernel runs at "
+                              "(profiles/ncu_spmm_r02.md)"},
         "e2e": {"value": round(float(np.mean(e2e)), 6), "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "includes": "steady state of an epoch loop (4 untimed epochs fill the prefetch queue): train_step(): exact C++ MT19937 "
                             "sampler + shuffle on host (the next two epochs are drawn on background threads), pinned H2D of "
