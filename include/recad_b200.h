@@ -223,6 +223,69 @@ int recad_bpr_fwd_bwd_i32(const float* O, const float* E, int64_t n_users, int64
 int recad_lightgcn_train_epoch_i32(const recad_lightgcn* st, const int32_t* samples, const int32_t* perm,
                                    int64_t n_samples, int64_t batch, int64_t step0, void* stream);
 
+/* ------------------------------------------------------------------------ *
+ * User-sharded LightGCN epoch (same math as recad_lightgcn_train_epoch,
+ * lightgcn.py:82-172), one process per GPU, exchanges over NVLink peer memory only.
+ * ------------------------------------------------------------------------ */
+
+/* One epoch's samples on the device, in either form (the other form's pointers NULL):
+ *   rows   int64[n_samples, 3] (GLOBAL user, pos, neg) in sampler order + perm64 int64[n_samples] (or NULL = identity)
+ *   users / rel / negs  uint32[n_samples] as recad_mt19937_pairwise_soa emits them (GLOBAL user id, index of the
+ *          positive inside the user's row, negative) + perm32 int32[n_samples] (or NULL = identity).
+ * Every rank holds the WHOLE epoch (0.8 GB at 50 M samples) and keeps the samples whose user it owns. */
+typedef struct recad_epoch_samples {
+  int64_t n_samples;
+  const int64_t* rows;
+  const int64_t* perm64;
+  const uint32_t* users;
+  const uint32_t* rel;
+  const uint32_t* negs;
+  const int32_t* perm32;
+} recad_epoch_samples;
+
+/* State of one rank.  Tables are [n_users_local + n_items, D] (own users first, then a replica of ALL items).
+ * Everything peers read or write lives in one symmetric block per rank, mapped into every process
+ * (torch.distributed._symmetric_memory): peer_base[r] is rank r's block as mapped HERE, off_* are byte offsets inside it:
+ *   off_X0 / off_X1 / off_O / off_g : float[max_r(n_users_local_r) + n_items, D]   layer ping / pong, propagated mean, gradient
+ *   off_cnt    : float[max_r(n_users_local_r) + n_items]        batch multiplicities
+ *   off_stage  : float[world, slice, D]   slot s receives rank s's partial rows of the items THIS rank owns
+ *   off_signal : uint32[64], zero-initialised: [0, world) barrier pad, [32] barrier epoch, [33] timeout flag
+ * Rank r owns items [r * slice, (r + 1) * slice).  mc_base: NVSwitch multicast mapping of the block (one store lands in
+ * every rank's copy) or NULL; used only when every rank has the same n_users_local. */
+typedef struct recad_lightgcn_shard {
+  int32_t rank, world, D, n_layers;
+  int64_t n_users_local, n_items, user_lo, slice;
+  float lambda, lr, beta1, beta2, eps;
+  int32_t _pad;
+  const recad_csr* g_user;     /* [n_users_local x n_items]: own user rows (gather the item replica) */
+  const recad_csr* g_item;     /* [n_items x n_users_local]: item rows over own users (partial sums) */
+  const int64_t* pos_rowptr;   /* [dev] int64[n_users_local + 1]: own users' sorted distinct positives (may be NULL with `rows`) */
+  const int32_t* pos_col;      /* [dev] int32[]: item id + pos_col_offset */
+  int64_t pos_col_offset;
+  float* E;                    /* [dev] local tables */
+  float* m;
+  float* v;
+  double* loss_acc;            /* [dev] double[4] as in recad_lightgcn; partial sums of THIS rank's samples */
+  void* const* peer_base;      /* [host] void*[world] */
+  void* mc_base;
+  const int64_t* peer_users;   /* [host] int64[world]: n_users_local of every rank */
+  int64_t off_X0, off_X1, off_O, off_g, off_cnt, off_stage, off_signal;
+} recad_lightgcn_shard;
+
+/* O = mean_k A^k E over the sharded matrix: L x (item-row SpMM pushing partial rows to their owners | user-row SpMM |
+ * barrier | owner reduce + store into every replica | barrier).  Collective: every rank must call it. */
+int recad_lightgcn_shard_propagate(const recad_lightgcn_shard* st, void* stream);
+/* One epoch over the GLOBAL sample list: per batch propagate, BPR on the rank's own users' samples (1/B of the global
+ * batch), gradient-block exchange, Horner backward, dense Adam on the own user rows and the item replica.  Nothing
+ * synchronises with the host; loss_acc[2] holds the rank's part of the sum of batch losses afterwards (sum over ranks /
+ * n_batches = the epoch loss).  trace_ms [host] double[8] or NULL: when given, the call synchronises the stream and
+ * returns the time spent per phase {0 item-row SpMM + push, 1 user-row SpMM, 2 barriers, 3 slice reduce + store,
+ * 4 zeroing, 5 BPR, 6 gradient exchange, 7 Adam} (CUDA events). */
+int recad_lightgcn_shard_train_epoch(const recad_lightgcn_shard* st, const recad_epoch_samples* ep, int64_t batch,
+                                     int64_t step0, double* trace_ms, void* stream);
+/* state2 [host] uint32[2] = {barriers passed, 1 if a barrier wait ever timed out}; synchronises the stream. */
+int recad_lightgcn_shard_barrier_state(const recad_lightgcn_shard* st, uint32_t* state2, void* stream);
+
 /* scores[b] = <O[users[b]], O[n_users + items[b]]> (lightgcn.py:174-183 after a
  * propagate; O must be current). */
 int recad_dot_scores(const float* O, int64_t n_users, const int64_t* users, const int64_t* items,

@@ -33,6 +33,25 @@ class LightGCN(C.Structure):
     ]
 
 
+class EpochSamples(C.Structure):
+    """struct recad_epoch_samples"""
+    _fields_ = [("n_samples", i64), ("rows", vp), ("perm64", vp), ("users", vp), ("rel", vp), ("negs", vp), ("perm32", vp)]
+
+
+class LightGCNShard(C.Structure):
+    """struct recad_lightgcn_shard"""
+    _fields_ = [
+        ("rank", i32), ("world", i32), ("D", i32), ("n_layers", i32),
+        ("n_users_local", i64), ("n_items", i64), ("user_lo", i64), ("slice", i64),
+        ("lam", f32), ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("_pad", i32),
+        ("g_user", C.POINTER(CSR)), ("g_item", C.POINTER(CSR)),
+        ("pos_rowptr", vp), ("pos_col", vp), ("pos_col_offset", i64),
+        ("E", vp), ("m", vp), ("v", vp), ("loss_acc", vp),
+        ("peer_base", C.POINTER(vp)), ("mc_base", vp), ("peer_users", C.POINTER(i64)),
+        ("off_X0", i64), ("off_X1", i64), ("off_O", i64), ("off_g", i64), ("off_cnt", i64), ("off_stage", i64), ("off_signal", i64),
+    ]
+
+
 class MF(C.Structure):
     """struct recad_mf"""
     _fields_ = [
@@ -77,6 +96,9 @@ SIGNATURES = {
     "recad_lightgcn_train_epoch": (C.c_int, [C.POINTER(LightGCN), vp, vp, i64, i64, i64, vp]),
     "recad_bpr_fwd_bwd_i32": (C.c_int, [vp, vp, i64, i64, vp, vp, i64, i64, f32, vp, vp, vp, i32, vp]),
     "recad_lightgcn_train_epoch_i32": (C.c_int, [C.POINTER(LightGCN), vp, vp, i64, i64, i64, vp]),
+    "recad_lightgcn_shard_propagate": (C.c_int, [C.POINTER(LightGCNShard), vp]),
+    "recad_lightgcn_shard_train_epoch": (C.c_int, [C.POINTER(LightGCNShard), C.POINTER(EpochSamples), i64, i64, C.POINTER(C.c_double), vp]),
+    "recad_lightgcn_shard_barrier_state": (C.c_int, [C.POINTER(LightGCNShard), C.POINTER(C.c_uint32), vp]),
     "recad_dot_scores": (C.c_int, [vp, i64, vp, vp, i64, i32, vp, vp]),
     "recad_mf_forward": (C.c_int, [C.POINTER(MF), vp, vp, i64, vp, vp]),
     "recad_mf_train_epoch": (C.c_int, [C.POINTER(MF), vp, vp, i64, i64, i64, vp]),

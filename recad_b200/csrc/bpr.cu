@@ -13,10 +13,64 @@ namespace recad {
 // BPR forward + backward.  A group of LPR lanes owns one sample; each lane holds VPL float4 columns
 // of the six rows (O_u, O_p, O_n, E_u, E_p, E_n).  Gradients leave through 128-bit vector REDs.
 // ------------------------------------------------------------------------------------------
-template <int LPR, int VPL, typename IdxT>
+// Where a batch's (user, pos, neg) triples come from.
+// RowSamples: rows [*, 3] in sampler order, visited through the epoch permutation (single GPU, reference layout).
+template <typename IdxT>
+struct RowSamples {
+  const IdxT* samples;
+  const IdxT* perm;
+  // returns 1 = valid sample, 0 = nothing to do, -1 = id out of range
+  __device__ __forceinline__ int fetch(int64_t b, int64_t n_users, int64_t n_items, int64_t& u, int64_t& p, int64_t& n) const {
+    const int64_t row = perm ? (int64_t)perm[b] : b;      // the epoch shuffle is this indirection
+    u = samples[3 * row]; p = samples[3 * row + 1]; n = samples[3 * row + 2];
+    return (u < 0 || u >= n_users || p < 0 || p >= n_items || n < 0 || n >= n_items) ? -1 : 1;
+  }
+};
+// ShardSamples: the GLOBAL epoch as the host sampler emits it (user, index of the positive inside the user's row,
+// negative; 32 bit each) + the global permutation.  A rank of the user-sharded path walks the whole global batch and
+// keeps the samples whose user it owns -- no routing pass, no per-rank copy of the epoch; the positive ITEM comes out
+// of the rank's own rows of the interaction matrix (its users' sorted distinct items, implicit.py:339-343).
+struct ShardSamples {
+  const uint32_t* users;
+  const uint32_t* rel;
+  const uint32_t* negs;
+  const int32_t* perm;
+  int64_t user_lo, user_hi;        // global ids [lo, hi) live on this rank as local users 0 .. hi - lo
+  const int64_t* pos_rowptr;       // [n_users_local + 1]
+  const int32_t* pos_col;          // item ids + pos_col_offset
+  int32_t pos_col_offset;
+  __device__ __forceinline__ int fetch(int64_t b, int64_t n_users, int64_t n_items, int64_t& u, int64_t& p, int64_t& n) const {
+    const int64_t row = perm ? (int64_t)perm[b] : b;
+    const int64_t gu = users[row];
+    if (gu < user_lo || gu >= user_hi) return 0;
+    u = gu - user_lo;
+    const int64_t lo = pos_rowptr[u], len = pos_rowptr[u + 1] - lo;
+    const int64_t r = rel[row];
+    n = negs[row];
+    if (u >= n_users || r >= len || n >= n_items) return -1;
+    p = (int64_t)pos_col[lo + r] - pos_col_offset;
+    return (p < 0 || p >= n_items) ? -1 : 1;
+  }
+};
+
+// ShardRows: the global epoch as (user, pos, neg) rows; a rank keeps its own users' rows (tests, injected datasets).
+struct ShardRows {
+  const int64_t* rows;
+  const int64_t* perm;
+  int64_t user_lo, user_hi;
+  __device__ __forceinline__ int fetch(int64_t b, int64_t n_users, int64_t n_items, int64_t& u, int64_t& p, int64_t& n) const {
+    const int64_t row = perm ? perm[b] : b;
+    const int64_t gu = rows[3 * row];
+    if (gu < user_lo || gu >= user_hi) return 0;
+    u = gu - user_lo; p = rows[3 * row + 1]; n = rows[3 * row + 2];
+    return (u >= n_users || p < 0 || p >= n_items || n < 0 || n >= n_items) ? -1 : 1;
+  }
+};
+
+template <int LPR, int VPL, typename Src>
 __global__ void __launch_bounds__(256)
 bpr_kernel(const float* __restrict__ O, const float* __restrict__ E, int64_t n_users, int64_t n_items,
-           const IdxT* __restrict__ samples, const IdxT* __restrict__ perm,
+           const Src src, int64_t b0,
            int64_t B, int64_t B_norm, float grad_scale, float* __restrict__ gO, float* __restrict__ cnt,
            double* __restrict__ loss_acc, int nvec, int* __restrict__ bad) {
   constexpr int GPW = 32 / LPR;  // sample groups per warp
@@ -32,16 +86,17 @@ bpr_kernel(const float* __restrict__ O, const float* __restrict__ E, int64_t n_u
   const int64_t iters = (B + n_groups - 1) / n_groups;
   for (int64_t it = 0; it < iters; ++it) {
     const int64_t b = it * n_groups + group;
-    const bool valid = b < B;
+    bool valid = b < B;
     int64_t u = 0, p = 0, n = 0;
     if (valid) {
-      const int64_t row = perm ? perm[b] : b;      // the epoch shuffle is this indirection
-      u = samples[3 * row]; p = samples[3 * row + 1]; n = samples[3 * row + 2];
-      if (u < 0 || u >= n_users || p < 0 || p >= n_items || n < 0 || n >= n_items) {
+      const int st = src.fetch(b0 + b, n_users, n_items, u, p, n);
+      if (st < 0) {
         if (l == 0) atomicOr(bad, 1);
         u = 0; p = 0; n = 0;
       }
+      valid = st != 0;
     }
+    if (!__any_sync(kFull, valid)) continue;     // sharded source: most samples of the global batch belong to other ranks
     const int64_t ru = u * nvec, rp = (n_users + p) * nvec, rn = (n_users + n) * nvec;
     float4 ou[VPL], op[VPL], on[VPL];
     float dn = 0.f, dp = 0.f, sq = 0.f;
@@ -180,29 +235,54 @@ int launch_adam(float* p, const float* g, const float* cnt, float reg_scale, flo
   return RECAD_OK;
 }
 
-template <int LPR, int VPL, typename IdxT>
-static int launch_bpr_t(const float* O, const float* E, int64_t U, int64_t I, const IdxT* samples,
-                        const IdxT* perm, int64_t B, int64_t B_norm, float gs, float* gO, float* cnt, double* loss, int nvec,
-                        int* bad, cudaStream_t s) {
+template <int LPR, int VPL, typename Src>
+static int launch_bpr_t(const float* O, const float* E, int64_t U, int64_t I, const Src& src, int64_t b0, int64_t B, int64_t B_work,
+                        int64_t B_norm, float gs, float* gO, float* cnt, double* loss, int nvec, int* bad, cudaStream_t s) {
   const int64_t groups_per_block = 256 / LPR;
-  const int64_t want = (B + groups_per_block - 1) / groups_per_block;
+  const int64_t want = (B_work + groups_per_block - 1) / groups_per_block;       // B_work: samples expected to be valid
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 32));
-  bpr_kernel<LPR, VPL, IdxT><<<grid, 256, 0, s>>>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad);
+  bpr_kernel<LPR, VPL, Src><<<grid, 256, 0, s>>>(O, E, U, I, src, b0, B, B_norm, gs, gO, cnt, loss, nvec, bad);
   RECAD_LAUNCH_CHECK();
   return RECAD_OK;
+}
+
+template <typename Src>
+static int launch_bpr_src(const float* O, const float* E, int64_t U, int64_t I, const Src& src, int64_t b0, int64_t B, int64_t B_work,
+                          int64_t B_norm, float gs, float* gO, float* cnt, double* loss, int D, int* bad, cudaStream_t s) {
+  const int nvec = D / 4;
+  if (nvec <= 8) return launch_bpr_t<8, 1, Src>(O, E, U, I, src, b0, B, B_work, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 16) return launch_bpr_t<16, 1, Src>(O, E, U, I, src, b0, B, B_work, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 32) return launch_bpr_t<32, 1, Src>(O, E, U, I, src, b0, B, B_work, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 64) return launch_bpr_t<32, 2, Src>(O, E, U, I, src, b0, B, B_work, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  if (nvec <= 128) return launch_bpr_t<32, 4, Src>(O, E, U, I, src, b0, B, B_work, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  return launch_bpr_t<32, 8, Src>(O, E, U, I, src, b0, B, B_work, B_norm, gs, gO, cnt, loss, nvec, bad, s);
 }
 
 template <typename IdxT>
 static int launch_bpr(const float* O, const float* E, int64_t U, int64_t I, const IdxT* samples, const IdxT* perm,
                int64_t B, int64_t B_norm, float gs, float* gO, float* cnt, double* loss, int D, int* bad,
                cudaStream_t s) {
-  const int nvec = D / 4;
-  if (nvec <= 8) return launch_bpr_t<8, 1, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 16) return launch_bpr_t<16, 1, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 32) return launch_bpr_t<32, 1, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 64) return launch_bpr_t<32, 2, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
-  if (nvec <= 128) return launch_bpr_t<32, 4, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
-  return launch_bpr_t<32, 8, IdxT>(O, E, U, I, samples, perm, B, B_norm, gs, gO, cnt, loss, nvec, bad, s);
+  const RowSamples<IdxT> src{samples, perm};
+  return launch_bpr_src(O, E, U, I, src, 0, B, B, B_norm, gs, gO, cnt, loss, D, bad, s);
+}
+
+// sharded path (shard.cu): samples b0 .. b0 + B of the global epoch, of which about B / world belong to this rank
+int launch_bpr_shard(const float* O, const float* E, int64_t U, int64_t I, const uint32_t* users, const uint32_t* rel,
+                     const uint32_t* negs, const int32_t* perm, int64_t b0, int64_t B, int64_t B_norm, int64_t user_lo,
+                     const int64_t* pos_rowptr, const int32_t* pos_col, int32_t pos_col_offset, int world, float gs, float* gO,
+                     float* cnt, double* loss, int D, cudaStream_t s) {
+  const ShardSamples src{users, rel, negs, perm, user_lo, user_lo + U, pos_rowptr, pos_col, pos_col_offset};
+  // groups sized for ~4 global samples each: the ownership test is 12 bytes per sample, the work 4.6 kB per kept sample
+  const int64_t B_work = std::max<int64_t>(B / std::max(1, std::min(world, 4)), 1);
+  return launch_bpr_src(O, E, U, I, src, b0, B, B_work, B_norm, gs, gO, cnt, loss, D, reinterpret_cast<int*>(loss + 3), s);
+}
+
+int launch_bpr_shard_rows(const float* O, const float* E, int64_t U, int64_t I, const int64_t* rows, const int64_t* perm, int64_t b0,
+                          int64_t B, int64_t B_norm, int64_t user_lo, int world, float gs, float* gO, float* cnt, double* loss, int D,
+                          cudaStream_t s) {
+  const ShardRows src{rows, perm, user_lo, user_lo + U};
+  const int64_t B_work = std::max<int64_t>(B / std::max(1, std::min(world, 4)), 1);
+  return launch_bpr_src(O, E, U, I, src, b0, B, B_work, B_norm, gs, gO, cnt, loss, D, reinterpret_cast<int*>(loss + 3), s);
 }
 
 // z = a * x + b * y (float4 grid-stride); z may alias x or y

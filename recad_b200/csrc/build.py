@@ -14,9 +14,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "librecad_b200.so")
-SOURCES = ["api.cu", "scan.cu", "sort.cu", "csr.cu", "spmm.cu", "bpr.cu", "mf.cu", "ncf.cu", "eval.cu", "eval_tc.cu", "gemm_tc.cu", "sampler.cpp"]
+SOURCES = ["api.cu", "scan.cu", "sort.cu", "csr.cu", "spmm.cu", "bpr.cu", "shard.cu", "mf.cu", "ncf.cu", "eval.cu", "eval_tc.cu", "gemm_tc.cu", "sampler.cpp"]
 HEADERS = ["common.cuh", "rank_epilogue.cuh", "tc_common.cuh", os.path.join(ROOT, "include", "recad_b200.h")]
+# host-only translation units built by g++ with ISA flags of their own (each is entered only after a run-time CPU check)
+CXX_SOURCES = {"sampler_avx512.cpp": ["-mavx512f", "-mbmi", "-mlzcnt"]}
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+CXX = os.environ.get("CXX", "g++")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
@@ -36,7 +39,10 @@ def _compile(src, verbose):
     deps = [path] + [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
     if not _stale(obj, deps):
         return obj
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", path, "-o", obj]
+    if src in CXX_SOURCES:
+        cmd = [CXX, "-O3", "-std=c++17", "-fPIC", "-Wall"] + CXX_SOURCES[src] + ["-c", path, "-o", obj]
+    else:
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
@@ -47,7 +53,7 @@ def _compile(src, verbose):
 
 def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, "_build"), exist_ok=True)
-    srcs = [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
+    srcs = [s for s in SOURCES + list(CXX_SOURCES) if os.path.exists(os.path.join(HERE, s))]
     if force:
         for f in os.listdir(os.path.join(HERE, "_build")):
             os.remove(os.path.join(HERE, "_build", f))

@@ -176,6 +176,8 @@ class _EpochPipe:
     def _to_device(self, got, device):
         if got[0] == "soa":
             _, u, r, g, p = got
+            if getattr(self, "raw_soa", False):       # sharded path: the host arrays themselves (each rank expands its own users)
+                return u, r, g, p
             ud, rd, gd, pd = (t.to(device, non_blocking=True) for t in (u, r, g, p))
             rows = torch.empty((int(u.shape[0]), 3), dtype=torch.int32, device=device)
             ops.samples_expand(*self.data.allpos_device(device), ud, rd, gd, rows)
@@ -241,7 +243,7 @@ class _EpochPipe:
             slot = self._free_slot()
             got, self.last_slot = self._draw_into(slot, cuda, key, pos), slot
         np.random.set_state((st[0], key, int(pos[0]), st[3], st[4]))
-        s_dev, p_dev = self._to_device(got, device)
+        on_dev = self._to_device(got, device)
         self.calls += 1
         # speculate only once the caller has come back for a second epoch: a dataset that lives for ONE epoch (the
         # attacked copy of an attack iteration) would otherwise leave two useless epochs running in the background,
@@ -252,7 +254,7 @@ class _EpochPipe:
                     self._spawn(cuda, prev=self.queue[-1])
                 else:
                     self._spawn(cuda, key=key.copy(), pos=int(pos[0]))
-        return s_dev, p_dev
+        return on_dev
 
 
 class ImplicitData:

@@ -43,62 +43,47 @@ def route_epoch(samples, perm, batch, lo, hi):
     return local, ptr
 
 
-class _PeerExchange:
-    """Peer-memory plumbing of the fused exchange: NVLink-mapped buffers from torch symmetric memory and the
-    pointer tables the two kernels take.  Per rank: a staging block [world, slice, D] (slot s receives rank s's
-    partial rows of the items this rank owns, slice = ceil(I / world)) and the layer buffers X0 / X1, whose
-    item blocks every owner writes its reduced slice into."""
+class _PeerBlock:
+    """Peer-memory plumbing of the C-driven sharded epoch (csrc/shard.cu): ONE NVLink-mapped symmetric block per rank
+    (torch symmetric memory) holding every buffer a peer reads or writes -- the layer buffers X0 / X1, the propagated
+    mean O, the gradient g (each [n_max, D]), the batch multiplicities cnt [n_max], the staging slots
+    [world, slice, D] (slot s receives rank s's partial rows of the items this rank owns, slice = ceil(I / world)) and
+    the barrier pad -- at the same byte offsets on every rank."""
 
     def __init__(self, Ug, I, D, dev, group):
+        import os
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > 16:
-            raise ops.RecadError("fused exchange supports at most 16 ranks")
+            raise ops.RecadError("the peer-memory exchange supports at most 16 ranks")
         ugs = torch.zeros(self.world, dtype=torch.int64, device=dev)
         ugs[self.rank] = Ug
         dist.all_reduce(ugs, group=group)
         self.Ugs = [int(x) for x in ugs.tolist()]
         self.I, self.D, self.dev = I, D, dev
         self.slice = (I + self.world - 1) // self.world
-        self.rows_mine = max(0, min(self.slice, I - self.rank * self.slice))
         n_max = max(self.Ugs) + I
-        self.stage = symm.empty((self.world, self.slice, D), dtype=torch.float32, device=dev)
-        self.h_stage = symm.rendezvous(self.stage, self.group)
-        self.bufs, self.handles = [], []
-        for _ in range(2):
-            t = symm.empty((n_max, D), dtype=torch.float32, device=dev)
-            self.handles.append(symm.rendezvous(t, self.group))
-            self.bufs.append(t)
-        fb = 4 * D                                   # bytes per row
-        # where MY partial rows for owner o go: slot `rank` of o's staging block
-        self._dst = (C.c_void_p * self.world)(*[int(p) + self.rank * self.slice * fb for p in self.h_stage.buffer_ptrs])
-        # where MY reduced slice goes in peer r's layer buffer k: its item block starts after ITS users
-        self._out = [(C.c_void_p * self.world)(*[int(p) + (self.Ugs[r] + self.rank * self.slice) * fb
-                                                 for r, p in enumerate(h.buffer_ptrs)]) for h in self.handles]
-        # NVSwitch multicast (one store lands in every replica): needs the item block at the SAME offset on every rank
-        import os
-        mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.handles]
-        self.multicast = (len(set(self.Ugs)) == 1 and all(mc) and os.environ.get("RECAD_DIST_MULTICAST", "1") != "0")
-        if self.multicast:
-            self._mc_out = [(C.c_void_p * 1)(p + (Ug + self.rank * self.slice) * fb) for p in mc]
+        al = lambda x: (x + 255) // 256 * 256     # noqa: E731
+        off, self.off = 0, {}
+        for name, nbytes in (("X0", n_max * D * 4), ("X1", n_max * D * 4), ("O", n_max * D * 4), ("g", n_max * D * 4),
+                             ("cnt", n_max * 4), ("stage", self.world * self.slice * D * 4), ("signal", 256)):
+            self.off[name] = off
+            off = al(off + nbytes)
+        self.block = symm.empty((off,), dtype=torch.uint8, device=dev)
+        self.block.zero_()
+        self.handle = symm.rendezvous(self.block, self.group)
+        self.handle.barrier(channel=0)                 # every pad is zero before anybody signals
+        self.peer_base = (C.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.peer_users = (C.c_int64 * self.world)(*self.Ugs)
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        self.multicast = bool(len(set(self.Ugs)) == 1 and mc and os.environ.get("RECAD_DIST_MULTICAST", "1") != "0")
+        self.mc_base = mc if self.multicast else None
 
-    def barrier(self):
-        self.h_stage.barrier(channel=0)
-
-    def scatter_item_rows(self, g_item, x_users):
-        """partial item rows R_g^T x_users -> the owners' staging blocks, from inside the SpMM epilogue"""
-        with torch.cuda.device(self.dev):
-            _lib.check(_lib.lib().recad_spmm_scatter(C.byref(g_item.struct(self.D)), x_users.data_ptr(), self._dst, self.world,
-                                                     self.slice, self.D, ops._stream(self.dev)), "recad_spmm_scatter")
-
-    def reduce_bcast(self, k):
-        """sum the world partial copies of my slice (rank order) and store the result into every rank's buffer k"""
-        with torch.cuda.device(self.dev):
-            out, n_out = (self._mc_out[k], 1) if self.multicast else (self._out[k], self.world)
-            _lib.check(_lib.lib().recad_peer_reduce_bcast(self.stage.data_ptr(), self.world, self.slice * self.D,
-                                                          self.rows_mine * self.D, out, n_out, int(self.multicast),
-                                                          ops._stream(self.dev)), "recad_peer_reduce_bcast")
+    def view(self, name, rows, cols=None):
+        n = rows * (cols or 1) * 4
+        t = self.block[self.off[name]:self.off[name] + n].view(torch.float32)
+        return t.view(rows, cols) if cols else t
 
 
 class ShardedLightGCN:
@@ -143,14 +128,16 @@ class ShardedLightGCN:
                 self.E[:Ug].copy_(init_user[self.lo:self.hi])
             self.E[Ug:].copy_(init_item)
             self.m, self.v = torch.zeros_like(self.E), torch.zeros_like(self.E)
-            self.O, self.g = torch.empty_like(self.E), torch.empty_like(self.E)
             self.peer = self._make_peer(fused)
-            if self.peer is not None:                 # layer buffers live in NVLink-mapped memory
-                self.X0, self.X1 = self.peer.bufs[0][:N], self.peer.bufs[1][:N]
+            if self.peer is not None:                 # everything a peer touches lives in the NVLink-mapped block
+                self.X0, self.X1, self.O, self.g = (self.peer.view(k, N, D) for k in ("X0", "X1", "O", "g"))
+                self.cnt = self.peer.view("cnt", N)
             else:
+                self.O, self.g = torch.empty_like(self.E), torch.empty_like(self.E)
                 self.X0, self.X1 = torch.empty_like(self.E), torch.empty_like(self.E)
-            self.cnt = torch.empty(N, dtype=torch.float32, device=self.dev)
+                self.cnt = torch.empty(N, dtype=torch.float32, device=self.dev)
             self.loss_acc = torch.zeros(4, dtype=torch.float64, device=self.dev)
+            self._st = self._shard_struct() if self.peer is not None else None
         self.steps = 0
         self._O_valid = False
         self.n_allreduce = 0
@@ -162,11 +149,11 @@ class ShardedLightGCN:
         import os
         if fused is None and os.environ.get("RECAD_DIST_FUSED", "1") == "0":
             fused = False
-        if fused is False or self.world == 1 or self.D not in (32, 64, 128):
+        if fused is False or self.world == 1 or self.D not in (32, 64, 128) or self.L < 1:
             return None
         peer, err = None, None
         try:
-            peer = _PeerExchange(self.Ug, self.I, self.D, self.dev, self.group)
+            peer = _PeerBlock(self.Ug, self.I, self.D, self.dev, self.group)
         except Exception as e:   # noqa: BLE001 -- no symmetric memory on this system
             err = e
         ok = torch.tensor([0 if peer is None else 1], device=self.dev)
@@ -177,26 +164,72 @@ class ShardedLightGCN:
             return None
         return peer
 
-    # ------------------------------------------------------------------ pieces
+    # ------------------------------------------------------------------ C-driven path (csrc/shard.cu)
+    def _shard_struct(self):
+        p, g = self.peer, self.graph
+        st = _lib.LightGCNShard()
+        st.rank, st.world, st.D, st.n_layers = self.rank, self.world, self.D, self.L
+        st.n_users_local, st.n_items, st.user_lo, st.slice = self.Ug, self.I, self.lo, p.slice
+        st.lam, st.lr, st.beta1, st.beta2, st.eps = self.lam, self.lr, 0.9, 0.999, 1e-8
+        self._csr_user, self._csr_item = self.g_user.struct(self.D), self.g_item.struct(self.D)
+        st.g_user, st.g_item = C.pointer(self._csr_user), C.pointer(self._csr_item)
+        # the rank's own users' sorted distinct items = its user rows of the matrix (columns carry the Ug offset)
+        st.pos_rowptr, st.pos_col, st.pos_col_offset = g.rowptr.data_ptr(), g.colidx.data_ptr(), self.Ug
+        st.E, st.m, st.v, st.loss_acc = self.E.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.loss_acc.data_ptr()
+        st.peer_base, st.mc_base, st.peer_users = p.peer_base, p.mc_base, p.peer_users
+        for k in ("X0", "X1", "O", "g", "cnt", "stage", "signal"):
+            setattr(st, "off_" + k, p.off[k])
+        return st
+
+    def _check_barriers(self):
+        state = (C.c_uint32 * 2)()
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().recad_lightgcn_shard_barrier_state(C.byref(self._st), state, ops._stream(self.dev)), "barrier_state")
+        if state[1]:
+            raise ops.RecadError("ShardedLightGCN: a cross-device barrier timed out (a peer rank never arrived)")
+
+    def _epoch_c(self, ep, n, trace=None):
+        """The whole epoch enqueued by ONE call: no collective library, no host synchronisation inside."""
+        n_batches = (n + self.batch - 1) // self.batch
+        tr = (C.c_double * 8)() if trace is not None else None
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().recad_lightgcn_shard_train_epoch(C.byref(self._st), C.byref(ep), self.batch, self.steps, tr,
+                                                                   ops._stream(self.dev)), "recad_lightgcn_shard_train_epoch")
+        self.steps += n_batches
+        self.n_fused += n_batches * (2 * self.L + 1)
+        self._O_valid = False
+        if trace is not None:
+            trace.update(dict(zip(("item_spmm_push", "user_spmm", "barriers", "slice_reduce_store", "zeroing", "bpr",
+                                   "gradient_exchange", "adam"), [round(float(x), 3) for x in tr])))
+        # [2] = this rank's part of the sum of batch losses, [3] = out-of-range flag (an int in the slot's bits)
+        out = torch.stack([self.loss_acc[2], (self.loss_acc[3:4].view(torch.int64) != 0).double()[0]])
+        dist.all_reduce(out, group=self.group)                   # ONE collective per epoch
+        loss, bad = out.tolist()
+        if bad:
+            raise ops.RecadError("ShardedLightGCN.train_epoch: a sample id is out of range")
+        self._check_barriers()
+        return loss / n_batches
+
+    def train_epoch_soa(self, users, rel, negs, perm=None, trace=None):
+        """One epoch from the host sampler's 32-bit arrays (GLOBAL user id, index of the positive inside the user's row,
+        negative; recad_mt19937_pairwise_soa) + the int32 epoch permutation, every rank holding the whole epoch."""
+        if self._st is None:
+            raise ops.RecadError("train_epoch_soa needs the peer-memory path (symmetric memory)")
+        ep = _lib.EpochSamples()
+        ep.n_samples = int(users.numel())
+        ep.users, ep.rel, ep.negs = users.data_ptr(), rel.data_ptr(), negs.data_ptr()
+        ep.perm32 = perm.data_ptr() if perm is not None else None
+        assert users.dtype == rel.dtype == negs.dtype == torch.int32 and (perm is None or perm.dtype == torch.int32)
+        return self._epoch_c(ep, ep.n_samples, trace)
+
+    # ------------------------------------------------------------------ pieces (NCCL path)
     def _allreduce_items(self, t):
         dist.all_reduce(t[self.Ug:], group=self.group)          # contiguous [I, D] (or [I]) block, in place
         self.n_allreduce += 1
 
     def _spmm_exchange(self, x, y):
-        """y = A_g x with the item block of y summed over ranks."""
+        """y = A_g x with the item block of y summed over ranks (NCCL)."""
         Ug = self.Ug
-        if self.peer is not None:
-            # ONE pass: the item-row SpMM sends every finished partial row to its owner over NVLink from its epilogue;
-            # while that traffic drains the user rows are multiplied; then the owners add the partials (rank order)
-            # and store their slice into every replica.  Two device-side barriers, no NCCL, no extra pass over y.
-            k = 0 if y.data_ptr() == self.X0.data_ptr() else 1
-            self.peer.scatter_item_rows(self.g_item, x[:Ug])
-            ops.spmm(self.g_user, x[Ug:], y[:Ug])
-            self.peer.barrier()
-            self.peer.reduce_bcast(k)
-            self.peer.barrier()
-            self.n_fused += 1
-            return
         if not self.overlap:
             ops.spmm(self.graph, x, y)
             self._allreduce_items(y)
@@ -208,8 +241,15 @@ class ShardedLightGCN:
         work.wait()
 
     def propagate(self):
-        """O = mean_k A^k E (lightgcn.py:82-113), L local SpMMs + L all-reduces of the item block."""
+        """O = mean_k A^k E (lightgcn.py:82-113), L local SpMMs + L exchanges of the item block."""
         L = self.L
+        if self._st is not None:
+            with torch.cuda.device(self.dev):
+                _lib.check(_lib.lib().recad_lightgcn_shard_propagate(C.byref(self._st), ops._stream(self.dev)),
+                           "recad_lightgcn_shard_propagate")
+            self.n_fused += L
+            self._O_valid = True
+            return self.O[:self.Ug], self.O[self.Ug:]
         if L == 0:
             self.O.copy_(self.E)
         x = self.E
@@ -222,22 +262,30 @@ class ShardedLightGCN:
         self._O_valid = True
         return self.O[:self.Ug], self.O[self.Ug:]
 
-    def train_epoch(self, samples, perm=None):
-        """One epoch (lightgcn.py:132-172) over the GLOBAL sample list; returns the mean batch loss."""
+    def train_epoch(self, samples, perm=None, trace=None):
+        """One epoch (lightgcn.py:132-172) over the GLOBAL sample list (int64 [n, 3] rows of GLOBAL ids, perm int64 [n]);
+        returns the mean batch loss."""
+        n = int(samples.shape[0])
+        if self._st is not None:
+            ep = _lib.EpochSamples()
+            ep.n_samples, ep.rows = n, samples.data_ptr()
+            ep.perm64 = perm.data_ptr() if perm is not None else None
+            assert samples.dtype == torch.int64 and samples.is_contiguous() and (perm is None or perm.dtype == torch.int64)
+            return self._epoch_c(ep, n, trace)
         if perm is None:
             perm = torch.arange(samples.shape[0], device=samples.device)
         local, ptr = route_epoch(samples, perm, self.batch, self.lo, self.hi)
-        n = int(samples.shape[0])
         n_batches = len(ptr) - 1
         B_of = [min(self.batch, n - b * self.batch) for b in range(n_batches)]
         parts = torch.zeros((n_batches, 2), dtype=torch.float64, device=self.dev)
-        L, D = self.L, self.D
+        L = self.L
+        self.loss_acc.zero_()
         for b in range(n_batches):
             self.steps += 1
             self.propagate()
             self.g.zero_()
             self.cnt.zero_()
-            self.loss_acc.zero_()
+            self.loss_acc[:2].zero_()                # [3] keeps the out-of-range flag of the whole epoch
             rows = local[ptr[b]:ptr[b + 1]]
             if rows.shape[0]:
                 ops.bpr_fwd_bwd(self.O, self.E, self.Ug, self.I, rows, None, 1.0 / (L + 1), self.g, self.cnt, self.loss_acc,
@@ -382,10 +430,47 @@ class _Rank0Epochs:
 
 
 # ---------------------------------------------------------------------------------------------- bench.py --gpus N
+def parity_check(dev, rank, world):
+    """Small-graph epoch + evaluation on the sharded path against the single-GPU path (rank 0), before anything is timed."""
+    from . import dataset, model, synthetic
+    U, I, E, D, L, B, n = 6000, 1500, 90_000, 64, 3, 8192, 40_000
+    u, i = synthetic.make_edges(U, I, E, seed=5)
+    eu, ei = torch.as_tensor(u, device=dev), torch.as_tensor(i, device=dev)
+    g = torch.Generator().manual_seed(7)
+    init_u, init_i = torch.randn(U, D, generator=g) * 0.1, torch.randn(I, D, generator=g) * 0.1
+    samples = torch.stack([torch.randint(0, U, (n,), generator=g), torch.randint(0, I, (n,), generator=g),
+                           torch.randint(0, I, (n,), generator=g)], 1).to(dev)
+    perm = torch.randperm(n, generator=g).to(dev)
+    m = ShardedLightGCN(U, I, (eu, ei), D=D, n_layers=L, batch=B, device=dev, init_user=init_u.to(dev), init_item=init_i.to(dev))
+    losses = [m.train_epoch(samples, perm) for _ in range(2)]
+    tu, ti = m.gather_tables()
+    res = torch.zeros(4, dtype=torch.float64, device=dev)
+    if rank == 0:
+        data = dataset.ArrayImplicitData("parity", U, I, (eu, ei), dev, batch_size=B, prefetch=False)
+        ref = model.from_config("victim", "lightgcn", latent_dim_rec=D, lightGCN_n_layers=L, device=dev).I(dataset=data)
+        ref.embedding_user.weight.data.copy_(init_u)
+        ref.embedding_item.weight.data.copy_(init_i)
+        data.epoch_samples = lambda device=None: (samples, perm)
+        ref_losses = [ref.train_step()[0] for _ in range(2)]
+        rel = lambda a, b: float(((a - b).abs() / (b.abs() + 2e-2 * b.abs().max())).max())     # noqa: E731
+        res[0] = max(abs(a - b) / abs(b) for a, b in zip(losses, ref_losses))
+        res[1], res[2] = rel(tu, ref.embedding_user.weight), rel(ti, ref.embedding_item.weight)
+        res[3] = 1.0 if (res[0] <= 1e-5 and res[1] <= 1e-4 and res[2] <= 1e-4) else 0.0
+    dist.broadcast(res, 0)
+    out = {"parity_checked": bool(res[3].item()), "loss_rel_err": float(res[0]), "user_table_rel_err": float(res[1]),
+           "item_table_rel_err": float(res[2]), "path": "peer-memory C driver" if m.peer is not None else "NCCL",
+           "case": f"{U} users x {I} items x {E} edges, 2 epochs of {n} samples (batch {B}) vs the single-GPU path on rank 0"}
+    del m
+    return out
+
+
 def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, peaks):
     import time
     U, I, D, L, B = w["n_users"], w["n_items"], w["D"], w["L"], args.batch or w["batch"]
     ev = lambda: torch.cuda.Event(enable_timing=True)     # noqa: E731
+    parity = parity_check(dev, rank, world)
+    if not parity["parity_checked"]:
+        raise ops.RecadError(f"sharded path does not reproduce the single-GPU path: {parity}")
     eu, ei = synth_edges(w, dev)                           # same seed on every rank: identical global edge list
     torch.manual_seed(2023)
     init_u = (torch.randn(U, D) * 0.1)
@@ -394,30 +479,41 @@ def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, 
     m = ShardedLightGCN(U, I, (eu, ei), D=D, n_layers=L, batch=B, device=dev, init_user=init_u.to(dev), init_item=init_i.to(dev))
     torch.cuda.synchronize()
     t_graph = time.time() - t0
-    # rank 0 draws the epoch with the exact MT19937 sampler (needs every user's positives) and broadcasts it
+    if m.peer is None:
+        raise ops.RecadError("bench --gpus N needs the peer-memory path (torch symmetric memory over NVLink)")
+    # rank 0 draws the epoch with the exact MT19937 sampler (needs every user's positives) and broadcasts it:
+    # four 32-bit arrays (user, index of the positive, negative, permutation), 16 bytes per sample
     n = int(eu.numel())
-    samples = torch.empty((n, 3), dtype=torch.int64, device=dev)
-    perm = torch.empty(n, dtype=torch.int64, device=dev)
-    t_sampler = 0.0
+    epoch = torch.empty((4, n), dtype=torch.int32, device=dev)
+    pipe = None
     if rank == 0:
         keys = torch.unique(eu * I + ei)
         ap_ptr = torch.zeros(U + 1, dtype=torch.int64, device=dev)
         ap_ptr[1:] = torch.cumsum(torch.bincount(keys // I, minlength=U), 0)
         ap = (ap_ptr.cpu().numpy(), (keys % I).int().cpu().numpy())
+        del keys
+        from .dataset import _EpochPipe
         np.random.seed(2023)
-        t0 = time.time()
-        S = ops.mt_pairwise(U, I, n, *ap)
-        P = ops.mt_permutation(len(S))
-        t_sampler = time.time() - t0
-        samples.copy_(torch.from_numpy(S))
-        perm.copy_(torch.from_numpy(P))
+        pipe = _EpochPipe(_Rank0Epochs(U, I, *ap))
+        pipe.raw_soa = True
     del eu, ei
-    dist.broadcast(samples, 0)
-    dist.broadcast(perm, 0)
+
+    def fetch_epoch():                                      # host sampler -> pinned H2D (rank 0) -> NVLink broadcast
+        if rank == 0:
+            got = pipe.next(dev)
+            assert len(got) == 4 and int(got[0].numel()) == n, "the synthetic graph has no user without positives"
+            for k in range(4):
+                epoch[k].copy_(got[k], non_blocking=True)
+        dist.broadcast(epoch, 0)
+
+    t0 = time.time()
+    fetch_epoch()
+    torch.cuda.synchronize()
+    t_sampler = time.time() - t0
     n_batches = (n + B - 1) // B
 
-    def step():
-        loss = m.train_epoch(samples, perm)
+    def step(trace=None):
+        loss = m.train_epoch_soa(epoch[0], epoch[1], epoch[2], epoch[3], trace=trace)
         topi, topv, rank_, score = m.full_rank([0], 20)
         hits = (rank_[:, 0] < 20).sum().double().view(1)
         dist.all_reduce(hits)
@@ -438,23 +534,21 @@ def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, 
     ms = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)            # device time, max over ranks
     step_ms = float(ms.item())
-    # end to end: rank 0 draws the epoch on the host (exact sampler), ships it over PCIe, broadcasts it over NVLink
+    # per-phase device timeline of one epoch (CUDA events inside the C driver), max over ranks per phase
+    trace = {}
+    step(trace)
+    tr = torch.tensor([trace[k] for k in sorted(trace)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+    trace = {k: round(float(v), 2) for k, v in zip(sorted(trace), tr.tolist())}
+    # end to end: rank 0 draws the epoch on the host (exact sampler, background threads), ships 16 B / sample over PCIe,
+    # broadcasts it over NVLink; all ranks: sharded epoch + evaluation; steady state of an epoch loop
     e2e = []
-    pipe = None
-    if rank == 0:
-        from .dataset import _EpochPipe
-        pipe = _EpochPipe(_Rank0Epochs(U, I, *ap))
-    prime = 4                                               # untimed: fill the prefetch queue (steady state of an epoch loop)
-    for it in range(prime + max(1, min(args.steps, 4))):
+    prime = 4                                               # untimed: fill the prefetch queue
+    for it in range(prime + max(1, args.steps)):
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.time()
-        if rank == 0:
-            s_dev, p_dev = pipe.next(dev)                   # pinned H2D of an epoch drawn in the background
-            samples.copy_(s_dev)
-            perm.copy_(p_dev)
-        dist.broadcast(samples, 0)
-        dist.broadcast(perm, 0)
+        fetch_epoch()
         step()
         torch.cuda.synchronize()
         dist.barrier()
@@ -474,20 +568,20 @@ def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, 
         "config": {"workload": f"{args.workload}: LightGCN {U} users x {I} items x {w['n_edges']} interactions, D={D}, L={L}, "
                                f"BPR batch {B} ({n_batches} batches/epoch, {n} samples), full-rank eval of all {U} users K=20",
                    "l2": "inputs exceed L2",
-                   "parallelism": (f"user rows sharded over {world} GPUs; per layer the partial item rows [{I} x {D}] fp32 go to their "
-                                   f"owner from the SpMM epilogue over NVLink peer memory, owners reduce and store into every replica "
-                                   f"({m.n_fused // max(1, args.steps + args.warmup + 2)} fused exchanges per epoch); gradient block by NCCL "
-                                   f"({m.n_allreduce // max(1, args.steps + args.warmup + 2)} all-reduces per epoch)") if m.peer is not None else
-                                  (f"user rows sharded over {world} GPUs; per layer one NCCL all-reduce of the item block [{I} x {D}] fp32; "
-                                   f"{m.n_allreduce // max(1, args.steps + args.warmup + 2)} all-reduces per epoch")},
+                   "parallelism": (f"user rows sharded over {world} GPUs, whole epoch enqueued by one C call per rank, no collective "
+                                   f"library inside: per layer / Horner step the partial item rows [{I} x {D}] fp32 go to their owner "
+                                   f"from the SpMM epilogue over NVLink peer memory, the owner reduces and stores into every replica "
+                                   f"({'multimem.st' if m.peer.multicast else 'peer stores'}); gradient block pulled by its owners; "
+                                   f"{2 * L + 1} exchanges per batch, 1 NCCL all-reduce per epoch (loss)")},
         "epoch_loss": loss, "HR@20(target 0)": hr, "graph_build_s": round(t_graph, 4), "host_sampler_s": round(t_sampler, 3),
+        "parity": parity, "phase_ms_per_epoch": trace,
         "roofline": {"bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None,
                      "note": "per-kernel roofline is reported by the 1-GPU run; this line is the sharded whole-step time"},
-        "e2e": {"value": round(float(e2e_t.item()), 6), "unit": "s", "h2d_bytes_per_step": n * 4 * 8, "d2h_bytes_per_step": 60,
+        "e2e": {"value": round(float(e2e_t.item()), 6), "unit": "s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": 60,
                 "per_step_s": [round(t, 3) for t in e2e],
                 "includes": "steady state of an epoch loop: rank 0 draws the next epochs with the exact C++ MT19937 sampler + shuffle on "
-                            "background threads, pinned H2D, NCCL broadcast of samples + permutation; all ranks: sharded epoch + "
+                            "background threads, pinned H2D of 16 B / sample, NCCL broadcast; all ranks: sharded epoch + "
                             "evaluation, metric all-reduce and D2H"},
-        "gpu_launches": args.steps * (n_batches * (4 * L * (2 if m.graph.n_mrow else 1) + 2) + 3),
+        "gpu_launches": args.steps * (n_batches * ((2 * L) * 5 + 9) + 3),
         "clocks": clocks.summary(),
     }

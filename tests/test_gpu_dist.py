@@ -49,6 +49,29 @@ def _worker(rank, world, port, q):
     ok_mc = bool(np.isclose(mc[True][0], mc[False][0], rtol=1e-5)) and all(
         torch.allclose(a, b, rtol=1e-4, atol=2e-6) for a, b in zip(mc[True][1:3], mc[False][1:3]))
     used_multicast = mc[True][3]
+    # the host sampler's 32-bit arrays (user, index of the positive inside the user's row, negative) + int32 permutation
+    # give the same epoch as the equivalent (user, pos, neg) rows
+    keys = torch.unique(eu * I + ei)
+    ap_ptr = torch.zeros(U + 1, dtype=torch.int64, device=dev)
+    ap_ptr[1:] = torch.cumsum(torch.bincount(keys // I, minlength=U), 0)
+    ap_col = keys % I
+    su = samples[:, 0]
+    deg = ap_ptr[su + 1] - ap_ptr[su]
+    rel = (torch.randint(0, 1 << 30, (n,), generator=g).to(dev) % deg.clamp(min=1))
+    rows_eq = torch.stack([su, ap_col[ap_ptr[su] + rel], samples[:, 2]], 1).contiguous()
+    soa = {}
+    for kind in ("soa", "rows"):
+        m4 = rdist.ShardedLightGCN(U, I, (eu, ei), D=D, n_layers=L, batch=B, device=dev, init_user=init_u.to(dev),
+                                   init_item=init_i.to(dev), fused=True)
+        tr = {}
+        if kind == "soa":
+            l4 = m4.train_epoch_soa(su.int(), rel.int(), samples[:, 2].int().contiguous(), perm.int(), trace=tr)
+            assert set(tr) >= {"bpr", "adam", "barriers"} and all(v >= 0 for v in tr.values())
+        else:
+            l4 = m4.train_epoch(rows_eq, perm)
+        soa[kind] = (l4, *m4.gather_tables())
+    ok_soa = bool(np.isclose(soa["soa"][0], soa["rows"][0], rtol=1e-6)) and all(
+        torch.allclose(a, b, rtol=1e-5, atol=1e-7) for a, b in zip(soa["soa"][1:], soa["rows"][1:]))
     # attacked model: 7 fake users appended to the last shard, fresh tables, one epoch that also samples them
     F = 7
     fake = (torch.rand(F, I, generator=g) < 0.03).float() * 5.0          # rating 5 on ~3 % of the items
@@ -89,7 +112,8 @@ def _worker(rank, world, port, q):
         ok2 = np.allclose(loss2, ref_loss2, rtol=1e-5)
         ok2 &= torch.allclose(eu2, ref2.embedding_user.weight, rtol=1e-4, atol=2e-6)
         ok2 &= torch.allclose(ei2, ref2.embedding_item.weight, rtol=1e-4, atol=2e-6)
-        q.put((bool(ok) and bool(ok2) and ok_mc, losses + [loss2, ("multicast", used_multicast, ok_mc)], ref_losses + [ref_loss2]))
+        q.put((bool(ok) and bool(ok2) and ok_mc and ok_soa, losses + [loss2, ("multicast", used_multicast, ok_mc), ("soa", ok_soa)],
+               ref_losses + [ref_loss2]))
     dist.barrier()
     dist.destroy_process_group()
 
