@@ -139,6 +139,13 @@ def run_b200(args, w):
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        # N rank processes share the host with rank 0's sampler threads: a rank waiting for its GPU sleeps instead of spinning
+        import ctypes
+        try:
+            ctypes.CDLL("libcudart.so.12").cudaSetDeviceFlags(4)        # cudaDeviceScheduleBlockingSync, before the context exists
+        except OSError:
+            pass
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

@@ -248,7 +248,7 @@ typedef struct recad_epoch_samples {
  * (torch.distributed._symmetric_memory): peer_base[r] is rank r's block as mapped HERE, off_* are byte offsets inside it:
  *   off_X0 / off_X1 / off_O / off_g : float[max_r(n_users_local_r) + n_items, D]   layer ping / pong, propagated mean, gradient
  *   off_cnt    : float[max_r(n_users_local_r) + n_items]        batch multiplicities
- *   off_stage  : float[world, slice, D]   slot s receives rank s's partial rows of the items THIS rank owns
+ *   off_stage  : float[2, world, slice, D]   (double buffered) slot s receives rank s's partial rows of the items THIS rank owns
  *   off_signal : uint32[64], zero-initialised: [0, world) barrier pad, [32] barrier epoch, [33] timeout flag
  * Rank r owns items [r * slice, (r + 1) * slice).  mc_base: NVSwitch multicast mapping of the block (one store lands in
  * every rank's copy) or NULL; used only when every rank has the same n_users_local. */

@@ -786,6 +786,13 @@ struct StreamReader {
 
 }  // namespace
 
+// sampler_avx512.cpp (built with -mavx512f; entered only when the CPU has it)
+uint64_t recad_shuffle_draws_avx512(const uint32_t* src, uint64_t n_words, uint32_t mask, int64_t* i_io, int64_t band_lo,
+                                    uint32_t* j_out);
+int64_t recad_parse_window_avx512(const uint32_t* ring, uint64_t ring_mask, uint64_t* t_io, uint64_t avail, const uint32_t* lens,
+                                  int64_t k0, int64_t k1, uint32_t* rel, uint32_t* negs, uint32_t* tst, int64_t tst_mask,
+                                  uint32_t neg_r, uint32_t neg_mask, uint32_t n_items);
+
 int recad_mt19937_pairwise_soa(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items, int64_t train_size,
                                const int64_t* allpos_rowptr, const int32_t* allpos_col, const uint64_t* filter,
                                const uint32_t* ext, int32_t n_threads, uint32_t* users, uint32_t* rel, uint32_t* negs,
@@ -795,6 +802,12 @@ int recad_mt19937_pairwise_soa(uint32_t* key, int32_t* pos, int64_t n_users, int
     recad::set_error("mt19937_pairwise_soa: bad argument");
     return RECAD_ERR_ARG;
   }
+#if defined(__x86_64__) && defined(__GNUC__)
+  const bool use_avx512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("bmi") && n_items > 1 &&
+                          !(getenv("RECAD_SAMPLER_SCALAR") && atoi(getenv("RECAD_SAMPLER_SCALAR")));
+#else
+  const bool use_avx512 = false;
+#endif
   const bool trace = getenv("RECAD_SAMPLER_TRACE") != nullptr;
   auto t0 = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -823,7 +836,7 @@ int recad_mt19937_pairwise_soa(uint32_t* key, int32_t* pos, int64_t n_users, int
   for (int64_t u = 0; u < n_users; ++u) deg[u] = (uint32_t)(allpos_rowptr[u + 1] - allpos_rowptr[u]);
   // ---- helper pool: first the length gather (chunks of the user array as they are drawn), then the block checks
   const int n_help = getenv("RECAD_SAMPLER_HELPERS") ? std::max(1, atoi(getenv("RECAD_SAMPLER_HELPERS")))
-                                                     : (int)std::max(1, std::min(n_threads / 2 - 1, 7));
+                                                     : (int)std::max(1, std::min(n_threads - 4, 8));   // parser, producer, swap thread, caller
   constexpr int64_t kChunk = 1 << 15;
   const int64_t n_chunks = (train_size + kChunk - 1) / kChunk;
   std::atomic<int64_t> users_ready{0};            // users [0, users_ready) are drawn
@@ -950,10 +963,23 @@ int recad_mt19937_pairwise_soa(uint32_t* key, int32_t* pos, int64_t n_users, int
     const uint32_t nr = neg_r, nm = neg_mask;
     const int64_t tmask = kTstMask;
     int rc_ = RECAD_OK;
-    for (int64_t k = k0; k < k1; ++k) {
+    int64_t k = k0;
+    while (k < k1) {
+      if (use_avx512 && k1 - k >= 8) {
+        // 64-word windows of the stream, acceptance masks by vector compares, the chain is shift / tzcnt / add
+        if (t + 64 > avail) {
+          rd.t = t;
+          rd.need(64);
+          avail = rd.avail;
+        }
+        k = recad_parse_window_avx512(ringbuf, StreamRing::kMask, &t, avail, lens, k, k1, rel_, negs_, tst_, tmask, nr, nm,
+                                      (uint32_t)std::min<int64_t>(n_items, 0xffffffffLL));
+        if (k >= k1) break;
+        // sample k is extraordinary (or the stream ran dry): the exact scalar code below takes it
+      }
       tst_[k & tmask] = (uint32_t)t;
       const uint32_t len = lens[k];
-      if (__builtin_expect(len == 0, 0)) { rel_[k] = kDropped; continue; }               // implicit.py:63-64
+      if (__builtin_expect(len == 0, 0)) { rel_[k] = kDropped; ++k; continue; }               // implicit.py:63-64
       if (__builtin_expect((int64_t)len >= n_items, 0)) {
         recad::set_error("mt19937_pairwise_soa: user %lld interacted with every item; negative sampling cannot terminate",
                          (long long)users[k]);
@@ -978,6 +1004,7 @@ int recad_mt19937_pairwise_soa(uint32_t* key, int32_t* pos, int64_t n_users, int
         rel_[k] = none ? 0u : (okA0 ? a0 : a1);
         negs_[k] = okB0 ? b0 : b1;
         t += (uint64_t)(cA + (okB0 ? 1 : 2));
+        ++k;
         continue;
       }
       rd.t = t;
@@ -985,6 +1012,7 @@ int recad_mt19937_pairwise_soa(uint32_t* key, int32_t* pos, int64_t n_users, int
       negs_[k] = nr ? rd.masked(nr, nm) : 0u;
       t = rd.t;
       avail = rd.avail;
+      ++k;
     }
     rd.t = t;
     return rc_;
@@ -1078,7 +1106,8 @@ int recad_mt19937_pairwise_soa(uint32_t* key, int32_t* pos, int64_t n_users, int
         uint64_t span = std::min<uint64_t>(rd.avail - rd.t, (uint64_t)(i - band_lo + 1));
         span = std::min<uint64_t>(span, StreamRing::kWords - (rd.t & StreamRing::kMask));
         const uint32_t* src = rd.at(rd.t);
-        for (uint64_t q = 0; q < span; ++q) {
+        const uint64_t q0 = use_avx512 ? recad_shuffle_draws_avx512(src, span, mask, &i, band_lo, j_out) : 0;
+        for (uint64_t q = q0; q < span; ++q) {
           const uint32_t v = src[q] & mask;
           j_out[i] = v;
           i -= (int64_t)v <= i;

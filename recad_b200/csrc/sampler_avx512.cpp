@@ -70,3 +70,30 @@ extern "C" int64_t recad_parse_window_avx512(const uint32_t* ring, uint64_t ring
   *t_io = T;
   return k;
 }
+
+// The draws of np.random.shuffle (implicit.py:24-25) inside one power-of-two band: j[i] = first stream word with
+// (word & mask) <= i, for i descending.  16 words per step: a word is accepted for certain when it is <= i - 15 (i drops
+// by at most 15 inside the step); if any word falls in the 16-wide doubtful zone below i the step is left to the caller's
+// scalar loop (probability 16 / (mask + 1) per word).  Accepted words are compressed, reversed and stored at
+// j[i - cnt + 1 .. i].  Stops while at least 16 acceptances remain in the band.  Returns the words consumed.
+extern "C" uint64_t recad_shuffle_draws_avx512(const uint32_t* src, uint64_t n_words, uint32_t mask, int64_t* i_io,
+                                               int64_t band_lo, uint32_t* j_out) {
+  int64_t i = *i_io;
+  uint64_t q = 0;
+  const __m512i vmask = _mm512_set1_epi32((int)mask);
+  const __m512i lane = _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+  while (q + 16 <= n_words && i - band_lo >= 16 && i >= 32) {
+    const __m512i v = _mm512_and_si512(_mm512_loadu_si512(src + q), vmask);
+    const __mmask16 sure = _mm512_cmple_epu32_mask(v, _mm512_set1_epi32((int)(uint32_t)(i - 15)));
+    const __mmask16 all = _mm512_cmple_epu32_mask(v, _mm512_set1_epi32((int)(uint32_t)i));
+    if (__builtin_expect(all != sure, 0)) break;             // a doubtful word: the caller decides it one by one
+    const int cnt = __builtin_popcount((unsigned)sure);
+    const __m512i packed = _mm512_maskz_compress_epi32(sure, v);
+    const __m512i rev = _mm512_permutexvar_epi32(_mm512_sub_epi32(_mm512_set1_epi32(cnt - 1), lane), packed);
+    _mm512_mask_storeu_epi32(j_out + (i - cnt + 1), (__mmask16)((1u << cnt) - 1u), rev);
+    i -= cnt;
+    q += 16;
+  }
+  *i_io = i;
+  return q;
+}

@@ -7,13 +7,15 @@
 // block per rank (layer buffers X0 / X1, the propagated mean O, the gradient g, the batch multiplicities cnt, the
 // staging slots, the barrier pad), so an exchange is plain loads / stores on peer pointers:
 //   layer / Horner step:  item-row SpMM whose epilogue PUSHES each finished partial row into the owner's staging slot
-//                         | user-row SpMM with the layer-mean / Horner epilogue fused (runs while the pushes drain)
-//                         | barrier | owner adds the `world` partial copies of its slice in rank order, applies the same
-//                         epilogue (mean / Horner) and stores the result into EVERY replica (one multimem.st through the
-//                         NVSwitch multicast mapping, or one peer store per rank) | barrier
+//                         | ONE barrier | user-row SpMM with the layer-mean / Horner epilogue fused | owner adds the `world`
+//                         partial copies of its slice in rank order, applies the same epilogue (mean / Horner) and stores
+//                         the result into EVERY replica (one multimem.st through the NVSwitch multicast mapping, or one
+//                         peer store per rank); those stores are certified by the NEXT exchange's barrier (staging slots
+//                         are double buffered), a sequence of exchanges ends with one more barrier
 //   gradient block:       BPR (each rank walks the global batch and keeps its users' samples) | barrier | owner PULLS
 //                         its slice of every rank's partial gradient over NVLink, adds in rank order, stores the sum
-//                         into every replica (same for the multiplicities) | barrier
+//                         into every replica (same for the multiplicities)
+// = 2 L + 3 barriers per batch.
 // The barrier is a one-block kernel on a monotonically increasing epoch (st.release.sys to every peer's pad, ld.acquire.sys
 // on the own pad), so the whole epoch is enqueued without touching the host.
 #include <algorithm>
@@ -186,26 +188,34 @@ struct Shard {
     return RECAD_OK;
   }
 
-  // y = A x over the sharded matrix.  x: byte offset of a symmetric buffer, or the local table E (x_local);
+  // y = A x over the sharded matrix.  x: local pointer to [users ; items] rows (a symmetric buffer or the table E);
   // item rows: sum of the ranks' partial rows -> raw into buffer off_y (if >= 0) and alpha * (C + sum) into off_z (if >= 0)
   // user rows: the same two outputs, local.  C: local base pointer of [users ; items] rows or null.
+  // ONE barrier per exchange: it sits between the push and the user-row SpMM and certifies two things at once -- every
+  // rank's pushes for THIS exchange have landed, and every owner's stores of the PREVIOUS exchange have landed (the
+  // user-row SpMM is the first kernel that reads them).  The staging slots are double buffered: a rank may push
+  // exchange e + 1 while a slower owner still adds up the slots of exchange e.  The results of the last exchange of a
+  // sequence become visible with finish_exchanges().
+  int n_exchange = 0;
   int spmm_exchange(const float* x, int64_t off_y, const float* C, int64_t off_z, float alpha) {
     const int64_t fD = D;
-    // 1. partial item rows, pushed to their owners from the epilogue
+    const int64_t stage_off = st->off_stage + (int64_t)(n_exchange & 1) * (int64_t)world * slice * fD * (int64_t)sizeof(float);
+    ++n_exchange;
+    // 1. partial item rows, pushed to their owners from the epilogue (reads only local user rows)
     float* dst[kMaxShardPeers];
-    for (int o = 0; o < world; ++o) dst[o] = buf(o, st->off_stage) + (int64_t)rank * slice * fD;
+    for (int o = 0; o < world; ++o) dst[o] = buf(o, stage_off) + (int64_t)rank * slice * fD;
     int rc = recad_spmm_scatter(st->g_item, x, dst, world, slice, D, s);
     if (rc) return rc;
     mark(0);
-    // 2. own user rows (complete), epilogue fused
+    if ((rc = barrier())) return rc;
+    // 2. own user rows (complete), epilogue fused; reads the item block the owners stored in the previous exchange
     rc = recad_spmm(st->g_user, x + Ug * fD, off_y >= 0 ? local(off_y) : nullptr, C, off_z >= 0 ? local(off_z) : nullptr, alpha, D, s);
     if (rc) return rc;
     mark(1);
-    if ((rc = barrier())) return rc;
     // 3. my slice: add the partial copies in rank order, store into every replica
     ReduceArgs a{};
     a.n_src = world;
-    for (int r = 0; r < world; ++r) a.src[r] = local(st->off_stage) + (int64_t)r * slice * fD;
+    for (int r = 0; r < world; ++r) a.src[r] = local(stage_off) + (int64_t)r * slice * fD;
     a.n = rows_mine * fD / 4;
     const int64_t mine = (int64_t)rank * slice * fD;                    // floats into the item block
     a.C = C ? C + Ug * fD + mine : nullptr;
@@ -220,8 +230,9 @@ struct Shard {
     fill(off_z, a.out_z, a.n_z);
     if ((rc = reduce_rows(a))) return rc;
     mark(3);
-    return barrier();
+    return RECAD_OK;
   }
+  int finish_exchanges() { return barrier(); }
 
   // O = mean_k A^k E
   int propagate() {
@@ -233,7 +244,7 @@ struct Shard {
       if (rc) return rc;
       if (!last) x = local(off_y);
     }
-    return RECAD_OK;
+    return finish_exchanges();       // O's item block is complete on every rank
   }
 
   // the item block of g and of cnt: every owner pulls its slice of every rank's partial block, sums, stores into every replica
@@ -262,7 +273,7 @@ struct Shard {
       RECAD_LAUNCH_CHECK();
     }
     mark(6);
-    return barrier();
+    return RECAD_OK;                 // visible after the barrier of the first Horner exchange
   }
 };
 
@@ -321,6 +332,7 @@ int recad_lightgcn_shard_train_epoch(const recad_lightgcn_shard* st, const recad
       if ((rc = sh.spmm_exchange(t, -1, g, off_z, 1.0f))) return rc;
       t = sh.local(off_z);
     }
+    if ((rc = sh.finish_exchanges())) return rc;
     LossFold fold{st->loss_acc, 1.0 / (double)B, 0.5 * (double)st->lambda};
     rc = launch_adam(st->E, t, cnt, st->lambda / (float)B, st->m, st->v, N * D, D,
                      adam_scalars(st->lr, st->beta1, st->beta2, st->eps, step), fold, s);

@@ -47,7 +47,7 @@ class _PeerBlock:
     """Peer-memory plumbing of the C-driven sharded epoch (csrc/shard.cu): ONE NVLink-mapped symmetric block per rank
     (torch symmetric memory) holding every buffer a peer reads or writes -- the layer buffers X0 / X1, the propagated
     mean O, the gradient g (each [n_max, D]), the batch multiplicities cnt [n_max], the staging slots
-    [world, slice, D] (slot s receives rank s's partial rows of the items this rank owns, slice = ceil(I / world)) and
+    [2, world, slice, D] (slot s receives rank s's partial rows of the items this rank owns, slice = ceil(I / world)) and
     the barrier pad -- at the same byte offsets on every rank."""
 
     def __init__(self, Ug, I, D, dev, group):
@@ -67,7 +67,7 @@ class _PeerBlock:
         al = lambda x: (x + 255) // 256 * 256     # noqa: E731
         off, self.off = 0, {}
         for name, nbytes in (("X0", n_max * D * 4), ("X1", n_max * D * 4), ("O", n_max * D * 4), ("g", n_max * D * 4),
-                             ("cnt", n_max * 4), ("stage", self.world * self.slice * D * 4), ("signal", 256)):
+                             ("cnt", n_max * 4), ("stage", 2 * self.world * self.slice * D * 4), ("signal", 256)):
             self.off[name] = off
             off = al(off + nbytes)
         self.block = symm.empty((off,), dtype=torch.uint8, device=dev)
