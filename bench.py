@@ -140,6 +140,8 @@ def run_b200(args, w):
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # the version banner goes to stdout, which carries ONE JSON line
         # N rank processes share the host with rank 0's sampler threads: a rank waiting for its GPU sleeps instead of spinning
         import ctypes
         try:
@@ -151,7 +153,8 @@ def run_b200(args, w):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         from recad_b200 import dist as rdist
-        return rdist.bench_sharded(args, w, dev, rank, world, METRIC, synth_edges, ClockSampler, peaks)
+        return rdist.bench_sharded(args, w, dev, rank, world, METRIC, synth_edges, ClockSampler, peaks,
+                                   workload_string(args.workload, w, args.batch or w["batch"]))
 
     ev = lambda: torch.cuda.Event(enable_timing=True)     # noqa: E731
     U, I, D, L, B = w["n_users"], w["n_items"], w["D"], w["L"], args.batch or w["batch"]
@@ -255,8 +258,7 @@ def run_b200(args, w):
         "metric": METRIC, "value": round(step_ms / 1e3, 6), "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(step_ms, 3), "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: LightGCN {U} users x {I} items x {w['n_edges']} interactions, D={D}, L={L}, "
-                               f"BPR batch {B} ({n_batches} batches/epoch, {n} samples), full-rank eval of all {U} users K=20",
+        "config": {"workload": workload_string(args.workload, w, B),
                    "l2": "inputs exceed L2 (graph + tables > 126 MB)" if graph.nnz * 8 > 126e6 else "L2-resident workload; absolute times only",
                    "parallelism": "single GPU"},
         "epoch_s": round(float(np.mean(ep_ms)) / 1e3, 6), "eval_s": round(float(np.mean(evl_ms)) / 1e3, 6),
@@ -291,7 +293,8 @@ def run_b200(args, w):
             out["gpu_library_baseline"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
         torch.cuda.empty_cache()
     if not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_reference(w, B, graph, m, data, steps=1)
+        torch.set_num_threads(os.cpu_count() or 1)
+        out["cpu_baseline"] = (reference_lightgcn(w, B, None, 1, csr=graph.to_numpy()) or cpu_reference(w, B, graph, m, data, steps=1))
     return out
 
 
@@ -408,25 +411,122 @@ def cpu_reference(w, B, graph=None, model_=None, data=None, steps=1, host_edges=
             "epoch_s": round(epoch_s, 3), "eval_s": round(eval_s, 3), "spmm_s": round(spmm, 4)}
 
 
+def workload_string(name, w, B):
+    U, I, D, L = w["n_users"], w["n_items"], w["D"], w["L"]
+    n = w["n_edges"]            # the pairwise sampler draws one sample per interaction (implicit.py:56-57)
+    return (f"{name}: LightGCN {U} users x {I} items x {w['n_edges']} interactions, D={D}, L={L}, "
+            f"BPR batch {B} ({(n + B - 1) // B} batches/epoch, {n} samples), full-rank eval of all {U} users K=20")
+
+
+class _StubDataset:
+    """The slice of the dataset interface the reference's LightGCN touches (lightgcn.py:32-34, 136): shapes, the
+    normalised adjacency as a coalesced torch sparse COO tensor (implicit.py:295-296) and pre-sampled batches.  The
+    reference's own dataset code cannot build a 50 M-interaction graph (Python dok / lil + per-user loops)."""
+    dataset_name = "stub"
+
+    def __init__(self, U, I, graph, batches):
+        self.n_users, self.n_items, self.graph, self.batches = U, I, graph, batches
+
+    def info_describe(self):
+        return {"n_users": self.n_users, "n_items": self.n_items, "graph": self.graph}
+
+    def generate_batch(self, **kw):
+        yield from self.batches
+
+    def mode(self):
+        return "train"
+
+    def switch_mode(self, mode):
+        pass
+
+
+def reference_lightgcn(w, B, host_edges, steps, csr=None):
+    """The reference's OWN model class (recad.model.victim.LightGCN from baseline/_ref, unmodified) on the host cores:
+    `train_step()` over a bounded number of batches and `getUsersRating` + topk over a bounded number of users,
+    extrapolated to one epoch + one evaluation of every user."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "recad")):
+        return None
+    cwd = os.getcwd()
+    import tempfile
+    os.chdir(tempfile.mkdtemp())                     # the reference creates ./generated relative to cwd at import
+    sys.path.insert(0, ref)
+    try:
+        import recad
+        from oracle import graph as og
+        from oracle import lightgcn as olg
+        U, I, D, L = w["n_users"], w["n_items"], w["D"], w["L"]
+        N = U + I
+        if csr is not None:                           # the device-built matrix: bit-equal to the reference's (tests/test_gpu_graph_spmm.py)
+            ptr, col, val = csr
+        else:
+            ptr, col, val, _, _ = og.norm_adj_csr(host_edges[0], host_edges[1], U, I)   # scipy fast path of implicit.py:243-298
+        A = olg.csr_to_torch_coo(ptr, col, val, N)
+        nnz = len(col)
+        del ptr, col, val
+        n = w["n_edges"]
+        n_batches = (n + B - 1) // B
+        g = torch.Generator().manual_seed(0)
+        Bs = min(B, n)
+
+        def batch():
+            return {"users": torch.randint(0, U, (Bs,), generator=g), "positive_items": torch.randint(0, I, (Bs,), generator=g),
+                    "negative_items": torch.randint(0, I, (Bs,), generator=g)}
+        data = _StubDataset(U, I, A, [batch()])
+        torch.manual_seed(2023)
+        m = recad.model.from_config("victim", "lightgcn", latent_dim_rec=D, lightGCN_n_layers=L,
+                                    device=torch.device("cpu")).I(dataset=data)
+        assert type(m).__module__ == "recad.model.victim.lightgcn"
+        t_step, t_comp, t_rate = [], [], []
+        ne = min(2048, U)
+        for _ in range(steps):
+            data.batches = [batch()]
+            t0 = time.time()
+            m.train_step()                                           # lightgcn.py:132-172, ONE batch of the epoch
+            t_step.append(time.time() - t0)
+            with torch.no_grad():
+                m.eval()
+                t0 = time.time()
+                users_emb, items_emb = m.computer()                  # what getUsersRating starts with (lightgcn.py:116)
+                t_comp.append(time.time() - t0)
+                t0 = time.time()
+                torch.topk(m.f(torch.matmul(users_emb[:ne], items_emb.t())), 20)    # lightgcn.py:117-120 + top-20
+                t_rate.append((time.time() - t0) / ne)
+        step_s, comp_s, rate_s = float(np.mean(t_step)), float(np.mean(t_comp)), float(np.mean(t_rate))
+        epoch_s, eval_s = n_batches * step_s, comp_s + rate_s * U
+        return {"value": round(epoch_s + eval_s, 3), "unit": "s", "cores": torch.get_num_threads(), "kind": "reference",
+                "sample": f"unmodified recad.model.victim.LightGCN (baseline/_ref) on a stub dataset over the full-size graph (nnz {nnz}): "
+                          f"{steps} x [train_step() over 1 of the {n_batches} batches of {Bs} ({step_s:.2f} s), computer() ({comp_s:.2f} s), "
+                          f"getUsersRating-style matmul + sigmoid + topk of {ne} users ({rate_s * 1e3:.3f} ms/user)]; extrapolated: "
+                          f"{n_batches} x train_step + computer + n_users x rating; the reference's own evaluation loop "
+                          f"(normal.py:62-71: one computer() PER USER = {comp_s:.1f} s/user) is NOT charged",
+                "epoch_s": round(epoch_s, 3), "eval_s": round(eval_s, 3), "batch_step_s": round(step_s, 3), "computer_s": round(comp_s, 3)}
+    finally:
+        sys.path.remove(ref)
+        os.chdir(cwd)
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return None
+    torch.set_num_threads(os.cpu_count() or 1)       # torchrun exports OMP_NUM_THREADS=1: the reference gets every host core
     B = args.batch or w["batch"]
     t0 = time.time()
     # same generator as the GPU arm, on the CPU torch device (seeded identically; streams differ by device)
     eu, ei = synth_edges(w, torch.device("cpu"))
     edges = (eu.numpy(), ei.numpy())
     t_gen = time.time() - t0
-    base = cpu_reference(w, B, host_edges=edges, steps=max(1, args.steps))
-    U, I, D, L = w["n_users"], w["n_items"], w["D"], w["L"]
+    steps = max(1, min(args.steps, 2))               # each step is ~1 min of host work at the synthetic size
+    base = reference_lightgcn(w, B, edges, steps) or cpu_reference(w, B, host_edges=edges, steps=steps)
     return {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": base["value"] * 1e3, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: LightGCN {U} users x {I} items x {w['n_edges']} interactions, D={D}, L={L}, BPR batch {B}",
+        "config": {"workload": workload_string(args.workload, w, B),
+                   "l2": "inputs exceed L2 (graph + tables > 126 MB)" if w["n_edges"] * 16 > 126e6 else "L2-resident workload; absolute times only",
                    "parallelism": f"{base['cores']} host threads (torch CPU)"},
-        "cpu_baseline": base, "edge_gen_s": round(t_gen, 2),
+        "cpu_baseline": base, "edge_gen_s": round(t_gen, 2), "timed_steps": steps,
         "e2e": {"value": base["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
 

@@ -464,7 +464,7 @@ def parity_check(dev, rank, world):
     return out
 
 
-def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, peaks):
+def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, peaks, workload):
     import time
     U, I, D, L, B = w["n_users"], w["n_items"], w["D"], w["L"], args.batch or w["batch"]
     ev = lambda: torch.cuda.Event(enable_timing=True)     # noqa: E731
@@ -565,9 +565,8 @@ def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, 
         "metric": metric, "value": round(step_ms / 1e3, 6), "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(step_ms, 3), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: LightGCN {U} users x {I} items x {w['n_edges']} interactions, D={D}, L={L}, "
-                               f"BPR batch {B} ({n_batches} batches/epoch, {n} samples), full-rank eval of all {U} users K=20",
-                   "l2": "inputs exceed L2",
+        "config": {"workload": workload,
+                   "l2": "inputs exceed L2 (graph + tables > 126 MB)",
                    "parallelism": (f"user rows sharded over {world} GPUs, whole epoch enqueued by one C call per rank, no collective "
                                    f"library inside: per layer / Horner step the partial item rows [{I} x {D}] fp32 go to their owner "
                                    f"from the SpMM epilogue over NVLink peer memory, the owner reduces and stores into every replica "

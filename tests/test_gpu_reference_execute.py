@@ -1,0 +1,109 @@
+"""The drop-in proven through the reference's OWN workflow: the unmodified reference package (installed under
+baseline/_ref, it travels to the GPU box) builds a "no defense" workflow with its own factories, its own explicit
+attack dataset and its own RandomAttacker; `recad_b200.register.install(override=True)` has rebound the victim classes,
+the implicit dataset and the evaluator to the CUDA path; `Normal.execute()` (recad/workflow/normal.py:162-225) then
+reproduces the table the live all-reference CPU run printed (tests/golden/meta.json, made by tests/golden/make_golden.py).
+"""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from . import util
+
+pytestmark = pytest.mark.gpu
+REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+@pytest.fixture()
+def ref_recad(tmp_path, monkeypatch):
+    if not os.path.isdir(os.path.join(REF, "recad")):
+        pytest.skip("baseline/_ref (pip install --target of the reference) is absent")
+    monkeypatch.chdir(tmp_path)                       # the reference resolves ./data and ./generated against cwd
+    sys.path.insert(0, REF)
+    try:
+        import recad
+        import recad_b200.register as reg
+        saved = (dict(recad.model.factories["victim"]), dict(recad.dataset.factories), recad.workflow.Normal.normal_evaluate,
+                 recad.workflow.Defense.normal_evaluate)
+        reg.install(override=True)
+        yield recad
+        recad.model.factories["victim"].clear(); recad.model.factories["victim"].update(saved[0])
+        recad.dataset.factories.clear(); recad.dataset.factories.update(saved[1])
+        recad.workflow.Normal.normal_evaluate, recad.workflow.Defense.normal_evaluate = saved[2], saved[3]
+    finally:
+        sys.path.remove(REF)
+
+
+@pytest.mark.parametrize("victim,kw,sample", [("lightgcn", {"latent_dim_rec": 64}, "pairwise"), ("mf", {"embedding_size": 64}, "pointwise")])
+def test_reference_execute_runs_on_the_cuda_path(ref_recad, victim, kw, sample):
+    recad = ref_recad
+    from recad_b200 import dataset as b_dataset, victim as b_victim
+    dev = torch.device("cuda:0")
+    z = util.load(f"workflow_{victim}_dev.npz")
+    gold = util.meta()[f"workflow_{victim}_dev"]
+    ex = util.load("dev_explicit.npz")
+    tr, va, te = util.dicts("dev")
+    random.seed(2023); np.random.seed(2023); torch.manual_seed(2023)
+    cfg = {
+        # the reference's own factories (recad/dataset/__init__.py:13, recad/model/__init__.py:3-21)
+        "victim_data": recad.dataset.from_config("implicit", "dev", need_graph=victim == "lightgcn", sample=sample, device=dev,
+                                                 train_dict=tr, valid_dict=va, test_dict=te),
+        "attack_data": recad.dataset.from_config("explicit", "dev", device=torch.device("cpu"), train_dict=ex["train"].copy(),
+                                                 valid_dict=ex["valid"].copy(), test_dict=ex["test"].copy()).partial_sample(user_ratio=0.2),
+        "victim": recad.model.from_config("victim", victim, device=dev, **kw),
+        "attacker": recad.model.from_config("attacker", "random", filler_num=36, device=torch.device("cpu")),
+        "rec_epoch": gold["rec_epoch"], "attack_epoch": 1, "device": dev,
+    }
+    assert isinstance(cfg["victim_data"], b_dataset.ImplicitData) and isinstance(cfg["victim"], b_victim.factories[victim])
+    assert type(cfg["attacker"]).__module__.startswith("recad.") and type(cfg["attack_data"]).__module__.startswith("recad.")
+    wf = recad.workflow.from_config("no defense", **cfg)
+    assert type(wf).__module__ == "recad.workflow.normal"
+    # same starting point as the golden run: initial weights and both generator states as recorded there
+    init = {k[len("init__"):]: z[k] for k in z.files if k.startswith("init__")}
+    sd = wf.victim.state_dict()
+    rng_ok = all(np.array_equal(sd[k].cpu().numpy(), v) for k, v in init.items() if k in sd)
+    for k, v in init.items():
+        if k in sd:
+            sd[k].copy_(torch.as_tensor(v))
+    np.random.set_state(("MT19937", z["np_key_start"], int(z["np_pos_start"]), 0, 0.0))
+    torch.set_rng_state(torch.as_tensor(z["torch_state_start"]))
+    seen = {}
+    gen_fake = wf.attacker.generate_fake
+
+    def cap_fake(**kwargs):
+        seen["fake"] = gen_fake(**kwargs)
+        return seen["fake"]
+    wf.attacker.generate_fake = cap_fake
+    ev = type(wf).normal_evaluate
+
+    def cap_eval(self, *a, **k):
+        seen["table"] = ev(self, *a, **k)
+        return seen["table"]
+    type(wf).normal_evaluate = cap_eval
+    try:
+        wf.execute()                                  # the reference's own driver, recad/workflow/normal.py:162-225
+    finally:
+        type(wf).normal_evaluate = ev
+    # the reference's attacker drew its profiles from np.random AFTER our sampler consumed the stream during step 1:
+    # equal fake profiles = the sampler left the generator exactly where the reference's Python loop leaves it
+    fake = np.zeros(tuple(z["fake_shape"]), dtype=np.float64)
+    fake[z["fake_rows"], z["fake_cols"]] = z["fake_vals"]
+    assert np.array_equal(np.asarray(seen["fake"], dtype=np.float64), fake)
+    final = {k[len("final__"):]: z[k] for k in z.files if k.startswith("final__")}
+    sd = wf.victim.state_dict()
+    for k, v in final.items():
+        if k in sd and k != "mean":
+            assert np.allclose(sd[k].cpu().numpy(), v, rtol=1e-4, atol=2e-6), k
+    n_eval = 310
+    for k, v in gold["table"].items():
+        if "after attack" in k or k == "pred_shift":
+            if not rng_ok:
+                continue                               # the attacked model's init needs the same torch CPU stream
+            tol = dict(rtol=1e-2, atol=2e-6) if k == "pred_shift" else dict(rtol=2e-3, atol=1.5 / n_eval)
+            assert np.isclose(seen["table"][k], v, **tol), (k, seen["table"][k], v)
+        else:
+            assert np.isclose(seen["table"][k], v, rtol=1e-4, atol=1.0 / n_eval), (k, seen["table"][k], v)
