@@ -223,6 +223,16 @@ int recad_bpr_fwd_bwd_i32(const float* O, const float* E, int64_t n_users, int64
 int recad_lightgcn_train_epoch_i32(const recad_lightgcn* st, const int32_t* samples, const int32_t* perm,
                                    int64_t n_samples, int64_t batch, int64_t step0, void* stream);
 
+/* Candidate users of the evaluation (normal.py:133-143), built on the device: users with a non-empty train row (or, when
+ * is_key [dev] uint8[n_users] is given, the users that are KEYS of train_dict), none of the targets in their train
+ * row, and at least one candidate item left; ascending ids into users_out [dev] int64[n_users], count into *n_out [host]
+ * (the call synchronises the stream to return it).  train rows sorted ascending.  targets [dev] int32[n_targets].
+ * scratch [dev]: recad_eligible_users_scratch_bytes(n_users) bytes. */
+int64_t recad_eligible_users_scratch_bytes(int64_t n_users);
+int recad_eligible_users(const int64_t* train_rowptr, const int32_t* train_col, int64_t n_users, int64_t n_items,
+                         const int32_t* targets, int32_t n_targets, const uint8_t* is_key, int64_t* users_out,
+                         int64_t* n_out, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* ------------------------------------------------------------------------ *
  * User-sharded LightGCN epoch (same math as recad_lightgcn_train_epoch,
  * lightgcn.py:82-172), one process per GPU, exchanges over NVLink peer memory only.

@@ -113,6 +113,8 @@ SIGNATURES = {
     "recad_fullrank_eval": (C.c_int, [vp, vp, i64, i64, i32, vp, i64, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
     "recad_fullrank_tc_scratch_floats": (i64, [i64, i64]),
     "recad_fullrank_eval_tc": (C.c_int, [vp, vp, i64, i32, vp, i64, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "recad_eligible_users_scratch_bytes": (i64, [i64]),
+    "recad_eligible_users": (C.c_int, [vp, vp, i64, i64, vp, i32, vp, vp, C.POINTER(i64), vp, i64, vp]),
     "recad_recall_ndcg": (C.c_int, [vp, i64, i32, vp, vp, vp, vp, vp]),
     "recad_rank_from_scores": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
     "recad_mt19937_pairwise": (C.c_int, [vp, C.POINTER(i32), i64, i64, i64, vp, vp, vp, C.POINTER(i64)]),

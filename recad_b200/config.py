@@ -77,12 +77,14 @@ for _m in MODEL["victim"].values():
 WORKFLOW = {   # default.py:247-282
     "no defense": {
         "rec_epoch": 400, "attack_epoch": 100, "target_id_list": [0], "filter_num": 4, "topks": [10, 20, 50, 100],
-        "logging_level": logging.INFO, "device": DEVICE,
+        "logging_level": logging.INFO, "device": DEVICE, "verbose": True,
+        "validate_every": 0, "validate_k": 20,       # per-epoch Recall/NDCG on the validation split (0 = off, as the reference)
         "cache_dir": os.path.abspath(os.path.join(".", "workflows_results")),
     },
     "defense": {
         "rec_epoch": 400, "attack_epoch": 100, "target_id_list": [0], "filter_num": 4, "topks": [10, 20, 50, 100],
-        "defense_epoch": 1, "logging_level": logging.INFO, "device": DEVICE,
+        "defense_epoch": 1, "logging_level": logging.INFO, "device": DEVICE, "verbose": True,
+        "validate_every": 0, "validate_k": 20,
         "cache_dir": os.path.abspath(os.path.join(".", "workflows_results")),
     },
 }

@@ -318,6 +318,36 @@ static int launch_fullrank(const float* user_emb, const float* item_T, int64_t l
 
 using namespace recad;
 
+// ------------------------------------------------------------------------------------------
+// Candidate users of the evaluation (normal.py:133-143): train users with NO target item in their train row and at
+// least one candidate item left, ascending.  flags -> exclusive scan -> compaction; train rows are sorted, so a target
+// is looked up by binary search.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+eligible_flag_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n_users, int64_t n_items,
+                     const int32_t* __restrict__ targets, int n_targets, const uint8_t* __restrict__ is_key, uint32_t* __restrict__ flag) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_users) return;
+  const int64_t lo = rowptr[u], hi = rowptr[u + 1];
+  bool ok = is_key ? is_key[u] != 0 : hi > lo;                 // every KEY of train_dict is evaluated, even with an empty list
+  ok = ok && (hi - lo) < n_items;                              // no candidate left: skipped (normal.py:63-64)
+  for (int t = 0; ok && t < n_targets; ++t) {
+    const int32_t x = targets[t];
+    int64_t a = lo, b = hi;
+    while (a < b) {
+      const int64_t m = (a + b) >> 1;
+      if (col[m] < x) a = m + 1; else b = m;
+    }
+    if (a < hi && col[a] == x) ok = false;
+  }
+  flag[u] = ok ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256)
+eligible_compact_kernel(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos, int64_t n_users, int64_t* __restrict__ out) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < n_users && flag[u]) out[pos[u]] = u;
+}
+
 extern "C" {
 
 int recad_transpose_items(const float* item_emb, int64_t n_items, int32_t D, float* item_T, int64_t ld, void* stream) {
@@ -374,6 +404,34 @@ int recad_recall_ndcg(const int32_t* topk_idx, int64_t n_eval, int32_t K, const 
   recall_ndcg_kernel<<<(unsigned)((n_eval + 255) / 256), 256, 0, as_stream(stream)>>>(topk_idx, n_eval, K, user_ids,
                                                                                        gt_rowptr, gt_col, out);
   RECAD_LAUNCH_CHECK();
+  return RECAD_OK;
+}
+
+int64_t recad_eligible_users_scratch_bytes(int64_t n_users) { return 2 * ((n_users + 3) / 4 * 4) * (int64_t)sizeof(uint32_t) + scan_scratch_bytes(n_users) + 64; }
+
+int recad_eligible_users(const int64_t* train_rowptr, const int32_t* train_col, int64_t n_users, int64_t n_items,
+                         const int32_t* targets, int32_t n_targets, const uint8_t* is_key, int64_t* users_out, int64_t* n_out,
+                         void* scratch, int64_t scratch_bytes, void* stream) {
+  RECAD_REQUIRE(train_rowptr && users_out && n_out && scratch && n_users > 0 && n_items > 0 && n_targets >= 0 &&
+                    (n_targets == 0 || targets) && scratch_bytes >= recad_eligible_users_scratch_bytes(n_users),
+                RECAD_ERR_ARG, "eligible_users: bad argument");
+  cudaStream_t s = as_stream(stream);
+  const int64_t n4 = (n_users + 3) / 4 * 4;
+  uint32_t* flag = static_cast<uint32_t*>(scratch);
+  uint32_t* pos = flag + n4;
+  unsigned long long* total = reinterpret_cast<unsigned long long*>(pos + n4);
+  void* scan_scratch = reinterpret_cast<char*>(total) + 64;
+  const unsigned grid = (unsigned)((n_users + 255) / 256);
+  eligible_flag_kernel<<<grid, 256, 0, s>>>(train_rowptr, train_col, n_users, n_items, targets, n_targets, is_key, flag);
+  RECAD_LAUNCH_CHECK();
+  int rc = exclusive_scan_u32(flag, pos, n_users, total, scan_scratch, s);
+  if (rc) return rc;
+  eligible_compact_kernel<<<grid, 256, 0, s>>>(flag, pos, n_users, users_out);
+  RECAD_LAUNCH_CHECK();
+  unsigned long long h = 0;
+  RECAD_CUDA_CHECK(cudaMemcpyAsync(&h, total, sizeof(h), cudaMemcpyDeviceToHost, s));
+  RECAD_CUDA_CHECK(cudaStreamSynchronize(s));
+  *n_out = (int64_t)h;
   return RECAD_OK;
 }
 

@@ -445,6 +445,22 @@ def rank_from_scores(scores, user_ids, train_rowptr, train_col, targets, K):
     return topi, topv, trank[:, :T], tscore[:, :T]
 
 
+def eligible_users(train_rowptr, train_col, n_users, n_items, targets, is_key=None):
+    """Candidate users of the evaluation (normal.py:133-143) as an ascending int64 device tensor."""
+    _need_cuda(train_rowptr, train_col, is_key)
+    dev = train_rowptr.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        t = torch.as_tensor(list(targets), dtype=torch.int32, device=dev)
+        out = torch.empty(n_users, dtype=torch.int64, device=dev)
+        nbytes = L.recad_eligible_users_scratch_bytes(n_users)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        n = C.c_int64()
+        check(L.recad_eligible_users(_ptr(train_rowptr), _ptr(train_col), n_users, n_items, _ptr(t), int(t.numel()), _ptr(is_key),
+                                     _ptr(out), C.byref(n), _ptr(scratch), nbytes, _stream(dev)), "recad_eligible_users")
+    return out[:n.value]
+
+
 def recall_ndcg(topk_idx, user_ids, gt_rowptr, gt_col):
     """Sums of Recall@K / NDCG@K and the number of users with ground truth."""
     _need_cuda(topk_idx, user_ids, gt_rowptr, gt_col)

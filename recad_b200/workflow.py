@@ -26,6 +26,7 @@ class Normal:
         self.victim_data = config["victim_data"]
         self.logger = get_logger(__name__, level=self.c["logging_level"])
         self.results = None
+        self.validation_log = []
 
     @classmethod
     def from_config(cls, **kwargs):
@@ -45,12 +46,20 @@ class Normal:
         """normal.py:95-109: one train_step per epoch; its tuple must match output_describe()."""
         model = config["model"]
         last = None
-        for _ in range(config["epoch"]):
+        every = int(self.c.get("validate_every", 0) or 0)
+        for e in range(config["epoch"]):
             loss = model.train_step(**self.info_describe(), progress_bar=None)
             out_des = model.output_describe()["train_step"]
             assert len(loss) == len(out_des), \
                 f"The output describe is not aligned with the actual output of train_step for {model.model_name}"
             last = loss
+            # optional per-epoch validation through the dataset's test-mode batches (implicit.py:461-476): the fused
+            # full-rank + Recall/NDCG kernels make it cheap enough to run every epoch (off by default, as in the reference)
+            if every and (e + 1) % every == 0 and hasattr(model, "full_rank") and hasattr(config.get("dataset"), "switch_mode"):
+                res = evaluate.recall_ndcg_batches(model, config["dataset"], K=self.c.get("validate_k", 20), split="validate")
+                self.validation_log.append({"epoch": e + 1, **res})
+                self.logger.info(f"epoch {e + 1}: recall@{self.c.get('validate_k', 20)} {res['recall']:.5f} ndcg {res['ndcg']:.5f} "
+                                 f"({res['n_users']} users)")
         return last
 
     def normal_evaluate(self, model, model_fake, dataset, target_id_list, topks):

@@ -199,6 +199,55 @@ def test_recall_ndcg_matches_oracle_definition():
     assert got["n_users"] == len(users)
 
 
+def test_device_candidate_users_and_batch_driven_validation():
+    """Evaluation front-end on the device (normal.py:133-143): the candidate users come out of a flag / scan / compaction
+    over the device copy of the train rows and equal the host construction for every target list, including targets that
+    many users trained on, a user who interacted with everything and keys with an empty list; and Recall/NDCG driven by
+    the dataset's test-mode batches (implicit.py:461-476) equals the CSR-driven evaluation."""
+    from recad_b200 import dataset, evaluate
+    tr, va, te = util.dicts("game")
+    tr = {k: list(v) for k, v in tr.items()}
+    g = np.random.default_rng(3)
+    I_all = 1 + max(max(v) for v in list(tr.values()) + list(va.values()) + list(te.values()) if len(v))
+    some = sorted(tr)[:3]
+    tr[some[0]] = list(range(I_all))                    # no candidate left
+    tr[some[1]] = []                                    # a key with an empty list is still evaluated
+    data = dataset.from_config("implicit", "game", train_dict=tr, valid_dict=va, test_dict=te, need_graph=False,
+                               sample="pointwise", device=torch.device(DEV))
+    U, I = data.n_users, data.n_items
+    ptr, col = data.train_csr()
+    popular = np.argsort(-np.bincount(col, minlength=I))[:3].tolist()
+    for targets in ([0], [5, 17], popular, [I - 1], []):
+        host = evaluate.eligible_users(data, targets)
+        devu = evaluate.eligible_users(data, targets, device=torch.device(DEV))
+        assert devu.is_cuda and devu.dtype == torch.int64
+        assert np.array_equal(devu.cpu().numpy(), host), targets
+        assert some[0] not in host and (some[1] in host) == (some[1] < U)
+    tabs = [g.standard_normal((U, 64)).astype(np.float32), g.standard_normal((U, 1)).astype(np.float32),
+            g.standard_normal((I, 64)).astype(np.float32), g.standard_normal((I, 1)).astype(np.float32)]
+    m = _mf_model(U, I, tabs, data)
+    for split in ("test", "validate"):
+        a = evaluate.recall_ndcg(m, data, K=20, split="valid" if split == "validate" else split)
+        b = evaluate.recall_ndcg_batches(m, data, K=20, split=split)
+        assert a["n_users"] == b["n_users"] and np.isclose(a["recall"], b["recall"], rtol=1e-12) and np.isclose(a["ndcg"], b["ndcg"], rtol=1e-12)
+    assert data.mode() == "train"
+
+
+def test_per_epoch_validation_in_the_training_driver():
+    from recad_b200 import dataset, model, workflow
+    tr, va, te = util.dicts("dev")
+    data = dataset.from_config("implicit", "dev", train_dict=tr, valid_dict=va, test_dict=te, need_graph=False,
+                               sample="pointwise", device=torch.device(DEV))
+    z = util.load("workflow_mf_dev.npz")
+    torch.manual_seed(2023)
+    wf = workflow.from_config("no defense", victim_data=data, attack_data=None, victim=model.from_config("victim", "mf", device=torch.device(DEV), embedding_size=16),
+                              attacker=FixtureAttacker(z), rec_epoch=3, attack_epoch=1, device=torch.device(DEV), verbose=False, validate_every=1)
+    wf.normal_train(model=wf.victim, epoch=3, dataset=data)
+    assert [r["epoch"] for r in wf.validation_log] == [1, 2, 3]
+    n_valid = sum(1 for v in va.values() if len(v))
+    assert all(r["n_users"] == n_valid and 0.0 <= r["recall"] <= 1.0 for r in wf.validation_log)
+
+
 # ------------------------------------------------------------------ whole workflow
 class FixtureAttacker:
     """Stands in for the reference's RandomAttack (out of scope): replays the fake profiles the

@@ -52,7 +52,7 @@ def test_reference_execute_runs_on_the_cuda_path(ref_recad, victim, kw, sample):
         # the reference's own factories (recad/dataset/__init__.py:13, recad/model/__init__.py:3-21)
         "victim_data": recad.dataset.from_config("implicit", "dev", need_graph=victim == "lightgcn", sample=sample, device=dev,
                                                  train_dict=tr, valid_dict=va, test_dict=te),
-        "attack_data": recad.dataset.from_config("explicit", "dev", device=torch.device("cpu"), train_dict=ex["train"].copy(),
+        "attack_data": recad.dataset.from_config("explicit", "dev", device=torch.device("cpu"), download=False, train_dict=ex["train"].copy(),
                                                  valid_dict=ex["valid"].copy(), test_dict=ex["test"].copy()).partial_sample(user_ratio=0.2),
         "victim": recad.model.from_config("victim", victim, device=dev, **kw),
         "attacker": recad.model.from_config("attacker", "random", filler_num=36, device=torch.device("cpu")),
