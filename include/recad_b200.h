@@ -296,6 +296,34 @@ int recad_lightgcn_shard_train_epoch(const recad_lightgcn_shard* st, const recad
 /* state2 [host] uint32[2] = {barriers passed, 1 if a barrier wait ever timed out}; synchronises the stream. */
 int recad_lightgcn_shard_barrier_state(const recad_lightgcn_shard* st, uint32_t* state2, void* stream);
 
+/* ------------------------------------------------------------------------ *
+ * WMF surrogate of the AIA / Leg-UP attack loop  (recad/model/attacker/aia.py:222-247, 283-289, 393-489)
+ * ------------------------------------------------------------------------ */
+typedef struct recad_wmf {
+  int64_t n_rows, n_items;   /* rows = genuine users + fake users (aia.py:133-141) */
+  int32_t dim, batch;        /* hidden_dim_s in {8, 16, 32}, batch_size_s <= 32 (default.py:179, 182) */
+  float lr, beta1, beta2, eps, weight_decay, weight_pos, weight_neg;
+  int32_t _pad;
+  float* P;                  /* [dev] float[n_rows, dim] */
+  float* Q;                  /* [dev] float[n_items, dim] */
+  float* mP; float* vP; float* mQ; float* vQ;   /* [dev] Adam state, same shapes */
+} recad_wmf;
+
+/* n_epochs epochs of WMFTrainer.fit_adv (aia.py:443-487) in ONE persistent cluster kernel: per batch of `batch` rows
+ * (row ids orders [dev] int32[n_epochs, n_rows], the np.random.shuffle'd idx_list of each epoch, aia.py:447 / 468)
+ * weighted-MSE gradient against data [dev] float[n_rows, n_items] and a dense Adam step with weight decay on P and Q.
+ * unrolled == 0: torch.optim.Adam arithmetic (the plain epochs); unrolled != 0: higher.optim.DifferentiableAdam
+ * arithmetic (the epochs inside higher.innerloop_ctx), and when snap != NULL every step records what the reverse pass
+ * needs (recad_wmf_snapshot_floats(st, n_epochs) floats).  step0 = optimiser steps taken before this call. */
+int64_t recad_wmf_snapshot_floats(const recad_wmf* st, int32_t n_epochs);
+int recad_wmf_fit(const recad_wmf* st, const float* data, const int32_t* orders, int32_t n_epochs, int64_t step0,
+                  int32_t unrolled, float* snap, void* stream);
+/* Reverse pass through the unrolled epochs: Pbar / Qbar [dev] = d loss / d (final P, Q) on entry (overwritten);
+ * d_data [dev] float[n_rows, n_items] += d loss / d data; scratch [dev] 2 * (n_rows + n_items) * dim + 1024 floats.
+ * Same data / orders / step0 / snap as the recad_wmf_fit call that recorded the snapshots. */
+int recad_wmf_backward(const recad_wmf* st, const float* data, const int32_t* orders, int32_t n_epochs, int64_t step0,
+                       const float* snap, float* Pbar, float* Qbar, float* scratch, float* d_data, void* stream);
+
 /* scores[b] = <O[users[b]], O[n_users + items[b]]> (lightgcn.py:174-183 after a
  * propagate; O must be current). */
 int recad_dot_scores(const float* O, int64_t n_users, const int64_t* users, const int64_t* items,

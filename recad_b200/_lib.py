@@ -52,6 +52,13 @@ class LightGCNShard(C.Structure):
     ]
 
 
+class WMF(C.Structure):
+    """struct recad_wmf"""
+    _fields_ = [("n_rows", i64), ("n_items", i64), ("dim", i32), ("batch", i32), ("lr", f32), ("beta1", f32), ("beta2", f32),
+                ("eps", f32), ("weight_decay", f32), ("weight_pos", f32), ("weight_neg", f32), ("_pad", i32),
+                ("P", vp), ("Q", vp), ("mP", vp), ("vP", vp), ("mQ", vp), ("vQ", vp)]
+
+
 class MF(C.Structure):
     """struct recad_mf"""
     _fields_ = [
@@ -99,6 +106,9 @@ SIGNATURES = {
     "recad_lightgcn_shard_propagate": (C.c_int, [C.POINTER(LightGCNShard), vp]),
     "recad_lightgcn_shard_train_epoch": (C.c_int, [C.POINTER(LightGCNShard), C.POINTER(EpochSamples), i64, i64, C.POINTER(C.c_double), vp]),
     "recad_lightgcn_shard_barrier_state": (C.c_int, [C.POINTER(LightGCNShard), C.POINTER(C.c_uint32), vp]),
+    "recad_wmf_snapshot_floats": (i64, [C.POINTER(WMF), i32]),
+    "recad_wmf_fit": (C.c_int, [C.POINTER(WMF), vp, vp, i32, i64, i32, vp, vp]),
+    "recad_wmf_backward": (C.c_int, [C.POINTER(WMF), vp, vp, i32, i64, vp, vp, vp, vp, vp, vp]),
     "recad_dot_scores": (C.c_int, [vp, i64, vp, vp, i64, i32, vp, vp]),
     "recad_mf_forward": (C.c_int, [C.POINTER(MF), vp, vp, i64, vp, vp]),
     "recad_mf_train_epoch": (C.c_int, [C.POINTER(MF), vp, vp, i64, i64, i64, vp]),

@@ -78,9 +78,9 @@ __device__ __forceinline__ void multimem_st4(float* p, float4 a) {
   asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
 }
 
-// kMulticast: out_y[0] / out_z[0] are NVSwitch multicast addresses (one store lands in every replica)
-template <bool kMulticast>
-__global__ void __launch_bounds__(256) shard_reduce_kernel(const __grid_constant__ ReduceArgs a) {
+// kMcY / kMcZ: out_y[0] / out_z[0] is an NVSwitch multicast address (one store lands in every replica)
+template <bool kMcY, bool kMcZ>
+__global__ void __launch_bounds__(512) shard_reduce_kernel(const __grid_constant__ ReduceArgs a) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < a.n; e += (int64_t)gridDim.x * blockDim.x) {
     float4 s = __ldcg(reinterpret_cast<const float4*>(a.src[0]) + e);    // written by peers: read at L2 / over NVLink, never via L1
     for (int r = 1; r < a.n_src; ++r) {
@@ -88,14 +88,14 @@ __global__ void __launch_bounds__(256) shard_reduce_kernel(const __grid_constant
       s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
     }
     if (a.n_y) {
-      if (kMulticast) multimem_st4(a.out_y[0] + 4 * e, s);
+      if (kMcY) multimem_st4(a.out_y[0] + 4 * e, s);
       else for (int r = 0; r < a.n_y; ++r) reinterpret_cast<float4*>(a.out_y[r])[e] = s;
     }
     if (a.n_z) {
       float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a.C) c = reinterpret_cast<const float4*>(a.C)[e];
       const float4 z = make_float4(a.alpha * (c.x + s.x), a.alpha * (c.y + s.y), a.alpha * (c.z + s.z), a.alpha * (c.w + s.w));
-      if (kMulticast) multimem_st4(a.out_z[0] + 4 * e, z);
+      if (kMcZ) multimem_st4(a.out_z[0] + 4 * e, z);
       else for (int r = 0; r < a.n_z; ++r) reinterpret_cast<float4*>(a.out_z[r])[e] = z;
     }
   }
@@ -120,6 +120,26 @@ int launch_bpr_shard_rows(const float* O, const float* E, int64_t U, int64_t I, 
 
 namespace {
 
+// per-device side stream (highest priority) + the two events that tie it to the caller's stream; created once
+struct SideRes {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_go = nullptr, ev_done = nullptr;
+};
+SideRes* side_res() {
+  static SideRes res[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideRes& r = res[dev];
+  if (!r.side) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&r.side, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&r.ev_go, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&r.ev_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &r;
+}
+
 struct Shard {
   const recad_lightgcn_shard* st;
   cudaStream_t s;
@@ -132,6 +152,8 @@ struct Shard {
   // phase trace
   std::vector<std::pair<int, cudaEvent_t>> marks;
   bool trace = false;
+  SideRes* sr = nullptr;
+  bool pending = false;                 // a slice reduce is in flight on the side stream
 
   float* buf(int r, int64_t off) const { return reinterpret_cast<float*>(base[r] + off); }
   float* mc(int64_t off) const { return reinterpret_cast<float*>(reinterpret_cast<char*>(st->mc_base) + off); }
@@ -159,6 +181,28 @@ struct Shard {
       if (st->peer_users[r] != Ug) multicast = false;            // the item block must sit at the same offset everywhere
     }
     bstate = reinterpret_cast<uint32_t*>(base[rank] + st->off_signal) + 32;
+    sr = side_res();
+    RECAD_REQUIRE(sr, RECAD_ERR_CUDA, "lightgcn_shard: cannot create the side stream");
+    return RECAD_OK;
+  }
+
+  // The owner's reduce + store runs on the side stream, next to the SpMMs of the main stream: it is bound by NVLink
+  // ingress (every rank receives the whole item block, 51 MB at I = 200 k), not by SMs, so it gets a small grid.
+  int side_begin() {
+    RECAD_CUDA_CHECK(cudaEventRecord(sr->ev_go, s));
+    RECAD_CUDA_CHECK(cudaStreamWaitEvent(sr->side, sr->ev_go, 0));
+    return RECAD_OK;
+  }
+  int side_end() {
+    RECAD_CUDA_CHECK(cudaEventRecord(sr->ev_done, sr->side));
+    pending = true;
+    return RECAD_OK;
+  }
+  int join_side() {                     // the main stream continues only after the side stream's reduce
+    if (!pending) return RECAD_OK;
+    RECAD_CUDA_CHECK(cudaStreamWaitEvent(s, sr->ev_done, 0));
+    pending = false;
+    mark(3);
     return RECAD_OK;
   }
 
@@ -178,12 +222,14 @@ struct Shard {
     return RECAD_OK;
   }
 
-  // owner's half of an exchange over its slice of the item block
-  int reduce_rows(const ReduceArgs& a) {
+  // owner's half of an exchange over its slice of the item block (side stream)
+  int reduce_rows(const ReduceArgs& a, bool mc_y, bool mc_z) {
     if (a.n <= 0) return RECAD_OK;
-    const unsigned grid = (unsigned)std::min<int64_t>((a.n + 255) / 256, (int64_t)sm_count() * 8);
-    if (multicast) shard_reduce_kernel<true><<<grid, 256, 0, s>>>(a);
-    else shard_reduce_kernel<false><<<grid, 256, 0, s>>>(a);
+    const unsigned grid = (unsigned)std::min<int64_t>((a.n + 511) / 512, 48);
+    if (mc_y && mc_z) shard_reduce_kernel<true, true><<<grid, 512, 0, sr->side>>>(a);
+    else if (mc_y) shard_reduce_kernel<true, false><<<grid, 512, 0, sr->side>>>(a);
+    else if (mc_z) shard_reduce_kernel<false, true><<<grid, 512, 0, sr->side>>>(a);
+    else shard_reduce_kernel<false, false><<<grid, 512, 0, sr->side>>>(a);
     RECAD_LAUNCH_CHECK();
     return RECAD_OK;
   }
@@ -197,7 +243,9 @@ struct Shard {
   // exchange e + 1 while a slower owner still adds up the slots of exchange e.  The results of the last exchange of a
   // sequence become visible with finish_exchanges().
   int n_exchange = 0;
-  int spmm_exchange(const float* x, int64_t off_y, const float* C, int64_t off_z, float alpha) {
+  // z_all: the epilogue result alpha * (C + sum) goes to EVERY replica (Horner steps, the last forward layer); otherwise only
+  // to the owner's own copy (the running mean of the inner forward layers is needed by nobody else until the last layer)
+  int spmm_exchange(const float* x, int64_t off_y, const float* C, int64_t off_z, float alpha, bool z_all) {
     const int64_t fD = D;
     const int64_t stage_off = st->off_stage + (int64_t)(n_exchange & 1) * (int64_t)world * slice * fD * (int64_t)sizeof(float);
     ++n_exchange;
@@ -207,12 +255,14 @@ struct Shard {
     int rc = recad_spmm_scatter(st->g_item, x, dst, world, slice, D, s);
     if (rc) return rc;
     mark(0);
+    if ((rc = join_side())) return rc;              // the previous exchange's stores were issued before this barrier
     if ((rc = barrier())) return rc;
+    if ((rc = side_begin())) return rc;
     // 2. own user rows (complete), epilogue fused; reads the item block the owners stored in the previous exchange
     rc = recad_spmm(st->g_user, x + Ug * fD, off_y >= 0 ? local(off_y) : nullptr, C, off_z >= 0 ? local(off_z) : nullptr, alpha, D, s);
     if (rc) return rc;
     mark(1);
-    // 3. my slice: add the partial copies in rank order, store into every replica
+    // 3. (side stream, concurrently) my slice: add the partial copies in rank order, store into every replica
     ReduceArgs a{};
     a.n_src = world;
     for (int r = 0; r < world; ++r) a.src[r] = local(stage_off) + (int64_t)r * slice * fD;
@@ -220,19 +270,25 @@ struct Shard {
     const int64_t mine = (int64_t)rank * slice * fD;                    // floats into the item block
     a.C = C ? C + Ug * fD + mine : nullptr;
     a.alpha = alpha;
-    auto fill = [&](int64_t off, float** out, int& n) {
+    auto fill = [&](int64_t off, float** out, int& n, bool all, bool& mc_flag) {
+      mc_flag = false;
       if (off < 0) { n = 0; return; }
-      if (multicast) { out[0] = mc(off) + item_off(rank) + mine; n = 1; return; }
+      if (!all) { out[0] = local(off) + item_off(rank) + mine; n = 1; return; }
+      if (multicast) { out[0] = mc(off) + item_off(rank) + mine; n = 1; mc_flag = true; return; }
       for (int r = 0; r < world; ++r) out[r] = buf(r, off) + item_off(r) + mine;
       n = world;
     };
-    fill(off_y, a.out_y, a.n_y);
-    fill(off_z, a.out_z, a.n_z);
-    if ((rc = reduce_rows(a))) return rc;
-    mark(3);
-    return RECAD_OK;
+    bool mc_y, mc_z;
+    fill(off_y, a.out_y, a.n_y, true, mc_y);
+    fill(off_z, a.out_z, a.n_z, z_all, mc_z);
+    if ((rc = reduce_rows(a, mc_y, mc_z))) return rc;
+    return side_end();
   }
-  int finish_exchanges() { return barrier(); }
+  int finish_exchanges() {
+    int rc = join_side();
+    if (rc) return rc;
+    return barrier();
+  }
 
   // O = mean_k A^k E
   int propagate() {
@@ -240,7 +296,7 @@ struct Shard {
     for (int k = 0; k < L; ++k) {
       const bool last = k == L - 1;
       const int64_t off_y = last ? -1 : ((k & 1) ? st->off_X1 : st->off_X0);
-      int rc = spmm_exchange(x, off_y, k == 0 ? st->E : local(st->off_O), st->off_O, last ? 1.0f / (float)(L + 1) : 1.0f);
+      int rc = spmm_exchange(x, off_y, k == 0 ? st->E : local(st->off_O), st->off_O, last ? 1.0f / (float)(L + 1) : 1.0f, last);
       if (rc) return rc;
       if (!last) x = local(off_y);
     }
@@ -250,8 +306,9 @@ struct Shard {
   // the item block of g and of cnt: every owner pulls its slice of every rank's partial block, sums, stores into every replica
   int gradient_exchange() {
     if (world == 1) return RECAD_OK;
-    int rc = barrier();
+    int rc = barrier();                           // every rank's BPR is done: the partial blocks are final
     if (rc) return rc;
+    if ((rc = side_begin())) return rc;
     const int64_t fD = D, mine = (int64_t)rank * slice * fD;
     ReduceArgs a{};
     a.n_src = world;
@@ -259,7 +316,7 @@ struct Shard {
     a.n = rows_mine * fD / 4;
     if (multicast) { a.out_y[0] = mc(st->off_g) + item_off(rank) + mine; a.n_y = 1; }
     else { for (int r = 0; r < world; ++r) a.out_y[r] = buf(r, st->off_g) + item_off(r) + mine; a.n_y = world; }
-    if ((rc = reduce_rows(a))) return rc;
+    if ((rc = reduce_rows(a, multicast, false))) return rc;
     ReduceArgs c{};
     c.n_src = world;
     for (int r = 0; r < world; ++r) {
@@ -269,11 +326,11 @@ struct Shard {
     c.n_y = world;
     c.n = rows_mine;
     if (c.n > 0) {
-      shard_reduce_scalar_kernel<<<(unsigned)std::min<int64_t>((c.n + 255) / 256, (int64_t)sm_count() * 4), 256, 0, s>>>(c);
+      shard_reduce_scalar_kernel<<<(unsigned)std::min<int64_t>((c.n + 255) / 256, 32), 256, 0, sr->side>>>(c);
       RECAD_LAUNCH_CHECK();
     }
     mark(6);
-    return RECAD_OK;                 // visible after the barrier of the first Horner exchange
+    return side_end();               // joined, then certified, by the barrier of the first Horner exchange
   }
 };
 
@@ -329,7 +386,7 @@ int recad_lightgcn_shard_train_epoch(const recad_lightgcn_shard* st, const recad
     const float* t = g;
     for (int k = 0; k < L; ++k) {
       const int64_t off_z = (k & 1) ? st->off_X1 : st->off_X0;
-      if ((rc = sh.spmm_exchange(t, -1, g, off_z, 1.0f))) return rc;
+      if ((rc = sh.spmm_exchange(t, -1, g, off_z, 1.0f, true))) return rc;
       t = sh.local(off_z);
     }
     if ((rc = sh.finish_exchanges())) return rc;
