@@ -17,6 +17,7 @@ namespace recad {
 // RowSamples: rows [*, 3] in sampler order, visited through the epoch permutation (single GPU, reference layout).
 template <typename IdxT>
 struct RowSamples {
+  static constexpr bool kSparse = false;     // every sample of the batch is processed
   const IdxT* samples;
   const IdxT* perm;
   // returns 1 = valid sample, 0 = nothing to do, -1 = id out of range
@@ -31,6 +32,7 @@ struct RowSamples {
 // keeps the samples whose user it owns -- no routing pass, no per-rank copy of the epoch; the positive ITEM comes out
 // of the rank's own rows of the interaction matrix (its users' sorted distinct items, implicit.py:339-343).
 struct ShardSamples {
+  static constexpr bool kSparse = true;      // only the samples of the rank's own users are processed
   const uint32_t* users;
   const uint32_t* rel;
   const uint32_t* negs;
@@ -55,6 +57,7 @@ struct ShardSamples {
 
 // ShardRows: the global epoch as (user, pos, neg) rows; a rank keeps its own users' rows (tests, injected datasets).
 struct ShardRows {
+  static constexpr bool kSparse = true;
   const int64_t* rows;
   const int64_t* perm;
   int64_t user_lo, user_hi;
@@ -82,48 +85,7 @@ bpr_kernel(const float* __restrict__ O, const float* __restrict__ E, int64_t n_u
   float sp_sum = 0.f, sq_sum = 0.f;
   const float4* __restrict__ O4 = reinterpret_cast<const float4*>(O);
   const float4* __restrict__ E4 = reinterpret_cast<const float4*>(E);
-  // A warp looks at 32 samples at a time, one per lane (coalesced index loads; for a sharded source this is also the
-  // ownership test), then its GPW lane groups work through the samples that are to be processed, GPW at a time.
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int grp = lane / LPR;
-  (void)group; (void)n_groups;
-  // the ids of the NEXT 32 samples are fetched before the current ones are processed (their two dependent loads hide
-  // behind the row gathers)
-  auto fetch32 = [&](int64_t c0, int64_t& fu, int64_t& fp, int64_t& fn) -> int {
-    int st = 0;
-    fu = 0; fp = 0; fn = 0;
-    if (c0 + lane < B) {
-      st = src.fetch(b0 + c0 + lane, n_users, n_items, fu, fp, fn);
-      if (st < 0) {
-        atomicOr(bad, 1);
-        fu = 0; fp = 0; fn = 0;
-        st = 1;
-      }
-    }
-    return st;
-  };
-  int64_t nu, np_, nn_;
-  int nst = fetch32(warp_global * 32, nu, np_, nn_);
-  for (int64_t c0 = warp_global * 32; c0 < B; c0 += n_warps * 32) {
-    const int64_t mu = nu, mp = np_, mn = nn_;
-    const int st = nst;
-    nst = fetch32(c0 + n_warps * 32, nu, np_, nn_);
-    unsigned todo = __ballot_sync(kFull, st != 0);
-    while (todo) {
-      // lane group `grp` takes the grp-th lowest pending sample
-      unsigned m = todo;
-      int from = -1;
-#pragma unroll
-      for (int k = 0; k < GPW; ++k) {
-        const int low = m ? __ffs(m) - 1 : -1;
-        if (k == grp) from = low;
-        m &= m - 1;
-      }
-      todo = m;
-      const bool valid = from >= 0;
-      const int sl = valid ? from : 0;
-      const int64_t u = __shfl_sync(kFull, mu, sl), p = __shfl_sync(kFull, mp, sl), n = __shfl_sync(kFull, mn, sl);
+  auto process = [&](const bool valid, const int64_t u, const int64_t p, const int64_t n) {
     const int64_t ru = u * nvec, rp = (n_users + p) * nvec, rn = (n_users + n) * nvec;
     float4 ou[VPL], op[VPL], on[VPL];
     float dn = 0.f, dp = 0.f, sq = 0.f;
@@ -171,6 +133,61 @@ bpr_kernel(const float* __restrict__ O, const float* __restrict__ E, int64_t n_u
         atomicAdd(cnt + n_users + n, 1.0f);
       }
     }
+  };
+  if constexpr (!Src::kSparse) {
+    // all lanes of a warp iterate the same number of times (the shuffles inside are warp-wide)
+    const int64_t iters = (B + n_groups - 1) / n_groups;
+    for (int64_t it = 0; it < iters; ++it) {
+      const int64_t b = it * n_groups + group;
+      const bool valid = b < B;
+      int64_t u = 0, p = 0, n = 0;
+      if (valid && src.fetch(b0 + b, n_users, n_items, u, p, n) < 0) {
+        if (l == 0) atomicOr(bad, 1);
+        u = 0; p = 0; n = 0;
+      }
+      process(valid, u, p, n);
+    }
+  } else {
+    // Sharded source: a warp looks at 32 samples of the GLOBAL batch at a time, one per lane (coalesced index loads = the
+    // ownership test), then its GPW lane groups work through the samples the rank keeps, GPW at a time.  The ids of the
+    // NEXT 32 samples are fetched before the current ones are processed.
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int grp = lane / LPR;
+    auto fetch32 = [&](int64_t c0, int64_t& fu, int64_t& fp, int64_t& fn) -> int {
+      int st = 0;
+      fu = 0; fp = 0; fn = 0;
+      if (c0 + lane < B) {
+        st = src.fetch(b0 + c0 + lane, n_users, n_items, fu, fp, fn);
+        if (st < 0) {
+          atomicOr(bad, 1);
+          fu = 0; fp = 0; fn = 0;
+          st = 1;
+        }
+      }
+      return st;
+    };
+    int64_t nu, np_, nn_;
+    int nst = fetch32(warp_global * 32, nu, np_, nn_);
+    for (int64_t c0 = warp_global * 32; c0 < B; c0 += n_warps * 32) {
+      const int64_t mu = nu, mp = np_, mn = nn_;
+      const int st = nst;
+      nst = fetch32(c0 + n_warps * 32, nu, np_, nn_);
+      unsigned todo = __ballot_sync(kFull, st != 0);
+      while (todo) {
+        unsigned m = todo;                       // lane group `grp` takes the grp-th lowest pending sample
+        int from = -1;
+#pragma unroll
+        for (int k = 0; k < GPW; ++k) {
+          const int low = m ? __ffs(m) - 1 : -1;
+          if (k == grp) from = low;
+          m &= m - 1;
+        }
+        todo = m;
+        const bool valid = from >= 0;
+        const int sl = valid ? from : 0;
+        process(valid, __shfl_sync(kFull, mu, sl), __shfl_sync(kFull, mp, sl), __shfl_sync(kFull, mn, sl));
+      }
     }
   }
   // block reduction of the two loss partials -> one double atomic each per block

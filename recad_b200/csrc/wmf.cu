@@ -157,10 +157,12 @@ __global__ void __launch_bounds__(kWmfThreads, 1) wmf_fit_kernel(const __grid_co
   for (int64_t step = 0; step < n_steps; ++step) {
     const int64_t epoch = step / spe, s0 = (step % spe) * a.batch;
     const int nb = (int)min((int64_t)a.batch, a.n_rows - s0);
-    const StepScalars sc = step_scalars(a, a.step0 + step + 1);
+    __shared__ StepScalars sc_s;
+    if (tid == 0) sc_s = step_scalars(a, a.step0 + step + 1);
     float* snap = a.snap ? a.snap + step * 3 * n_params : nullptr;
     if (tid < nb) sm.sB[tid] = a.orders[epoch * a.n_rows + s0 + tid];
     __syncthreads();
+    const StepScalars sc = sc_s;
     for (int e = tid; e < nb * D; e += kWmfThreads) sm.sP[e] = __ldcg(a.P + (int64_t)sm.sB[e / D] * D + e % D);   // written by other CTAs: L2
     __syncthreads();
     float acc[D];
@@ -170,48 +172,83 @@ __global__ void __launch_bounds__(kWmfThreads, 1) wmf_fit_kernel(const __grid_co
     for (int64_t chunk = gwarp; chunk * 32 < a.n_items; chunk += ngwarps) {
       const int64_t i = chunk * 32 + lane;
       const bool on = i < a.n_items;
-      float q[D], gq[D];
+      float q[D], gq[D], dv[kWmfBatchMax];
+#pragma unroll
+      for (int b = 0; b < kWmfBatchMax; ++b)          // all loads of the batch's column issued before any is used
+        dv[b] = (on && b < nb) ? __ldg(a.data + (int64_t)sm.sB[b] * a.n_items + i) : 0.f;
 #pragma unroll
       for (int d = 0; d < D; d += 4) {
         const float4 t = on ? *reinterpret_cast<const float4*>(a.Q + i * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
         q[d] = t.x; q[d + 1] = t.y; q[d + 2] = t.z; q[d + 3] = t.w;
       }
+      float mq[D], vq[D];
+#pragma unroll
+      for (int d = 0; d < D; d += 4) {
+        const float4 tm = on ? *reinterpret_cast<const float4*>(a.mQ + i * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 tv = on ? *reinterpret_cast<const float4*>(a.vQ + i * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mq[d] = tm.x; mq[d + 1] = tm.y; mq[d + 2] = tm.z; mq[d + 3] = tm.w;
+        vq[d] = tv.x; vq[d + 1] = tv.y; vq[d + 2] = tv.z; vq[d + 3] = tv.w;
+      }
 #pragma unroll
       for (int d = 0; d < D; ++d) { gq[d] = 0.f; Y[lane * (D + 1) + d] = q[d]; }
-      for (int b = 0; b < nb; ++b) {
-        const float dv = on ? a.data[(int64_t)sm.sB[b] * a.n_items + i] : 0.f;
-        const float w = dv > 0.f ? a.wpos : a.wneg;
-        float logit = 0.f;
 #pragma unroll
-        for (int d = 0; d < D; ++d) logit = fmaf(sm.sP[b * D + d], q[d], logit);
-        const float r = on ? w * (dv - logit) : 0.f;
-        X[b * 32 + lane] = r;
+      for (int b = 0; b < kWmfBatchMax; ++b) {
+        if (b < nb) {
+          const float w = dv[b] > 0.f ? a.wpos : a.wneg;
+          float logit = 0.f;
 #pragma unroll
-        for (int d = 0; d < D; ++d) gq[d] = fmaf(-2.f * r, sm.sP[b * D + d], gq[d]);
+          for (int d = 0; d < D; ++d) logit = fmaf(sm.sP[b * D + d], q[d], logit);
+          const float r = on ? w * (dv[b] - logit) : 0.f;
+          X[b * 32 + lane] = r;
+#pragma unroll
+          for (int d = 0; d < D; ++d) gq[d] = fmaf(-2.f * r, sm.sP[b * D + d], gq[d]);
+        }
       }
       __syncwarp();
       warp_outer<D>(X, Y, nb, lane, -2.f, acc);
       __syncwarp();
       if (on) {
+        float pn[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          float p = q[d], m = a.mQ[i * D + d], v = a.vQ[i * D + d];
-          adam1(a, sc, gq[d] + a.wd * p, p, m, v);
-          a.Q[i * D + d] = p; a.mQ[i * D + d] = m; a.vQ[i * D + d] = v;
-          if (snap) { snap[nP + i * D + d] = q[d]; snap[n_params + nP + i * D + d] = m; snap[2 * n_params + nP + i * D + d] = v; }
+          pn[d] = q[d];
+          adam1(a, sc, gq[d] + a.wd * q[d], pn[d], mq[d], vq[d]);
+        }
+#pragma unroll
+        for (int d = 0; d < D; d += 4) {
+          *reinterpret_cast<float4*>(a.Q + i * D + d) = make_float4(pn[d], pn[d + 1], pn[d + 2], pn[d + 3]);
+          *reinterpret_cast<float4*>(a.mQ + i * D + d) = make_float4(mq[d], mq[d + 1], mq[d + 2], mq[d + 3]);
+          *reinterpret_cast<float4*>(a.vQ + i * D + d) = make_float4(vq[d], vq[d + 1], vq[d + 2], vq[d + 3]);
+          if (snap) {
+            *reinterpret_cast<float4*>(snap + nP + i * D + d) = make_float4(q[d], q[d + 1], q[d + 2], q[d + 3]);
+            *reinterpret_cast<float4*>(snap + n_params + nP + i * D + d) = make_float4(mq[d], mq[d + 1], mq[d + 2], mq[d + 3]);
+            *reinterpret_cast<float4*>(snap + 2 * n_params + nP + i * D + d) = make_float4(vq[d], vq[d + 1], vq[d + 2], vq[d + 3]);
+          }
         }
       }
     }
     cluster_reduce<D>(cluster, sm, acc, nb, tid, lane, warp);
-    // every row of P: dense Adam (rows outside the batch have gradient weight_decay * p only)
-    for (int64_t e = gtid; e < nP; e += gthreads) {
+    // every row of P: dense Adam (rows outside the batch have gradient weight_decay * p only); 128-bit accesses
+    for (int64_t e4 = gtid; e4 < nP / 4; e4 += gthreads) {
+      const int64_t e = e4 * 4;
       const int row = (int)(e / D), d = (int)(e % D);
       const int k = batch_pos<D>(sm.sB, nb, row);
-      const float p0 = a.P[e];
-      float p = p0, m = a.mP[e], v = a.vP[e];
-      adam1(a, sc, (k >= 0 ? sm.sGt[k * D + d] : 0.f) + a.wd * p0, p, m, v);
-      a.P[e] = p; a.mP[e] = m; a.vP[e] = v;
-      if (snap) { snap[e] = p0; snap[n_params + e] = m; snap[2 * n_params + e] = v; }
+      const float4 p0 = *reinterpret_cast<const float4*>(a.P + e);
+      float4 m = *reinterpret_cast<const float4*>(a.mP + e), v = *reinterpret_cast<const float4*>(a.vP + e);
+      const float4 g = k >= 0 ? *reinterpret_cast<const float4*>(sm.sGt + k * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 p = p0;
+      adam1(a, sc, g.x + a.wd * p0.x, p.x, m.x, v.x);
+      adam1(a, sc, g.y + a.wd * p0.y, p.y, m.y, v.y);
+      adam1(a, sc, g.z + a.wd * p0.z, p.z, m.z, v.z);
+      adam1(a, sc, g.w + a.wd * p0.w, p.w, m.w, v.w);
+      *reinterpret_cast<float4*>(a.P + e) = p;
+      *reinterpret_cast<float4*>(a.mP + e) = m;
+      *reinterpret_cast<float4*>(a.vP + e) = v;
+      if (snap) {
+        *reinterpret_cast<float4*>(snap + e) = p0;
+        *reinterpret_cast<float4*>(snap + n_params + e) = m;
+        *reinterpret_cast<float4*>(snap + 2 * n_params + e) = v;
+      }
     }
     __threadfence();
     cluster.sync();           // the new P rows are visible to every CTA; the shared buffers may be reused
@@ -376,23 +413,33 @@ static int launch_wmf(bool backward, const WmfArgs& a, cudaStream_t s) {
   auto kern = backward ? wmf_backward_kernel<D> : wmf_fit_kernel<D>;
   const size_t smem = WmfSmem<D>::bytes();
   RECAD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int C = 8;
-  if (const char* e = getenv("RECAD_WMF_CLUSTER")) C = std::max(1, std::min(8, atoi(e)));
+  int C = 16;                                          // B200: 16 CTAs per cluster with the non-portable opt-in
+  if (const char* e = getenv("RECAD_WMF_CLUSTER")) C = std::max(1, std::min(16, atoi(e)));
   while (C > 1 && (int64_t)C * kWmfThreads / 2 > a.n_items + a.n_rows) C >>= 1;     // tiny problems: fewer CTAs, cheaper barriers
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)C);
-  cfg.blockDim = dim3(kWmfThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  RECAD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, a));
-  return RECAD_OK;
+  if (C > 8) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      C = 8;
+    }
+  }
+  for (;; C >>= 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)C);
+    cfg.blockDim = dim3(kWmfThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+    if (e == cudaSuccess) return RECAD_OK;
+    if (C <= 8) RECAD_CUDA_CHECK(e);
+    cudaGetLastError();                                // a 16-CTA cluster could not be placed: fall back to the portable size
+  }
 }
 
 static int check_wmf(const recad_wmf* st, const float* data, const int32_t* orders, int32_t n_epochs, const char* who) {

@@ -349,9 +349,30 @@ class ImplicitData:
             dev = torch.device(self.config["device"])
             if dev.type != "cuda":
                 raise ops.RecadError("recad_b200 builds the graph on a CUDA device; config['device'] is " + str(dev))
+            # the reference's on-disk cache (implicit.py:246-256, 279-289): same file name, same scipy .npz of the
+            # normalised CSR, so either implementation reads what the other wrote
+            cache = os.path.join(self.config["cache_dir"], f"adj_mat_{self.dataset_name}_{self.n_users}_{self.n_items}.npz")
+            if self.config.get("if_cache") and os.path.exists(cache):
+                import scipy.sparse as sp
+                m = sp.load_npz(cache).tocsr()
+                m.sort_indices()
+                N = self.n_users + self.n_items
+                if m.shape != (N, N):
+                    raise ValueError(f"{cache}: cached adjacency is {m.shape}, the dataset needs {(N, N)}")
+                self.logger.info(f"successfully loaded adj_mat from {cache}, this could cause the inconsistency of the dataset")
+                self.Graph = ops.Graph.from_csr(torch.from_numpy(m.indptr.astype(np.int64)).to(dev),
+                                                torch.from_numpy(m.indices.astype(np.int32)).to(dev),
+                                                torch.from_numpy(m.data.astype(np.float32)).to(dev), n_cols=N, split=self.n_users)
+                return self.Graph
             u = torch.from_numpy(self.trainUser).to(dev)
             i = torch.from_numpy(self.trainItem).to(dev)
             self.Graph = ops.Graph.from_edges(u, i, self.n_users, self.n_items)
+            if self.config.get("if_cache"):
+                import scipy.sparse as sp
+                os.makedirs(self.config["cache_dir"], exist_ok=True)
+                ptr, col, val = self.Graph.to_numpy()
+                N = self.n_users + self.n_items
+                sp.save_npz(cache, sp.csr_matrix((val, col, ptr), shape=(N, N)))
         return self.Graph
 
     @property
@@ -498,7 +519,7 @@ class ImplicitData:
                 rows = [[] for _ in range(F)]   # reference quirk: fake users add rows but NO edges
             else:
                 rows = None                     # item universe grew: rebuild from scratch
-            if rows is not None and self.Graph is not None:
+            if rows is not None and self.Graph is not None and self.Graph.mult is not None:   # a graph read from the cache carries no multiplicities
                 fake_rowptr = torch.tensor(np.concatenate([[0], np.cumsum([len(r) for r in rows])]), dtype=torch.int64)
                 fake_items = torch.tensor([i for r in rows for i in r], dtype=torch.int32)
                 new.Graph = self.Graph.append_users(self.n_users, self.n_items, fake_rowptr, fake_items)

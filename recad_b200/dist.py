@@ -316,9 +316,11 @@ class ShardedLightGCN:
             self.propagate()
         Ug = self.Ug
         uid = torch.arange(Ug, device=self.dev) if users_local is None else users_local
-        rowptr = self.graph.rowptr[:Ug + 1].contiguous()
-        col = (self.graph.colidx[:int(rowptr[-1])] - Ug).contiguous()
-        return ops.fullrank_eval(self.O[:Ug].contiguous(), self.O[Ug:].contiguous(), uid, rowptr, col, targets, K)
+        if getattr(self, "_eval_csr", None) is None:        # the users' train rows = the mask of the evaluation; built once
+            rowptr = self.graph.rowptr[:Ug + 1].contiguous()
+            self._eval_csr = (rowptr, (self.graph.colidx[:int(rowptr[-1])] - Ug).contiguous())
+        rowptr, col = self._eval_csr
+        return ops.fullrank_eval(self.O[:Ug], self.O[Ug:], uid, rowptr, col, targets, K)
 
     def gather_tables(self):
         """(user table [U, D], item table [I, D]) assembled on every rank (tests / checkpoints)."""
@@ -512,11 +514,18 @@ def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, 
     t_sampler = time.time() - t0
     n_batches = (n + B - 1) // B
 
+    marks = []
+
     def step(trace=None):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
         loss = m.train_epoch_soa(epoch[0], epoch[1], epoch[2], epoch[3], trace=trace)
+        e1.record()
         topi, topv, rank_, score = m.full_rank([0], 20)
         hits = (rank_[:, 0] < 20).sum().double().view(1)
         dist.all_reduce(hits)
+        e2.record()
+        marks.append((e0, e1, e2))
         return loss, float(hits.item()) / U
 
     for _ in range(args.warmup):
@@ -531,9 +540,11 @@ def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, 
         b.record()
         torch.cuda.synchronize()
     dist.barrier()
-    ms = torch.tensor([a.elapsed_time(b) / args.steps], dtype=torch.float64, device=dev)
+    timed = marks[-args.steps:]
+    ms = torch.tensor([a.elapsed_time(b) / args.steps, float(np.mean([x.elapsed_time(y) for x, y, _ in timed])),
+                       float(np.mean([y.elapsed_time(z) for _, y, z in timed]))], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)            # device time, max over ranks
-    step_ms = float(ms.item())
+    step_ms, epoch_ms, eval_ms = (float(x) for x in ms.tolist())
     # per-phase device timeline of one epoch (CUDA events inside the C driver), max over ranks per phase
     trace = {}
     step(trace)
@@ -572,6 +583,7 @@ def bench_sharded(args, w, dev, rank, world, metric, synth_edges, ClockSampler, 
                                    f"from the SpMM epilogue over NVLink peer memory, the owner reduces and stores into every replica "
                                    f"({'multimem.st' if m.peer.multicast else 'peer stores'}); gradient block pulled by its owners; "
                                    f"{2 * L + 1} exchanges per batch, 1 NCCL all-reduce per epoch (loss)")},
+        "epoch_s": round(epoch_ms / 1e3, 6), "eval_s": round(eval_ms / 1e3, 6), "eval_users_per_s": round(U / (eval_ms / 1e3), 1),
         "epoch_loss": loss, "HR@20(target 0)": hr, "graph_build_s": round(t_graph, 4), "host_sampler_s": round(t_sampler, 3),
         "parity": parity, "phase_ms_per_epoch": trace,
         "roofline": {"bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None,

@@ -254,11 +254,12 @@ class Graph:
         return Graph(self.n_rows, self.n_cols, self.rowptr, self.colidx, vals, self.mult, degree, self.seg_len, split=self.split)
 
     @classmethod
-    def from_csr(cls, rowptr, colidx, vals, n_cols, seg_len=SEG_LEN):
-        """Wrap an existing (possibly rectangular) CSR, e.g. a user-row shard."""
+    def from_csr(cls, rowptr, colidx, vals, n_cols, seg_len=SEG_LEN, split=None):
+        """Wrap an existing (possibly rectangular) CSR, e.g. a user-row shard or a cached adjacency (split = n_users for
+        the symmetric bipartite matrix).  Without multiplicities / degrees such a graph cannot be extended in place."""
         _need_cuda(rowptr, colidx, vals)
         return cls(rowptr.numel() - 1, n_cols, rowptr.contiguous().long(), colidx.contiguous().int(),
-                   vals.contiguous().float(), None, None, seg_len)
+                   vals.contiguous().float(), None, None, seg_len, split=split)
 
     # -- plan ---------------------------------------------------------------- #
     def _plan(self):

@@ -203,3 +203,32 @@ def test_spmm_linearity_at_scale():
     key = rows * N + g.colidx.long()
     assert bool((key[1:] > key[:-1]).all())
     assert g.nnz % 2 == 0
+
+
+def test_adjacency_cache_file_is_the_reference_format(tmp_path):
+    """if_cache=True: the normalised adjacency is written as `adj_mat_<name>_<U>_<I>.npz` (scipy CSR, implicit.py:279-289)
+    and a second dataset is built from that file; its value bits equal the reference's matrix (golden), so either
+    implementation can read what the other cached."""
+    import scipy.sparse as sp
+    from recad_b200 import dataset
+    tr, va, te = util.dicts("dev")
+    kw = dict(train_dict=tr, valid_dict=va, test_dict=te, need_graph=True, device=torch.device(DEV), if_cache=True,
+              cache_dir=str(tmp_path))
+    a = dataset.from_config("implicit", "dev", **kw)
+    f = tmp_path / f"adj_mat_dev_{a.n_users}_{a.n_items}.npz"
+    assert f.exists()
+    m = sp.load_npz(str(f))
+    z = util.load("dev_graph.npz")
+    assert m.dtype == np.float32 and np.array_equal(m.indptr, z["crow"]) and np.array_equal(m.indices, z["col"])
+    assert m.data.tobytes() == z["val"].astype(np.float32).tobytes()       # the reference-actual graph (graph_edges="reference")
+    b = dataset.from_config("implicit", "dev", **kw)              # read back from the cache file
+    pa, ca, va_ = a.Graph.to_numpy()
+    pb, cb, vb = b.Graph.to_numpy()
+    assert np.array_equal(pa, pb) and np.array_equal(ca, cb) and va_.tobytes() == vb.tobytes()
+    X = torch.randn(a.n_users + a.n_items, 64, device=DEV)
+    from recad_b200 import ops
+    ya, _ = ops.spmm(a.Graph, X, torch.empty_like(X))
+    yb, _ = ops.spmm(b.Graph, X, torch.empty_like(X))
+    assert torch.equal(ya, yb)
+    c = b.inject_data("explicit", np.full((3, a.n_items), 5.0), filter_num=4)      # a cached graph is rebuilt, not extended
+    assert c.n_users == a.n_users + 3 and c.Graph.n_rows == a.Graph.n_rows + 3
