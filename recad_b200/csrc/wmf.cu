@@ -125,8 +125,12 @@ __device__ __forceinline__ void cluster_reduce(cg::cluster_group& cluster, WmfSm
   cluster.sync();
   const int C = (int)cluster.num_blocks();
   for (int o = tid; o < nb * D; o += kWmfThreads) {
+    float part[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) part[r] = r < C ? cluster.map_shared_rank(sm.sGc, r)[o] : 0.f;   // 16 remote loads in flight
     float t = 0.f;
-    for (int r = 0; r < C; ++r) t += cluster.map_shared_rank(sm.sGc, r)[o];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) t += part[r];                                                   // rank order: deterministic
     sm.sGt[o] = t;
   }
   __syncthreads();
@@ -229,6 +233,16 @@ __global__ void __launch_bounds__(kWmfThreads, 1) wmf_fit_kernel(const __grid_co
     }
     cluster_reduce<D>(cluster, sm, acc, nb, tid, lane, warp);
     // every row of P: dense Adam (rows outside the batch have gradient weight_decay * p only); 128-bit accesses
+    if (step + 1 < n_steps) {                                    // pull the next batch's data rows towards L2 while P is updated
+      const int64_t s1 = ((step + 1) % spe) * a.batch, ep1 = (step + 1) / spe;
+      const int nb1 = (int)min((int64_t)a.batch, a.n_rows - s1);
+      for (int64_t c = gtid; c < (int64_t)nb1 * ((a.n_items + 31) / 32); c += gthreads) {
+        const int64_t row = a.orders[ep1 * a.n_rows + s1 + c / ((a.n_items + 31) / 32)];
+        const float* ptr = a.data + row * a.n_items + (c % ((a.n_items + 31) / 32)) * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+      }
+    }
+#pragma unroll 4
     for (int64_t e4 = gtid; e4 < nP / 4; e4 += gthreads) {
       const int64_t e = e4 * 4;
       const int row = (int)(e / D), d = (int)(e % D);

@@ -211,6 +211,7 @@ def test_adjacency_cache_file_is_the_reference_format(tmp_path):
     implementation can read what the other cached."""
     import scipy.sparse as sp
     from recad_b200 import dataset
+    DEV = "cuda:0"
     tr, va, te = util.dicts("dev")
     kw = dict(train_dict=tr, valid_dict=va, test_dict=te, need_graph=True, device=torch.device(DEV), if_cache=True,
               cache_dir=str(tmp_path))
