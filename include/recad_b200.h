@@ -485,6 +485,10 @@ int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t
 int recad_host_advise_huge(void* ptr, int64_t bytes);   /* madvise(MADV_HUGEPAGE) on an untouched host buffer; best effort */
 int recad_pairwise_filter_build(const int64_t* allpos_rowptr, const int32_t* allpos_col, int64_t n_users,
                                 uint64_t* filter, uint32_t* ext, int32_t n_threads);
+/* The same for users [u_lo, n_users) only; the other users' blocks are left untouched (dataset injection: the parent's
+ * blocks are copied, only the appended fake users' are built). */
+int recad_pairwise_filter_build_range(const int64_t* allpos_rowptr, const int32_t* allpos_col, int64_t u_lo, int64_t n_users,
+                                      uint64_t* filter, uint32_t* ext, int32_t n_threads);
 int recad_mt19937_pairwise_fast(uint32_t* key, int32_t* pos, int64_t n_users, int64_t n_items,
                                 int64_t train_size, const int64_t* allpos_rowptr,
                                 const int32_t* allpos_col, const uint64_t* filter, const uint32_t* ext,

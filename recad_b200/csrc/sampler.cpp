@@ -357,7 +357,14 @@ static inline uint64_t ext_probe(uint32_t item, int j, uint64_t nbits) {
 
 int recad_pairwise_filter_build(const int64_t* allpos_rowptr, const int32_t* allpos_col, int64_t n_users, uint64_t* filter,
                                 uint32_t* ext, int32_t n_threads) {
-  if (!allpos_rowptr || !filter || !ext || n_users <= 0) {
+  return recad_pairwise_filter_build_range(allpos_rowptr, allpos_col, 0, n_users, filter, ext, n_threads);
+}
+
+// users [u_lo, u_hi) only: the blocks of the other users are left as they are (an injected dataset copies its parent's
+// blocks -- appended fake users do not move anybody's row -- and builds only the new ones)
+int recad_pairwise_filter_build_range(const int64_t* allpos_rowptr, const int32_t* allpos_col, int64_t u_lo, int64_t n_users,
+                                      uint64_t* filter, uint32_t* ext, int32_t n_threads) {
+  if (!allpos_rowptr || !filter || !ext || n_users <= 0 || u_lo < 0 || u_lo > n_users) {
     recad::set_error("pairwise_filter_build: bad argument");
     return RECAD_ERR_ARG;
   }
@@ -365,13 +372,13 @@ int recad_pairwise_filter_build(const int64_t* allpos_rowptr, const int32_t* all
     recad::set_error("pairwise_filter_build: more than 2^40 interactions");
     return RECAD_ERR_UNSUPPORTED;
   }
-  for (int64_t u = 0; u < n_users; ++u)
+  for (int64_t u = u_lo; u < n_users; ++u)
     if (allpos_rowptr[u + 1] - allpos_rowptr[u] >= ((int64_t)1 << 24)) {
       recad::set_error("pairwise_filter_build: user %lld has 2^24 or more interactions", (long long)u);
       return RECAD_ERR_UNSUPPORTED;
     }
-  parallel_for(n_users, n_threads, [&](int64_t lo, int64_t hi) {
-    for (int64_t u = lo; u < hi; ++u) {
+  parallel_for(n_users - u_lo, n_threads, [&](int64_t lo, int64_t hi) {
+    for (int64_t u = u_lo + lo; u < u_lo + hi; ++u) {
       uint64_t* f = filter + u * kFilterWords;
       for (int q = 0; q < kFilterWords; ++q) f[q] = 0;
       const int64_t a0 = allpos_rowptr[u], a1 = allpos_rowptr[u + 1];

@@ -563,7 +563,7 @@ class ArrayImplicitData:
     test:  optional (users, items) host arrays of held-out pairs (ground truth for Recall/NDCG)."""
 
     def __init__(self, name, n_users, n_items, train, device, test=None, sample="pairwise", batch_size=1024,
-                 negative_ratio=4, need_graph=True, graph=None, prefetch=None):
+                 negative_ratio=4, need_graph=True, graph=None, prefetch=None, allpos_host=None):
         self._dataset_name = name
         self.n_users, self.n_items = int(n_users), int(n_items)
         dev = torch.device(device)
@@ -581,7 +581,8 @@ class ArrayImplicitData:
         n_train = int(rowptr_u[-1])
         col_u = (graph.colidx[:n_train] - U).contiguous()                 # int32 item ids, ascending per user
         self._train_csr_dev = (rowptr_u, col_u)
-        self._allpos = (ops.to_host(rowptr_u), ops.to_host(col_u))        # host copy (huge pages) for the C++ sampler
+        # host copy (huge pages) of the positives for the C++ sampler; an injected dataset gets it from its parent
+        self._allpos = allpos_host if allpos_host is not None else (ops.to_host(rowptr_u), ops.to_host(col_u))
         self._train_csr = self._allpos
         self.traindataSize = n_train
         # pointwise sampler: dict order = users ascending, each list ascending
@@ -645,9 +646,19 @@ class ArrayImplicitData:
         graph = self.Graph.append_users(self.n_users, self.n_items, torch.from_numpy(rowptr), torch.from_numpy(items))
         c = self.config
         batch = c["pairwise_batch_size"] if c["sample"] == "pairwise" else c["pointwise_batch_size"]
+        # the positives of the attacked dataset = the parent's with F rows appended: a host concatenation instead of a
+        # device -> host copy, and the sampler's per-user filter blocks of the genuine users are reused (ops.pairwise_filter)
+        old_ptr, old_col = self._allpos
+        new_ptr = ops.host_empty(len(old_ptr) + F, np.int64)
+        new_ptr[:len(old_ptr)] = old_ptr
+        new_ptr[len(old_ptr):] = old_ptr[-1] + rowptr[1:]
+        new_col = ops.host_empty(len(old_col) + len(items), np.int32)
+        new_col[:len(old_col)] = old_col
+        new_col[len(old_col):] = items
+        ops.filter_parent_hint(new_ptr, new_col, old_ptr, old_col, self.n_users)
         return ArrayImplicitData(self._dataset_name, self.n_users + F, self.n_items, None, c["device"], test=self._test,
                                  sample=c["sample"], batch_size=batch, negative_ratio=c["negative_ratio"],
-                                 need_graph=c["need_graph"], graph=graph, prefetch=c.get("prefetch"))
+                                 need_graph=c["need_graph"], graph=graph, prefetch=c.get("prefetch"), allpos_host=(new_ptr, new_col))
 
     def info_describe(self):
         infos = {"n_users": self.n_users, "n_items": self.n_items, "train_interactions": self.traindataSize,

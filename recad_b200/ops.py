@@ -609,17 +609,44 @@ _filters = _DerivedCache(3)
 _sorted_lists = _DerivedCache(4)
 
 
+_filter_parents = {}     # (new col address, new rowptr address) -> (parent rowptr, parent col, parent n_users): injected datasets
+
+
+def filter_parent_hint(new_rowptr, new_col, old_rowptr, old_col, n_users_old):
+    """The positives (new_rowptr, new_col) are (old_rowptr, old_col) with rows APPENDED (dataset injection): the sampler's
+    filter blocks of the old users can be copied instead of rebuilt."""
+    if len(_filter_parents) > 8:
+        _filter_parents.clear()
+    _filter_parents[(new_col.ctypes.data, new_rowptr.ctypes.data)] = (old_rowptr, old_col, int(n_users_old))
+
+
+def _filter_key(rowptr, col, n_users):
+    return (col.ctypes.data, rowptr.ctypes.data, len(col), int(n_users))
+
+
 def pairwise_filter(allpos_rowptr, allpos_col, n_users):
-    """Per-user 128-byte blocks (row bounds + two-level membership filter, first line decisive) for mt_pairwise_raw(fast); built once per positives array."""
+    """Per-user 128-byte blocks (row bounds + two-level membership filter, first line decisive) for mt_pairwise_raw(fast);
+    built once per positives array -- or, for a dataset derived by injection from one whose blocks are still cached,
+    copied from the parent and completed for the appended users only."""
     def build():
         filt = host_empty(int(n_users) * 16, np.uint64)
         ext = host_empty(max(len(allpos_col), 1), np.uint32)
-        check(_lib.lib().recad_pairwise_filter_build(allpos_rowptr.ctypes.data, allpos_col.ctypes.data, n_users,
-                                                     filt.ctypes.data, ext.ctypes.data, os.cpu_count() or 1),
-              "recad_pairwise_filter_build")
+        u_lo = 0
+        parent = _filter_parents.pop((allpos_col.ctypes.data, allpos_rowptr.ctypes.data), None)
+        if parent is not None:
+            prp, pcol, pn = parent
+            got = _filters.entries.get(_filter_key(prp, pcol, pn))        # build() runs under the cache's lock
+            if got is not None and pn <= n_users:
+                _filters.entries.move_to_end(_filter_key(prp, pcol, pn))    # a parent in use is not the eviction candidate
+                (pf, pe), _ = got
+                filt[:pn * 16] = pf[:pn * 16]
+                ext[:len(pe)] = pe
+                u_lo = pn
+        check(_lib.lib().recad_pairwise_filter_build_range(allpos_rowptr.ctypes.data, allpos_col.ctypes.data, u_lo, n_users,
+                                                           filt.ctypes.data, ext.ctypes.data, os.cpu_count() or 1),
+              "recad_pairwise_filter_build_range")
         return filt, ext
-    return _filters.get((allpos_col.ctypes.data, allpos_rowptr.ctypes.data, len(allpos_col), int(n_users)),
-                        (allpos_rowptr, allpos_col), build)
+    return _filters.get(_filter_key(allpos_rowptr, allpos_col, n_users), (allpos_rowptr, allpos_col), build)
 
 
 def mt_pointwise_raw(key, pos, user_ids, pos_rowptr, pos_items, n_items, ratio, out=None):

@@ -9,7 +9,9 @@ registries -- no reference file is edited:
 Registries touched: recad.model.factories['victim'] (recad/model/__init__.py:3-18),
 recad.default.MODEL['victim'] (recad/default.py:104-133), recad.dataset.factories
 (recad/dataset/__init__.py:13), and with override=True `Normal.normal_evaluate` /
-`Defense.normal_evaluate` (recad/workflow/normal.py:111-160, defense.py:125-174).
+`Defense.normal_evaluate` (recad/workflow/normal.py:111-160, defense.py:125-174) and the name
+`recad.model.attacker.aia.WMFTrainer`, which AIA / Leg-UP look up every attack step to retrain their surrogate
+(aia.py:125-207; aushplus.py:11 inherits the method): the CUDA trainer needs no `higher`.
 """
 from . import evaluate
 from .config import MODEL
@@ -33,4 +35,7 @@ def install(override=False):
             return evaluate.normal_evaluate(model, model_fake, dataset, target_id_list, topks)
         ref_workflow.Normal.normal_evaluate = _normal_evaluate
         ref_workflow.Defense.normal_evaluate = _normal_evaluate
+        from recad.model.attacker import aia as ref_aia
+        from .surrogate import WMFTrainer
+        ref_aia.WMFTrainer = WMFTrainer
     return True

@@ -27,10 +27,13 @@ def ref_recad(tmp_path, monkeypatch):
     try:
         import recad
         import recad_b200.register as reg
+        from recad.model.attacker import aia as ref_aia
         saved = (dict(recad.model.factories["victim"]), dict(recad.dataset.factories), recad.workflow.Normal.normal_evaluate,
                  recad.workflow.Defense.normal_evaluate)
+        saved_wmf = ref_aia.WMFTrainer
         reg.install(override=True)
         yield recad
+        ref_aia.WMFTrainer = saved_wmf
         recad.model.factories["victim"].clear(); recad.model.factories["victim"].update(saved[0])
         recad.dataset.factories.clear(); recad.dataset.factories.update(saved[1])
         recad.workflow.Normal.normal_evaluate, recad.workflow.Defense.normal_evaluate = saved[2], saved[3]
@@ -107,3 +110,35 @@ def test_reference_execute_runs_on_the_cuda_path(ref_recad, victim, kw, sample):
             assert np.isclose(seen["table"][k], v, **tol), (k, seen["table"][k], v)
         else:
             assert np.isclose(seen["table"][k], v, rtol=1e-4, atol=1.0 / n_eval), (k, seen["table"][k], v)
+
+
+def test_reference_attacker_retrains_its_surrogate_on_the_cuda_path(ref_recad):
+    """AIA.get_sur_predictions (recad/model/attacker/aia.py:125-207, unmodified; Leg-UP inherits it) builds whatever
+    `WMFTrainer` its module names.  After install(override=True) that is the CUDA trainer: the reference method returns
+    predictions whose gradient reaches the generator's fake profiles without `higher` being installed."""
+    import types
+    from recad.model.attacker import aia as ref_aia
+    from recad_b200 import surrogate
+    assert ref_aia.WMFTrainer is surrogate.WMFTrainer
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    U, I, F = 90, 60, 10
+    train = ((rng.random((U, I)) < 0.2) * rng.integers(1, 6, (U, I))).astype(np.float32)
+    me = types.SimpleNamespace(train_array=train, device=dev, n_users=U, n_items=I, attack_num=F, surrogate="WMF",
+                               config={"hidden_dim_s": 16, "lr_s": 1e-2, "weight_decay_s": 1e-5, "batch_size_s": 16,
+                                       "weight_pos_s": 1.0, "weight_neg_s": 0.0, "epoch_s": 4, "unroll_steps_s": 1})
+    fake = torch.tensor(rng.random((F, I)).astype(np.float32) * 5, device=dev, requires_grad=True)
+    torch.manual_seed(0); np.random.seed(0)
+    pred = ref_aia.AIA.get_sur_predictions(me, fake)
+    assert pred.shape == (U + F, I) and pred.is_cuda
+    pred[:U, 3].sum().backward()                       # an attack-style loss on a target item's scores of the genuine users
+    assert fake.grad is not None and float(fake.grad.abs().max()) > 0
+    # same call on the oracle (CPU): same predictions, same gradient to the fake profiles
+    from oracle import wmf as owmf
+    torch.manual_seed(0); np.random.seed(0)
+    fake_c = fake.detach().cpu().clone().requires_grad_(True)
+    data_c = torch.cat([torch.from_numpy(train), fake_c], 0)
+    pred_c, _, _ = owmf.fit_adv(data_c, 4, 1)
+    pred_c[:U, 3].sum().backward()
+    assert np.abs(pred.detach().cpu().numpy() - pred_c.detach().numpy()).max() <= 1e-4 * float(pred_c.abs().max()) + 1e-6
+    assert np.abs(fake.grad.cpu().numpy() - fake_c.grad.numpy()).max() <= 2e-3 * float(fake_c.grad.abs().max())

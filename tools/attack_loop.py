@@ -54,6 +54,7 @@ def main():
 
     if world == 1:
         clean = dataset.ArrayImplicitData(args.workload, U, I, (eu, ei), dev, batch_size=B, prefetch=False)
+        ops.pairwise_filter(*clean._allpos, U)                           # the clean dataset's sampler filter, built once
         del eu, ei
         for it in range(args.iters):
             fake = fake_profiles(rng, args.fake, I, target[0])
@@ -85,9 +86,11 @@ def main():
             keys = torch.unique(eu * I + ei)
             ptr = torch.zeros(U + 1, dtype=torch.int64, device=dev)
             ptr[1:] = torch.cumsum(torch.bincount(keys // I, minlength=U), 0)
-            ap_ptr, ap_col = ptr.cpu().numpy(), (keys % I).int().cpu().numpy()
+            ap_ptr, ap_col = ops.to_host(ptr), ops.to_host((keys % I).int())
+            ops.pairwise_filter(ap_ptr, ap_col, U)                       # the clean dataset's filter blocks, built once
             del keys, ptr
         del eu, ei
+        epoch_bufs = None
         for it in range(args.iters):
             fake = fake_profiles(rng, args.fake, I, target[0])        # same generator state on every rank
             frp, fit = dataset.ArrayImplicitData.fake_rows(fake, 4)
@@ -96,19 +99,31 @@ def main():
             m = base.inject(frp, fit)
             sync(); dist.barrier(); t1 = time.time()
             n2 = n + len(fit)
-            samples = torch.empty((n2, 3), dtype=torch.int64, device=dev)
-            perm = torch.empty(n2, dtype=torch.int64, device=dev)
+            if epoch_bufs is None or epoch_bufs.shape[1] < n2:
+                epoch_bufs = torch.empty((4, n2 + 64 * args.fake), dtype=torch.int32, device=dev)
+            ep = epoch_bufs[:, :n2]
             if rank == 0:
-                ptr2 = np.concatenate([ap_ptr, ap_ptr[-1] + frp[1:]])
-                col2 = np.concatenate([ap_col, fit])
-                S = ops.mt_pairwise(U + F, I, n2, ptr2, col2)
-                assert len(S) == n2
-                samples.copy_(torch.from_numpy(S))
-                perm.copy_(torch.from_numpy(ops.mt_permutation(n2)))
-            dist.broadcast(samples, 0)
-            dist.broadcast(perm, 0)
+                # positives of the attacked dataset = the clean ones + the appended fake rows; the sampler's per-user filter
+                # blocks of the genuine users are copied from the clean dataset's (ops.filter_parent_hint)
+                ptr2 = ops.host_empty(len(ap_ptr) + F, np.int64)
+                ptr2[:len(ap_ptr)] = ap_ptr
+                ptr2[len(ap_ptr):] = ap_ptr[-1] + frp[1:]
+                col2 = ops.host_empty(len(ap_col) + len(fit), np.int32)
+                col2[:len(ap_col)] = ap_col
+                col2[len(ap_col):] = fit
+                ops.filter_parent_hint(ptr2, col2, ap_ptr, ap_col, U)
+                st, key, pos = ops._np_state()
+                host = [ops.host_empty(n2, np.uint32) for _ in range(4)]
+                perm = ops.host_empty(n2, np.int32)
+                cnt = ops.mt_pairwise_soa_raw(key, pos, U + F, I, n2, ptr2, col2, host[0], host[1], host[2], host[3])
+                assert cnt == n2
+                ops._np_state_commit(st, key, pos)
+                ops.permutation_apply32(host[3][:cnt], perm)
+                for k, a in enumerate((host[0], host[1], host[2], perm)):
+                    ep[k].copy_(torch.from_numpy(a.view(np.int32)))
+            dist.broadcast(ep, 0)
             sync(); dist.barrier(); t2 = time.time()
-            loss = m.train_epoch(samples, perm)
+            loss = m.train_epoch_soa(ep[0], ep[1], ep[2], ep[3])
             sync(); dist.barrier(); t3 = time.time()
             genuine = torch.arange(min(m.Ug, max(0, U - m.lo)), device=dev)
             _, _, rank_, _ = m.full_rank(target, 20, users_local=genuine)
@@ -119,7 +134,7 @@ def main():
             for k, v in zip(phases, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
                 phases[k].append(v)
             hrs.append(hr)
-            del m, samples, perm
+            del m
     if rank == 0:
         out = {"tool": "attack_loop", "workload": args.workload, "n_gpus": world, "iters": args.iters, "fake_users": args.fake,
                "loss_last": loss, "HR@20_target_last": hrs[-1]}
