@@ -136,13 +136,28 @@ class _EpochPipe:
         return (cuda and d.config["sample"] == "pairwise" and d.traindataSize >= ops.FAST_SAMPLER_MIN
                 and d.traindataSize < (1 << 31) and d.n_users < (1 << 31) and d.n_items < (1 << 31))
 
+    _POOL = []          # pinned 32-bit buffer sets of pipes that were garbage collected (page-locking 0.8 GB costs ~0.3 s)
+
+    def __del__(self):
+        try:
+            for b in self.bufs:
+                if b is not None and b[0] and len(_EpochPipe._POOL) < 4 and not self.queue:
+                    _EpochPipe._POOL.append(b)
+        except Exception:   # noqa: BLE001 -- interpreter teardown
+            pass
+
     def _buffers(self, slot, cuda):
         n = self.data.traindataSize * (1 if self.data.config["sample"] == "pairwise" else 1 + self.data.config["negative_ratio"])
         soa = self._soa(cuda)
         if self.bufs[slot] is None or self.bufs[slot][-1].shape[0] < n or self.bufs[slot][0] != soa:
             if soa:
-                host = [torch.empty(max(n, 1), dtype=torch.int32).pin_memory() for _ in range(4)]   # users, rel, negs, perm
-                self.bufs[slot] = (True, *host, ops.host_empty(max(n, 1), np.uint32))
+                for k, b in enumerate(_EpochPipe._POOL):        # a dataset derived by injection is a few hundred samples larger
+                    if b[-1].shape[0] >= n:
+                        self.bufs[slot] = _EpochPipe._POOL.pop(k)
+                        return self.bufs[slot]
+                cap = max(n + (n >> 8), 1)                      # head-room so that the next injected dataset fits the same buffers
+                host = [torch.empty(cap, dtype=torch.int32).pin_memory() for _ in range(4)]   # users, rel, negs, perm
+                self.bufs[slot] = (True, *host, ops.host_empty(cap, np.uint32))
             else:
                 s, p = torch.empty((max(n, 1), 3), dtype=torch.int64), torch.empty(max(n, 1), dtype=torch.int64)
                 if cuda:

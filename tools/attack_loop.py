@@ -99,9 +99,9 @@ def main():
             m = base.inject(frp, fit)
             sync(); dist.barrier(); t1 = time.time()
             n2 = n + len(fit)
-            if epoch_bufs is None or epoch_bufs.shape[1] < n2:
-                epoch_bufs = torch.empty((4, n2 + 64 * args.fake), dtype=torch.int32, device=dev)
-            ep = epoch_bufs[:, :n2]
+            if epoch_bufs is None or epoch_bufs.numel() < 4 * n2:
+                epoch_bufs = torch.empty(4 * (n2 + 64 * args.fake), dtype=torch.int32, device=dev)
+            ep = epoch_bufs[:4 * n2].view(4, n2)
             if rank == 0:
                 # positives of the attacked dataset = the clean ones + the appended fake rows; the sampler's per-user filter
                 # blocks of the genuine users are copied from the clean dataset's (ops.filter_parent_hint)

@@ -13,7 +13,9 @@ run() {  # name, tool, command...
   echo "$name $tool rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $OUT/sanitizer_${name}_${tool}.log | tail -1)"
 }
 if [ "${1:-}" = "dist" ]; then
-  run dist memcheck --target-processes all python -m pytest tests/test_gpu_dist.py -x -q -k sharded
+  # --report-api-errors no: torch's own fabric-handle probe (c10::cuda::isFabricSupported -> cuMemCreate) is refused on this
+  # box and would be counted as two errors that have nothing to do with a kernel
+  run dist memcheck --target-processes all --report-api-errors no python -m pytest tests/test_gpu_dist.py -x -q -k sharded
   exit 0
 fi
 run smoke memcheck python -c "import __graft_entry__ as g; g.smoke()"

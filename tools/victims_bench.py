@@ -1,6 +1,8 @@
-"""Epoch / evaluation timings of the three victims on the ml1m-shaped graph (BASELINE.json configs[0..2] shapes):
-one JSON line per model, with the CPU oracle port (torch CPU, all host threads) timed on a bounded sample beside it.
-    python tools/victims_bench.py > profiles/victims_ml1m_r01.jsonl"""
+"""Epoch / evaluation timings of the three victims on the ml1m-shaped graph (BASELINE.json configs[0..2] shapes), or of
+NCF on the yelp-shaped one (configs[2]: 54 632 x 34 474, 1.5 M interactions): one JSON line per model, with the CPU
+oracle port (torch CPU, all host threads) timed on a bounded sample beside it.
+    python tools/victims_bench.py > profiles/victims_ml1m_r02.jsonl
+    python tools/victims_bench.py yelp > profiles/ncf_yelp_r02.jsonl"""
 import json
 import os
 import sys
@@ -15,7 +17,10 @@ from oracle import pointwise_models as opm  # noqa: E402  (CPU baseline leg only
 from recad_b200 import dataset, evaluate, model, synthetic  # noqa: E402
 
 DEV = torch.device("cuda:0")
-tr, va, te = synthetic.make_splits(synthetic.ML1M, seed=0)
+YELP = len(sys.argv) > 1 and sys.argv[1] == "yelp"
+SHAPE = synthetic.YELP if YELP else synthetic.ML1M
+tr, va, te = synthetic.make_splits(SHAPE, seed=0)
+torch.set_num_threads(os.cpu_count() or 1)
 
 
 def timed(fn, n=3):
@@ -36,9 +41,11 @@ def cpu_epoch_estimate(oracle, samples, batch, n_batches_total, n_time=20):
     return (time.time() - t0) / n_time * n_batches_total
 
 
-for name, kw in (("mf", {"embedding_size": 64}), ("ncf", {}), ("ncf", {"tower_precision": "fp32"}), ("lightgcn", {"latent_dim_rec": 64})):
+MODELS = ((("ncf", {}), ("ncf", {"tower_precision": "fp32"})) if YELP else
+          (("mf", {"embedding_size": 64}), ("ncf", {}), ("ncf", {"tower_precision": "fp32"}), ("lightgcn", {"latent_dim_rec": 64})))
+for name, kw in MODELS:
     pairwise = name == "lightgcn"
-    data = dataset.from_config("implicit", "ml1m", train_dict=tr, valid_dict=va, test_dict=te, need_graph=pairwise,
+    data = dataset.from_config("implicit", "yelp" if YELP else "ml1m", train_dict=tr, valid_dict=va, test_dict=te, need_graph=pairwise,
                                graph_edges="train", sample="pairwise" if pairwise else "pointwise", device=DEV)
     torch.manual_seed(2023)
     np.random.seed(2023)
@@ -47,7 +54,8 @@ for name, kw in (("mf", {"embedding_size": 64}), ("ncf", {}), ("ncf", {"tower_pr
     ev_s, rows = timed(lambda: evaluate.model_rows(m, data, [0], [10, 20, 50, 100])[0])
     n = data.traindataSize * (1 if pairwise else 5)
     B = 1024
-    rec = {"victim": name, **{k: v for k, v in kw.items()}, "workload": "ml1m-shaped 5950 x 3702, 468 649 train interactions",
+    rec = {"victim": name, **{k: v for k, v in kw.items()},
+           "workload": f"{'yelp' if YELP else 'ml1m'}-shaped {SHAPE['n_users']} x {SHAPE['n_items']}, {SHAPE['train']} train interactions",
            "samples_per_epoch": n, "batch": B, "epoch_s (train_step, incl. exact host sampler + H2D)": round(ep_s, 4),
            "loss": loss[0], "fullrank_eval_s (all eligible users, HR@k rows)": round(ev_s, 5), "eval_users": int(len(rows))}
     if not pairwise:
