@@ -232,6 +232,28 @@ def run_b200(args, w):
     ncu = ncu_spmm_traffic(args.workload)
     traffic = (ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ncu else None
 
+    # second kernel of the step: the fused full-rank evaluation (tcgen05, 3xTF32 = 3 tensor-core passes per score tile)
+    fr_ms, roofline_eval = None, None
+    if ops.EVAL_PRECISION == "tf32x3" and D <= 64:
+        Ou, Oi = m.O[:U], m.O[U:]
+        ops.fullrank_eval(Ou, Oi, users_all, rp, rc, target, 20)
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(3):
+            ops.fullrank_eval(Ou, Oi, users_all, rp, rc, target, 20)
+        b.record()
+        torch.cuda.synchronize()
+        fr_ms = a.elapsed_time(b) / 3
+        issued = 3 * 2.0 * U * I * D                                   # tf32 MMA flops issued (hi*hi + hi*lo + lo*hi)
+        tf32_peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) / 2      # tf32 runs at half the bf16 rate; measured bf16 peak / 2
+        roofline_eval = {"bound": "tensor", "kernel": "fullrank_tc_kernel", "ms_per_launch": round(fr_ms, 3),
+                         "achieved": round(issued / (fr_ms * 1e-3) / 1e12, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
+                         "frac": round(issued / (fr_ms * 1e-3) / 1e12 / tf32_peak, 4),
+                         "useful_tflops": round(2.0 * U * I * D / (fr_ms * 1e-3) / 1e12, 1),
+                         "model": "issued tf32 flops = 3 x 2 U I D (3xTF32 split keeps fp32-accurate scores); peak = measured "
+                                  "sustained bf16 cuBLAS rate / 2 (tf32 : bf16 = 1 : 2 on the tcgen05 pipe); the kernel also masks "
+                                  "train items, ranks the target and keeps a top-20 per user in its epilogue"}
+
     # end to end through the public API: host sampler + pinned H2D + epoch + loss D2H, then evaluation + metric D2H
     # (the next epoch's samples are drawn on a background thread while the GPU works: dataset._EpochPipe)
     data.config["prefetch"] = True
@@ -283,9 +305,11 @@ def run_b200(args, w):
                             "sampler + shuffle on host (the next two epochs are drawn on background threads), pinned H2D of "
                             "samples + permutation, epoch, loss D2H; then full-rank eval of all users, Recall/NDCG/HR D2H",
                 "per_step_s": [round(t, 3) for t in e2e], "metrics_last_step": metrics},
-        "gpu_launches": args.steps * (n_batches * (2 * L * (2 if graph.n_mrow else 1) + 2) + 3),
+        "gpu_launches": args.steps * (n_batches * (2 * L + 4) + 3 + 4),
         "clocks": clocks.summary(),
     }
+    if roofline_eval:
+        out["roofline_eval"] = roofline_eval
     if not args.no_gpu_baseline:
         try:
             out["gpu_library_baseline"] = torch_gpu_reference(graph, U, I, D, L, B, n_batches, dev)
