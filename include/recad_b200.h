@@ -379,7 +379,9 @@ typedef struct recad_ncf {
   float lr, beta1, beta2, eps;
   int32_t tower_fp32; /* 0: tower GEMMs on tcgen05 (3xTF32, fp32-accurate); 1: exact fp32 CUDA-core GEMMs (bit-stable
                          ReLU masks; what the strict parity tests use) */
-  int32_t _pad;
+  int32_t variant;    /* ncf.py:49-53, 112-131: 0 = NeuMF (predict on cat(GMF, MLP), 2f inputs; 'NeuMF-end' / 'NeuMF-pre'),
+                         1 = 'GMF' (predict on the GMF product, f inputs), 2 = 'MLP' (predict on the tower output, f inputs).
+                         The layout is the same for all three; the unused predict weights stay zero. */
   float* params;      /* [dev] float[n_params] */
   float* m;           /* [dev] Adam first moment  (training only) */
   float* v;           /* [dev] Adam second moment (training only) */

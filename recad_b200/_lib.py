@@ -76,7 +76,7 @@ class NCF(C.Structure):
     """struct recad_ncf"""
     _fields_ = [
         ("n_users", i64), ("n_items", i64), ("factor", i32), ("n_layers", i32),
-        ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("tower_fp32", i32), ("_pad", i32),
+        ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("tower_fp32", i32), ("variant", i32),
         ("params", vp), ("m", vp), ("v", vp), ("grads", vp), ("n_params", i64),
         ("work", vp), ("work_floats", i64), ("max_batch", i64), ("loss_acc", vp),
     ]

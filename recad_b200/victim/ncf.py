@@ -1,4 +1,4 @@
-"""NCF / NeuMF-end victim (drop-in for recad/model/victim/ncf.py) on the CUDA kernels.
+"""NCF victim (drop-in for recad/model/victim/ncf.py: 'NeuMF-end', 'NeuMF-pre', 'GMF', 'MLP') on the CUDA kernels.
 
 Every parameter lives in one flat fp32 buffer laid out by `recad_ncf_layout`; the module
 attributes of the reference (`embed_user_GMF`, `MLP_layers`, `predict_layer`, ...) are rebuilt as
@@ -36,8 +36,10 @@ class NCF(BaseVictim):
         self.dataset = config["dataset"]
         if dropout:
             raise NotImplementedError("NCF dropout is 0 by default and not implemented")
-        if model != "NeuMF-end":
-            raise NotImplementedError("only the default 'NeuMF-end' variant (default.py:127) is implemented")
+        if model not in ("NeuMF-end", "NeuMF-pre", "GMF", "MLP"):
+            raise ValueError(f"unknown NCF model {model!r}")
+        if model == "NeuMF-pre" and (GMF_model is None or MLP_model is None):
+            raise ValueError("'NeuMF-pre' needs GMF_model and MLP_model (ncf.py:79-104)")
         if str(config["optim"]).lower() != "adam":
             raise ValueError("optimizer not supported")
         self.tower_precision = config.get("tower_precision", "tf32x3")
@@ -46,24 +48,41 @@ class NCF(BaseVictim):
         info = self.dataset.info_describe()
         U, I = info["n_users"], info["n_items"]
         self.num_users, self.num_items, self.f, self.L = U, I, factor_num, num_layers
+        self.variant = {"GMF": 1, "MLP": 2}.get(model, 0)
         w = factor_num * (2 ** (num_layers - 1))
-        # constructor + _init_weight_ sequence of ncf.py:32-77 on the CPU generator
+        # constructor + _init_weight_ sequence of ncf.py:32-104 on the CPU generator (the constructors draw their default
+        # initialisation for every variant; 'NeuMF-pre' then copies the trained GMF / MLP parts instead of re-drawing)
         ug, ig = nn.Embedding(U, factor_num), nn.Embedding(I, factor_num)
         um, im = nn.Embedding(U, w), nn.Embedding(I, w)
         lins = []
         for i in range(num_layers):
             size = factor_num * (2 ** (num_layers - i))
             lins.append(nn.Linear(size, size // 2))
-        pred = nn.Linear(factor_num * 2, 1)
-        nn.init.normal_(ug.weight, std=0.01)
-        nn.init.normal_(um.weight, std=0.01)
-        nn.init.normal_(ig.weight, std=0.01)
-        nn.init.normal_(im.weight, std=0.01)
-        for m in lins:
-            nn.init.xavier_uniform_(m.weight)
-        nn.init.kaiming_uniform_(pred.weight, a=1, nonlinearity="sigmoid")
-        for m in lins + [pred]:
-            m.bias.data.zero_()
+        pred = nn.Linear(factor_num if self.variant else factor_num * 2, 1)
+        if model != "NeuMF-pre":
+            nn.init.normal_(ug.weight, std=0.01)
+            nn.init.normal_(um.weight, std=0.01)
+            nn.init.normal_(ig.weight, std=0.01)
+            nn.init.normal_(im.weight, std=0.01)
+            for m in lins:
+                nn.init.xavier_uniform_(m.weight)
+            nn.init.kaiming_uniform_(pred.weight, a=1, nonlinearity="sigmoid")
+            for m in lins + [pred]:
+                m.bias.data.zero_()
+        else:
+            cpu = lambda t: t.detach().to("cpu", torch.float32)      # noqa: E731
+            ug.weight.data.copy_(cpu(GMF_model.embed_user_GMF.weight))
+            ig.weight.data.copy_(cpu(GMF_model.embed_item_GMF.weight))
+            um.weight.data.copy_(cpu(MLP_model.embed_user_MLP.weight))
+            im.weight.data.copy_(cpu(MLP_model.embed_item_MLP.weight))
+            theirs = [x for x in MLP_model.MLP_layers if isinstance(x, nn.Linear)]
+            for m1, m2 in zip(lins, theirs):
+                m1.weight.data.copy_(cpu(m2.weight))
+                m1.bias.data.copy_(cpu(m2.bias))
+            pw = torch.cat([cpu(GMF_model.predict_layer.weight), cpu(MLP_model.predict_layer.weight)], dim=1)
+            pb = cpu(GMF_model.predict_layer.bias) + cpu(MLP_model.predict_layer.bias)
+            pred.weight.data.copy_(0.5 * pw)
+            pred.bias.data.copy_(0.5 * pb)
         pieces = [ug.weight.data, ig.weight.data, um.weight.data, im.weight.data]
         for m in lins:
             pieces += [m.weight.data, m.bias.data]
@@ -110,6 +129,7 @@ class NCF(BaseVictim):
         st.n_users, st.n_items, st.factor, st.n_layers = U, I, f, self.L
         st.lr, st.beta1, st.beta2, st.eps = self.config["lr"], 0.9, 0.999, 1e-8
         st.tower_fp32 = 1 if self.tower_precision == "fp32" else 0
+        st.variant = self.variant
         st.params, st.m, st.v, st.grads, st.n_params = (self.flat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                                         self.g.data_ptr(), total)
         st.work, st.work_floats, st.max_batch, st.loss_acc = self.work.data_ptr(), work_floats, self.max_batch, self.loss_acc.data_ptr()

@@ -267,6 +267,51 @@ def test_ncf_default_tower_init_stream_and_epoch_match_reference(precision):
         _mostly_close(m(torch.as_tensor(z["q_users"]), torch.as_tensor(z["q_items"])).cpu(), z["q_scores"], 5e-3, 1e-5, 0.9, 1e-2)
 
 
+@pytest.mark.parametrize("variant", ["GMF", "MLP", "NeuMF-pre"])
+def test_ncf_variants_match_reference(variant):
+    """ncf.py:49-53, 62-104, 112-131: 'GMF' (predict on the GMF product), 'MLP' (predict on the tower output) and
+    'NeuMF-pre' (initialised from the two trained ones, ncf.py:79-104) against golden runs of the reference
+    (tests/golden/make_golden_ncf_variants.py), fp32 tower, element-wise."""
+    from recad_b200 import model
+    z0 = util.load("ncf_dev.npz")
+    z = util.load("ncf_variants_dev.npz")
+    U, I = META["dev"]["n_users"], META["dev"]["n_items"]
+    batches = util.split_batches(z0, ("batch_users", "batch_items", "batch_labels"))
+
+    def build(name, prefix, **extra):
+        data = StubData(U, I, batches, ("users", "items", "labels"))
+        data.per_epoch = len(batches) // 2
+        m = model.from_config("victim", "ncf", factor_num=8, num_layers=3, model=name, tower_precision="fp32",
+                              device=torch.device(DEV), **extra).I(dataset=data)
+        return m
+
+    def check(m, prefix, n_epochs):
+        losses = [m.train_step()[0] for _ in range(n_epochs)]
+        _close(losses, z[f"{prefix}_losses"], rtol=1e-4, atol=0)
+        lins = [x for x in m.MLP_layers if isinstance(x, torch.nn.Linear)]
+        for got, key in ((m.embed_user_GMF.weight, "ug"), (m.embed_item_GMF.weight, "ig"), (m.embed_user_MLP.weight, "um"),
+                         (m.embed_item_MLP.weight, "im"), (lins[0].weight, "W0"), (lins[2].bias, "b2"),
+                         (m.predict_layer.weight, "Wp"), (m.predict_layer.bias, "bp")):
+            _close(got.cpu(), z[f"{prefix}_final_{key}"], rtol=1e-4, atol=2e-6)
+        _close(m(torch.as_tensor(z0["q_users"]), torch.as_tensor(z0["q_items"])).cpu(), z[f"{prefix}_q_scores"], rtol=1e-4, atol=2e-6)
+
+    if variant in ("GMF", "MLP"):
+        m = build(variant, variant)
+        assert m.predict_layer.weight.shape == (1, 8)
+        _load_ncf(m, z, f"{variant}_init", 3)
+        check(m, variant, 2)
+        return
+    parts = {}
+    for name in ("GMF", "MLP"):                       # the trained parts, as the reference left them
+        parts[name] = build(name, name)
+        _load_ncf(parts[name], z, f"{name}_final", 3)
+    m = build("NeuMF-pre", "pre", GMF_model=parts["GMF"], MLP_model=parts["MLP"])
+    for got, key in ((m.embed_user_GMF.weight, "ug"), (m.embed_item_MLP.weight, "im"), (m.predict_layer.weight, "Wp"),
+                     (m.predict_layer.bias, "bp")):
+        assert np.array_equal(got.cpu().numpy(), z[f"pre_init_{key}"]), key        # ncf.py:79-104, copies and halves: exact
+    check(m, "pre", 1)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 def test_ncf_training_is_bit_stable_from_run_to_run(precision):
     """No atomics on any parameter gradient: two runs from the same weights over the same batches end with identical bits
