@@ -49,11 +49,11 @@ def main():
     t0 = time.time()
     victim_data = recad.dataset.from_config("implicit", "ml1m", need_graph=True, sample="pairwise", device=dev, download=False,
                                             train_dict=tr, valid_dict=va, test_dict=te, graph_edges="train")
-    attack_data = recad.dataset.from_config("explicit", "ml1m", device=torch.device("cpu"), download=False, train_dict=ex_train,
+    attack_data = recad.dataset.from_config("explicit", "ml1m", device=dev, download=False, train_dict=ex_train,
                                             valid_dict=kvr(va, 4), test_dict=kvr(te, 4)).partial_sample(user_ratio=0.2)
     cfg = {"victim_data": victim_data, "attack_data": attack_data,
            "victim": recad.model.from_config("victim", "lightgcn", latent_dim_rec=64, lightGCN_n_layers=3, device=dev),
-           "attacker": recad.model.from_config("attacker", "aush", device=torch.device("cpu")),
+           "attacker": recad.model.from_config("attacker", "aush", device=dev),       # the reference's own torch code, moved by execute()
            "rec_epoch": a.rec_epoch, "attack_epoch": a.attack_epoch, "device": dev}
     wf = recad.workflow.from_config("no defense", **cfg)
     t_build = time.time() - t0
@@ -65,7 +65,7 @@ def main():
         torch.cuda.synchronize(); t = time.time()
         out = nt(self, **kw)
         torch.cuda.synchronize()
-        key = "attacker_train_s (reference AUSH, host)" if kw["model"] is self.attacker else f"victim_train_s[{len([k for k in phases if k.startswith('victim')])}]"
+        key = "attacker_train_s (reference AUSH: its own torch code + numpy masks)" if kw["model"] is self.attacker else f"victim_train_s[{len([k for k in phases if k.startswith('victim')])}]"
         phases[key] = round(time.time() - t, 3)
         return out
     ev = type(wf).normal_evaluate
