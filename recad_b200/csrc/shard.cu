@@ -18,6 +18,8 @@
 // = 2 L + 3 barriers per batch.
 // The barrier is a one-block kernel on a monotonically increasing epoch (st.release.sys to every peer's pad, ld.acquire.sys
 // on the own pad), so the whole epoch is enqueued without touching the host.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -133,7 +135,8 @@ SideRes* side_res() {
   if (!r.side) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&r.side, cudaStreamNonBlocking, hi) != cudaSuccess) return nullptr;
+    const bool low = getenv("RECAD_SHARD_SIDE_LOW") && atoi(getenv("RECAD_SHARD_SIDE_LOW"));   // experiment: reduce fills the SpMM's tail
+    if (cudaStreamCreateWithPriority(&r.side, cudaStreamNonBlocking, low ? lo : hi) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&r.ev_go, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&r.ev_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
@@ -225,7 +228,8 @@ struct Shard {
   // owner's half of an exchange over its slice of the item block (side stream)
   int reduce_rows(const ReduceArgs& a, bool mc_y, bool mc_z) {
     if (a.n <= 0) return RECAD_OK;
-    const unsigned grid = (unsigned)std::min<int64_t>((a.n + 511) / 512, 48);
+    static const int max_blocks = getenv("RECAD_SHARD_REDUCE_BLOCKS") ? std::max(1, atoi(getenv("RECAD_SHARD_REDUCE_BLOCKS"))) : 48;
+    const unsigned grid = (unsigned)std::min<int64_t>((a.n + 511) / 512, max_blocks);
     if (mc_y && mc_z) shard_reduce_kernel<true, true><<<grid, 512, 0, sr->side>>>(a);
     else if (mc_y) shard_reduce_kernel<true, false><<<grid, 512, 0, sr->side>>>(a);
     else if (mc_z) shard_reduce_kernel<false, true><<<grid, 512, 0, sr->side>>>(a);
