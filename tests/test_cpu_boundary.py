@@ -434,3 +434,46 @@ def test_soa_epoch_sampler_equals_plain_sampler_and_shuffle():
             assert np.array_equal(key2, key) and pos2[0] == pos[0]
             perm32 = ops.permutation_apply32(j[:m], np.empty(max(m, 1), np.int32))
             assert np.array_equal(perm32, ops.permutation_apply(j_ref))
+
+
+def test_scalar_and_avx512_stream_parse_agree(monkeypatch):
+    """The AVX-512 window parse (csrc/sampler_avx512.cpp, taken when the CPU has it) and the scalar parse produce the same
+    samples, shuffle draws and generator state."""
+    rng = np.random.default_rng(3)
+    U, I, n = 4000, 500, 200000
+    lens = rng.integers(0, 70, U)
+    lens[::97] = 0                                           # users without positives are dropped (implicit.py:63-64)
+    ptr = np.zeros(U + 1, np.int64)
+    np.cumsum(lens, out=ptr[1:])
+    col = np.concatenate([np.sort(rng.choice(I, l, replace=False)) for l in lens]).astype(np.int32)
+    outs = []
+    for scalar in ("1", "0"):
+        monkeypatch.setenv("RECAD_SAMPLER_SCALAR", scalar)
+        np.random.seed(12)
+        _, key, pos = ops._np_state()
+        users, rel, negs, j = (np.empty(n, np.uint32) for _ in range(4))
+        m = ops.mt_pairwise_soa_raw(key, pos, U, I, n, ptr, col, users, rel, negs, j)
+        outs.append((m, users[:m].copy(), rel[:m].copy(), negs[:m].copy(), j[:m].copy(), key.copy(), pos[0]))
+    a, b = outs
+    assert a[0] == b[0] and all(np.array_equal(x, y) for x, y in zip(a[1:6], b[1:6])) and a[6] == b[6]
+
+
+def test_injected_dataset_reuses_the_parents_sampler_filter():
+    """ops.filter_parent_hint: the per-user filter blocks of a dataset derived by appending rows equal a build from scratch."""
+    rng = np.random.default_rng(0)
+    U, I, F = 5000, 800, 7
+    lens = rng.integers(0, 60, U)
+    ptr = np.zeros(U + 1, np.int64)
+    np.cumsum(lens, out=ptr[1:])
+    col = np.concatenate([np.sort(rng.choice(I, l, replace=False)) for l in lens]).astype(np.int32)
+    ops.pairwise_filter(ptr, col, U)
+    fl = rng.integers(1, 40, F)
+    fptr = np.concatenate([[0], np.cumsum(fl)])
+    fcol = np.concatenate([np.sort(rng.choice(I, l, replace=False)) for l in fl]).astype(np.int32)
+    nptr = np.concatenate([ptr, ptr[-1] + fptr[1:]]).astype(np.int64)
+    ncol = np.concatenate([col, fcol]).astype(np.int32)
+    ops.filter_parent_hint(nptr, ncol, ptr, col, U)
+    f1, e1 = ops.pairwise_filter(nptr, ncol, U + F)
+    nptr2, ncol2 = nptr.copy(), ncol.copy()
+    f2, e2 = ops.pairwise_filter(nptr2, ncol2, U + F)
+    assert np.array_equal(f1, f2) and np.array_equal(e1, e2)
