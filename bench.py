@@ -226,6 +226,21 @@ def run_b200(args, w):
     b.record()
     torch.cuda.synchronize()
     spmm_ms = a.elapsed_time(b) / reps
+    # parity at full size, outside every timed region: one product against torch.sparse.mm accumulating in fp64
+    spmm_check = None
+    try:
+        rows_chk = torch.randint(0, graph.n_rows, (200_000,), device=dev)
+        Aref = torch.sparse_csr_tensor(graph.rowptr, graph.colidx.long(), graph.vals.double(), (graph.n_rows, graph.n_rows))
+        ref = torch.sparse.mm(Aref, X.double())
+        ops.spmm(graph, X, Y, X, Z, 0.25)
+        e1 = float(((Y.double() - ref).abs().max() / ref.abs().max()).item())
+        e2 = float(((Z.double() - 0.25 * (X.double() + ref)).abs().max() / ref.abs().max()).item())
+        spmm_check = {"vs": "torch.sparse.mm (CSR, fp64 accumulate) on the same graph and input", "nnz": graph.nnz,
+                      "max_abs_err_over_max_abs_Y": e1, "max_abs_err_over_max_abs_Z(fused mean epilogue)": e2, "ok": bool(e1 < 1e-5 and e2 < 1e-5)}
+        del Aref, ref, rows_chk
+        torch.cuda.empty_cache()
+    except Exception as e:   # noqa: BLE001 -- informative only
+        spmm_check = {"error": f"{type(e).__name__}: {str(e)[:160]}"}
     pk, pk_src = peaks()
     alg = graph.algorithmic_bytes(D) + graph.n_rows * 4 * D * 2       # + read C, write Z of the fused epilogue
     achieved = alg / (spmm_ms * 1e-3) / 1e9
@@ -310,6 +325,7 @@ def run_b200(args, w):
     }
     if roofline_eval:
         out["roofline_eval"] = roofline_eval
+    out["spmm_check_full_size"] = spmm_check
     if not args.no_gpu_baseline:
         try:
             out["gpu_library_baseline"] = torch_gpu_reference(graph, U, I, D, L, B, n_batches, dev)

@@ -61,6 +61,7 @@ MODEL = {   # default.py:104-133 (+ logging_level / device, 232-233)
         "lightgcn": {
             "latent_dim_rec": 128, "lightGCN_n_layers": 3, "A_split": False, "pretrain": False, "keep_prob": 0.6,
             "dropout": 0.0, "lambda": 0.0001, "optim": "adam", "lr": 0.001,
+            "init_on_device": False,     # NEW: draw the initial tables on the GPU (not the reference's CPU stream)
         },
         "mf": {"factor_num": 3, "embedding_size": 128, "dropout": 0, "optim": "adam", "lr": 0.001},
         "ncf": {"factor_num": 32, "num_layers": 5, "dropout": 0, "model": "NeuMF-end", "GMF_model": None,

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--workload", default="synthetic")
     ap.add_argument("--fake", type=int, default=50)
+    ap.add_argument("--device-init", action="store_true", help="fresh models drawn on the GPU instead of replaying the CPU init stream")
     args = ap.parse_args()
     w = bench.WORKLOADS[args.workload]
     U, I, D, L, B = w["n_users"], w["n_items"], w["D"], w["L"], w["batch"]
@@ -60,7 +61,8 @@ def main():
             fake = fake_profiles(rng, args.fake, I, target[0])
             sync(); t0 = time.time()
             data = clean.inject_data("explicit", fake, filter_num=4)
-            victim = model.from_config("victim", "lightgcn", latent_dim_rec=D, lightGCN_n_layers=L, device=dev).I(dataset=data)
+            victim = model.from_config("victim", "lightgcn", latent_dim_rec=D, lightGCN_n_layers=L, device=dev,
+                                       init_on_device=args.device_init).I(dataset=data)
             sync(); t1 = time.time()
             samples = data.epoch_samples(dev)
             sync(); t2 = time.time()
