@@ -324,6 +324,76 @@ int recad_wmf_fit(const recad_wmf* st, const float* data, const int32_t* orders,
 int recad_wmf_backward(const recad_wmf* st, const float* data, const int32_t* orders, int32_t n_epochs, int64_t step0,
                        const float* snap, float* Pbar, float* Qbar, float* scratch, float* d_data, void* stream);
 
+/* ------------------------------------------------------------------------ *
+ * AUSH generator / discriminator step  (recad/model/attacker/aush.py:78-180, 182-230, 254-283)
+ * ------------------------------------------------------------------------ */
+
+/* The discriminator's parameters (Linear(I,150)-Sigmoid-Linear(150,150)-Sigmoid-Linear(150,150)-Sigmoid-Linear(150,1)-Sigmoid,
+ * aush.py:269-283) live in one flat [dev] float buffer; offsets [host] int64[9] = float offsets of
+ *   main.0.weight^T [I, 152], main.0.bias [152], main.2.weight [150, 152], main.2.bias [152], main.4.weight [150, 152],
+ *   main.4.bias [152], main.6.weight [152], main.6.bias [4], and the TOTAL float count
+ * (rows padded from 150 to 152 floats; the padding must be zero-initialised and stays zero). */
+int recad_aush_d_layout(int64_t n_items, int64_t* offsets);
+
+typedef struct recad_aush {
+  int64_t n_items;
+  int32_t n_sel;             /* |selected_ids| (default.py:166), <= 64 */
+  int32_t filler_num;        /* default.py:161 */
+  float lr, beta1, beta2, eps;   /* the discriminator's Adam (aush.py:32-35; lr_d, default.py:163) */
+  /* generator Linear(I,128)-Sigmoid-Linear(128,I)-Sigmoid, x 5 (aush.py:254-266).  Read only: the reference detaches the
+   * generator's output before every loss (aush.py:128), so its optimizer never sees a gradient. */
+  const float* G_W1t;        /* [dev] float[I, 128] = main.0.weight^T */
+  const float* G_b1;         /* [dev] float[128] */
+  const float* G_W2;         /* [dev] float[I, 128] = main.2.weight */
+  const float* G_b2;         /* [dev] float[I] */
+  float* D;                  /* [dev] float[recad_aush_d_layout total] */
+  float* Dm;                 /* [dev] Adam first moment, same layout  (training only) */
+  float* Dv;                 /* [dev] Adam second moment              (training only) */
+  const int32_t* selected;   /* [dev] int32[n_sel], ascending */
+  float* work;               /* [dev] float[recad_aush_work_floats]   (training only) */
+} recad_aush;
+
+/* The sparse form of one epoch of batches (aush.py:100-121).  Row r of the epoch = the r-th user the dataset's batch
+ * generator handed out; batch k = rows [k * batch, min(n_rows, (k + 1) * batch)).  F = filler_num, S = n_sel, slots s in
+ * the order of recad_aush.selected. */
+typedef struct recad_aush_epoch {
+  int64_t n_rows;
+  int32_t batch;
+  int32_t _pad;
+  const int32_t* cols;       /* [dev] int32[n_rows, F] the filler columns sample_fillers drew (repeats kept) */
+  const float* tval;         /* [dev] float[n_rows, F] input_template at that column = real rating (0 for a repeated column) */
+  const float* dval;         /* [dev] float[n_rows, F] real * (fillers_mask + selects_mask) at that column, 0 for a repeated
+                                                       or a selected column (those are carried by rsel) */
+  const float* rsel;         /* [dev] float[n_rows, S] real * (fillers_mask + selects_mask) at the selected columns */
+  const float* tsel;         /* [dev] float[n_rows, S] input_template at the selected columns */
+  const float* msel;         /* [dev] float[n_rows, S] fillers_mask + selects_mask at the selected columns */
+  const float* zr;           /* [dev] float[n_rows, S] ZR_mask at the selected columns (aush.py:111-117) */
+  const int32_t* colptr;     /* [dev] int32[n_batches, I + 1]  column index of every batch (recad_aush_plan_columns) */
+  const int32_t* ent;        /* [dev] int32[n_rows * (F + S)] */
+} recad_aush_epoch;
+
+int64_t recad_aush_work_floats(int64_t n_items, int64_t n_rows, int32_t batch, int32_t n_sel);
+/* HOST: per batch, the (row, slot) pairs of the discriminator inputs grouped by item column (row-major inside a column):
+ * colptr [host] int32[n_batches, I + 1] (offsets relative to the batch's first entry), ent [host] int32[n_rows * (F + S)]
+ * = row_in_batch * (F + S) + slot.  This index gives the first-layer gradient a fixed summation order without atomics. */
+int recad_aush_plan_columns(const int32_t* cols, int64_t n_rows, int32_t batch, int32_t F, const int32_t* selected, int32_t S,
+                            int64_t n_items, int32_t* colptr, int32_t* ent);
+/* One epoch of Aush.train_step (aush.py:100-170): per batch the generator's forward on the selected columns, the
+ * discriminator's forward / backward on the real and the fake rows, its dense Adam step (step0 = steps taken before), and
+ * the forward of the updated discriminator on the fake rows.  loss_out [dev] double[4] = the tuple train_step returns:
+ * means over the batches of d_loss, g_loss_rec, g_loss_shilling, g_loss_gan (aush.py:171-176). */
+int recad_aush_train_epoch(const recad_aush* st, const recad_aush_epoch* ep, int64_t step0, double* loss_out, void* stream);
+/* Generator forward of generate_fake (aush.py:213-216): gen_out [dev] float[n_rows, S] = netG(input_template)[:, selected]. */
+int recad_aush_generate(const recad_aush* st, const int32_t* cols, const float* tval, int64_t n_rows, float* gen_out, void* stream);
+/* HOST: the global-generator draws of ONE batch, bit-exact (aush.py:59-76 sample_fillers = np.random.choice with
+ * replacement per row from the row's candidate list; 113-117 np.random.shuffle of the argwhere'd ZR pool).
+ * users [host] int64[B]; cand_ptr / cand_items: per-user candidate lists in the order of the reference's
+ * list(set(nonzero columns) & filler_pool); zero_sel [host] uint8[B, S] = (real == 0) at the selected columns, slots in
+ * ascending column order; cols_out [host] int32[B, F]; zr_out [host] float[B, S]. */
+int recad_mt19937_aush_batch(uint32_t* key, int32_t* pos, int64_t B, const int64_t* users, const int64_t* cand_ptr,
+                             const int32_t* cand_items, int32_t F, int32_t S, const uint8_t* zero_sel, double zr_ratio,
+                             int32_t* cols_out, float* zr_out);
+
 /* scores[b] = <O[users[b]], O[n_users + items[b]]> (lightgcn.py:174-183 after a
  * propagate; O must be current). */
 int recad_dot_scores(const float* O, int64_t n_users, const int64_t* users, const int64_t* items,

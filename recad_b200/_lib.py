@@ -59,6 +59,18 @@ class WMF(C.Structure):
                 ("P", vp), ("Q", vp), ("mP", vp), ("vP", vp), ("mQ", vp), ("vQ", vp)]
 
 
+class Aush(C.Structure):
+    """struct recad_aush"""
+    _fields_ = [("n_items", i64), ("n_sel", i32), ("filler_num", i32), ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32),
+                ("G_W1t", vp), ("G_b1", vp), ("G_W2", vp), ("G_b2", vp), ("D", vp), ("Dm", vp), ("Dv", vp), ("selected", vp), ("work", vp)]
+
+
+class AushEpoch(C.Structure):
+    """struct recad_aush_epoch"""
+    _fields_ = [("n_rows", i64), ("batch", i32), ("_pad", i32), ("cols", vp), ("tval", vp), ("dval", vp), ("rsel", vp), ("tsel", vp),
+                ("msel", vp), ("zr", vp), ("colptr", vp), ("ent", vp)]
+
+
 class MF(C.Structure):
     """struct recad_mf"""
     _fields_ = [
@@ -109,6 +121,12 @@ SIGNATURES = {
     "recad_wmf_snapshot_floats": (i64, [C.POINTER(WMF), i32]),
     "recad_wmf_fit": (C.c_int, [C.POINTER(WMF), vp, vp, i32, i64, i32, vp, vp]),
     "recad_wmf_backward": (C.c_int, [C.POINTER(WMF), vp, vp, i32, i64, vp, vp, vp, vp, vp, vp]),
+    "recad_aush_d_layout": (C.c_int, [i64, C.POINTER(i64)]),
+    "recad_aush_work_floats": (i64, [i64, i64, i32, i32]),
+    "recad_aush_plan_columns": (C.c_int, [vp, i64, i32, i32, vp, i32, i64, vp, vp]),
+    "recad_aush_train_epoch": (C.c_int, [C.POINTER(Aush), C.POINTER(AushEpoch), i64, vp, vp]),
+    "recad_aush_generate": (C.c_int, [C.POINTER(Aush), vp, vp, i64, vp, vp]),
+    "recad_mt19937_aush_batch": (C.c_int, [vp, C.POINTER(i32), i64, vp, vp, vp, i32, i32, vp, C.c_double, vp, vp]),
     "recad_dot_scores": (C.c_int, [vp, i64, vp, vp, i64, i32, vp, vp]),
     "recad_mf_forward": (C.c_int, [C.POINTER(MF), vp, vp, i64, vp, vp]),
     "recad_mf_train_epoch": (C.c_int, [C.POINTER(MF), vp, vp, i64, i64, i64, vp]),

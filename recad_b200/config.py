@@ -69,11 +69,16 @@ MODEL = {   # default.py:104-133 (+ logging_level / device, 232-233)
                 # NEW: "tf32x3" = tower GEMMs on the tensor cores (fp32-accurate, ~2^-21); "fp32" = exact CUDA-core
                 # GEMMs whose ReLU masks are bit-stable (element-wise parity with the reference's fp32)
                 "tower_precision": "tf32x3"},
-    }
+    },
+    "attacker": {   # default.py:159-168
+        "aush": {"attack_num": 50, "filler_num": 36, "lr_g": 0.01, "lr_d": 0.001, "optim_g": "adam", "optim_d": "adam",
+                 "selected_ids": [62], "ZR_ratio": 0.2},
+    },
 }
-for _m in MODEL["victim"].values():
-    _m["logging_level"] = logging.INFO
-    _m["device"] = DEVICE
+for _scope in MODEL.values():
+    for _m in _scope.values():
+        _m["logging_level"] = logging.INFO
+        _m["device"] = DEVICE
 
 WORKFLOW = {   # default.py:247-282
     "no defense": {

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "librecad_b200.so")
-SOURCES = ["api.cu", "scan.cu", "sort.cu", "csr.cu", "spmm.cu", "bpr.cu", "shard.cu", "wmf.cu", "mf.cu", "ncf.cu", "eval.cu", "eval_tc.cu", "gemm_tc.cu", "sampler.cpp"]
+SOURCES = ["api.cu", "scan.cu", "sort.cu", "csr.cu", "spmm.cu", "bpr.cu", "shard.cu", "wmf.cu", "aush.cu", "mf.cu", "ncf.cu", "eval.cu", "eval_tc.cu", "gemm_tc.cu", "sampler.cpp"]
 HEADERS = ["common.cuh", "rank_epilogue.cuh", "tc_common.cuh", os.path.join(ROOT, "include", "recad_b200.h")]
 # host-only translation units built by g++ with ISA flags of their own (each is entered only after a run-time CPU check)
 CXX_SOURCES = {"sampler_avx512.cpp": ["-mavx512f", "-mbmi", "-mlzcnt"]}

@@ -16,6 +16,7 @@
 #include <atomic>
 #include <chrono>
 #include <climits>
+#include <cmath>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -1278,6 +1279,41 @@ int recad_permutation_apply(int64_t n, const uint32_t* j, int64_t* perm) {
   }
   if (getenv("RECAD_SAMPLER_TRACE"))
     fprintf(stderr, "[sampler] shuffle swaps %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+  return RECAD_OK;
+}
+
+// The draws of one AUSH batch on the global generator, in the reference's order: per row F draws of
+// random_interval(len - 1) indexing the row's candidate list (np.random.choice(a, size=F, replace=True) ==
+// randint(0, len, F), aush.py:64-68), then the Fisher-Yates pass of np.random.shuffle over the batch's ZR pool (the
+// (row, selected column) pairs with real == 0 in row-major order, aush.py:113-117); the first floor(P * (1 - ZR_ratio))
+// pairs of the shuffled pool leave the mask.
+int recad_mt19937_aush_batch(uint32_t* key, int32_t* pos, int64_t B, const int64_t* users, const int64_t* cand_ptr,
+                             const int32_t* cand_items, int32_t F, int32_t S, const uint8_t* zero_sel, double zr_ratio,
+                             int32_t* cols_out, float* zr_out) {
+  if (!key || !pos || B < 0 || F < 0 || S < 0 || (B && (!users || !cand_ptr || !cand_items || !cols_out)) || (B && S && (!zero_sel || !zr_out))) {
+    recad::set_error("mt19937_aush_batch: bad argument");
+    return RECAD_ERR_ARG;
+  }
+  MT mt(key, *pos);
+  for (int64_t b = 0; b < B; ++b) {
+    const int64_t lo = cand_ptr[users[b]], len = cand_ptr[users[b] + 1] - lo;
+    if (len <= 0) {
+      recad::set_error("mt19937_aush_batch: user %lld has no filler candidate", (long long)users[b]);   // np.random.choice: 'a' cannot be empty
+      return RECAD_ERR_ARG;
+    }
+    const uint32_t r = (uint32_t)(len - 1), mask = MT::mask_of(r);
+    for (int f = 0; f < F; ++f) cols_out[b * F + f] = cand_items[lo + (r ? mt.masked_with(r, mask) : 0u)];
+  }
+  std::vector<int64_t> pool;
+  for (int64_t q = 0; q < B * S; ++q) {
+    zr_out[q] = zero_sel[q] ? 1.f : 0.f;
+    if (zero_sel[q]) pool.push_back(q);
+  }
+  const int64_t P = (int64_t)pool.size();
+  for (int64_t i = P - 1; i > 0; --i) std::swap(pool[i], pool[(int64_t)mt.masked((uint64_t)i)]);
+  const int64_t cut = (int64_t)std::floor((double)P * (1.0 - zr_ratio));
+  for (int64_t q = 0; q < cut && q < P; ++q) zr_out[pool[q]] = 0.f;
+  *pos = mt.pos;
   return RECAD_OK;
 }
 

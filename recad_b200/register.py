@@ -2,12 +2,12 @@
 registries -- no reference file is edited:
 
     import recad, recad_b200.register
-    recad_b200.register.install()            # adds 'lightgcn_b200', 'mf_b200', 'ncf_b200', dataset 'implicit_b200'
-    recad_b200.register.install(override=True)   # ALSO rebinds 'lightgcn'/'mf'/'ncf'/'implicit' and the evaluator,
+    recad_b200.register.install()            # adds 'lightgcn_b200', 'mf_b200', 'ncf_b200', attacker 'aush_b200', dataset 'implicit_b200'
+    recad_b200.register.install(override=True)   # ALSO rebinds 'lightgcn'/'mf'/'ncf'/'aush'/'implicit' and the evaluator,
                                                  # so an unmodified `recad_runner ...` runs on the CUDA kernels
 
-Registries touched: recad.model.factories['victim'] (recad/model/__init__.py:3-18),
-recad.default.MODEL['victim'] (recad/default.py:104-133), recad.dataset.factories
+Registries touched: recad.model.factories['victim'] / ['attacker'] (recad/model/__init__.py:3-18),
+recad.default.MODEL['victim'] / ['attacker'] (recad/default.py:104-168), recad.dataset.factories
 (recad/dataset/__init__.py:13), and with override=True `Normal.normal_evaluate` /
 `Defense.normal_evaluate` (recad/workflow/normal.py:111-160, defense.py:125-174) and the name
 `recad.model.attacker.aia.WMFTrainer`, which AIA / Leg-UP look up every attack step to retrain their surrogate
@@ -27,6 +27,10 @@ def install(override=False):
         for key in ([f"{name}_b200", name] if override else [f"{name}_b200"]):
             ref_model.factories["victim"][key] = cls
             ref_default.MODEL["victim"].setdefault(key, dict(MODEL["victim"][name]))
+    from .attacker import Aush
+    for key in (["aush_b200", "aush"] if override else ["aush_b200"]):
+        ref_model.factories["attacker"][key] = Aush
+        ref_default.MODEL["attacker"].setdefault(key, dict(MODEL["attacker"]["aush"]))
     ref_dataset.factories["implicit_b200"] = ImplicitData
     if override:
         ref_dataset.factories["implicit"] = ImplicitData

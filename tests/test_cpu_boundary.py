@@ -36,6 +36,8 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.LightGCN) == 8 + 16 + 8 + 6 * 4 + 9 * 8
     assert C.sizeof(_lib.MF) == 16 + 6 * 4 + 17 * 8
     assert C.sizeof(_lib.NCF) == 16 + 8 + 16 + 8 + 4 * 8 + 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(_lib.Aush) == 8 + 2 * 4 + 4 * 4 + 9 * 8
+    assert C.sizeof(_lib.AushEpoch) == 8 + 2 * 4 + 9 * 8
 
 
 def test_host_error_paths_report_through_last_error():
@@ -51,6 +53,9 @@ def test_host_error_paths_report_through_last_error():
     assert lib.recad_ncf_grad(None, None, None, 4, 4, None) < 0
     assert lib.recad_mt19937_permutation_draw(None, None, 5, None) < 0 and b"permutation_draw" in lib.recad_last_error()
     assert lib.recad_permutation_apply(5, None, None) < 0 and b"permutation_apply" in lib.recad_last_error()
+    assert lib.recad_aush_train_epoch(None, None, 0, None, None) < 0 and b"aush_train_epoch" in lib.recad_last_error()
+    assert lib.recad_aush_generate(None, None, None, 4, None, None) < 0 and lib.recad_aush_plan_columns(None, 4, 2, 3, None, 1, 10, None, None) < 0
+    assert lib.recad_mt19937_aush_batch(None, None, 4, None, None, None, 3, 1, None, 0.2, None, None) < 0
     assert lib.recad_fullrank_eval_tc(None, None, 10, 64, None, 4, None, None, None, 0, 20, None, None, None, None, None, None, 0,
                                       None) < 0 and b"fullrank_tc" in lib.recad_last_error()
 
@@ -477,3 +482,53 @@ def test_injected_dataset_reuses_the_parents_sampler_filter():
     nptr2, ncol2 = nptr.copy(), ncol.copy()
     f2, e2 = ops.pairwise_filter(nptr2, ncol2, U + F)
     assert np.array_equal(f1, f2) and np.array_equal(e1, e2)
+
+
+def test_aush_host_draws_and_column_plan_match_the_oracle():
+    """Host half of the AUSH step: recad_mt19937_aush_batch consumes np.random exactly as the reference's sample_fillers +
+    ZR-pool shuffle (restated in oracle/aush.py, which the golden run pins), and recad_aush_plan_columns groups the sparse
+    discriminator inputs by column in row order.  No kernel is launched: the attacker object is assembled without its
+    device state."""
+    import ctypes as C
+    from oracle import aush as oa
+    from recad_b200 import attacker
+    mat, _, _, kw, batch, targets, _ = util.aush_case("b")
+    a = attacker.Aush.__new__(attacker.Aush)
+    a._mat, a.n_items, a.selected_ids, a._sel = mat, mat.shape[1], kw["selected_ids"], np.unique(np.asarray(kw["selected_ids"]))
+    a.filler_num, a.ZR_ratio, a._cand = kw["filler_num"], kw["ZR_ratio"], {}
+    np.random.seed(5)
+    elig = oa.eligible_rows(mat, a.selected_ids, targets, a.filler_num)
+    assert np.array_equal(elig, attacker.filler_filter_mat(mat, targets, a.selected_ids, a.filler_num))
+    users = np.random.permutation(elig)[:batch]
+    st = np.random.get_state()
+    real = mat[users]
+    fill = oa.draw_fillers(real, a.n_items, a.selected_ids, targets, a.filler_num)
+    sel = np.zeros_like(fill)
+    sel[:, a.selected_ids] = 1
+    zr = oa.draw_zr(real, sel, a.ZR_ratio)
+    after = np.random.get_state()
+    np.random.set_state(st)
+    cols, zr2 = a._draw_batch(users, targets)
+    mine = np.random.get_state()
+    assert np.array_equal(after[1], mine[1]) and after[2] == mine[2]
+    f2 = np.zeros_like(fill)
+    f2[np.arange(len(users))[:, None], cols] = 1
+    assert np.array_equal(fill, f2) and np.array_equal(zr[:, a._sel], zr2)
+    tval = a._template(users, cols)
+    dense = np.zeros_like(fill)
+    np.add.at(dense, (np.arange(len(users))[:, None], cols), tval)           # repeats carry 0: the sum IS the template
+    assert np.array_equal(dense, real * fill)
+    # column plan of two ragged batches
+    F, S, I, n = a.filler_num, len(a._sel), a.n_items, len(users)
+    b2 = 64
+    nb = (n + b2 - 1) // b2
+    colptr, ent = np.empty((nb, I + 1), dtype=np.int32), np.empty(n * (F + S), dtype=np.int32)
+    sel32 = a._sel.astype(np.int32)
+    vp = lambda x: C.c_void_p(x.ctypes.data)
+    _lib.check(_lib.lib().recad_aush_plan_columns(vp(cols), n, b2, F, vp(sel32), S, I, vp(colptr), vp(ent)), "plan")
+    for k in range(nb):
+        lo, hi = k * b2, min(n, (k + 1) * b2)
+        allc = np.concatenate([cols[lo:hi], np.broadcast_to(sel32, (hi - lo, S))], 1)
+        order = np.argsort(allc.ravel(), kind="stable")
+        assert np.array_equal(ent[lo * (F + S):hi * (F + S)], order)
+        assert np.array_equal(colptr[k], np.concatenate([[0], np.cumsum(np.bincount(allc.ravel(), minlength=I))]))

@@ -29,12 +29,13 @@ def ref_recad(tmp_path, monkeypatch):
         import recad_b200.register as reg
         from recad.model.attacker import aia as ref_aia
         saved = (dict(recad.model.factories["victim"]), dict(recad.dataset.factories), recad.workflow.Normal.normal_evaluate,
-                 recad.workflow.Defense.normal_evaluate)
+                 recad.workflow.Defense.normal_evaluate, dict(recad.model.factories["attacker"]))
         saved_wmf = ref_aia.WMFTrainer
         reg.install(override=True)
         yield recad
         ref_aia.WMFTrainer = saved_wmf
         recad.model.factories["victim"].clear(); recad.model.factories["victim"].update(saved[0])
+        recad.model.factories["attacker"].clear(); recad.model.factories["attacker"].update(saved[4])
         recad.dataset.factories.clear(); recad.dataset.factories.update(saved[1])
         recad.workflow.Normal.normal_evaluate, recad.workflow.Defense.normal_evaluate = saved[2], saved[3]
     finally:
@@ -142,3 +143,34 @@ def test_reference_attacker_retrains_its_surrogate_on_the_cuda_path(ref_recad):
     pred_c[:U, 3].sum().backward()
     assert np.abs(pred.detach().cpu().numpy() - pred_c.detach().numpy()).max() <= 1e-4 * float(pred_c.abs().max()) + 1e-6
     assert np.abs(fake.grad.cpu().numpy() - fake_c.grad.numpy()).max() <= 2e-3 * float(fake_c.grad.abs().max())
+
+
+def test_reference_dataset_and_factory_drive_the_cuda_aush(ref_recad):
+    """`recad.model.from_config("attacker", "aush")` (the reference's factory) resolves to the CUDA attacker after
+    install(override=True); fed by the reference's own ExplicitData batch generator (recad/dataset/explicit.py:166-188) it
+    reproduces the golden run of the reference's Aush on the same dataset: epoch losses, generator state, fake profiles."""
+    recad = ref_recad
+    from recad_b200 import attacker as b_attacker
+    dev = torch.device("cuda:0")
+    mat, G, D, kw, batch, targets, z = util.aush_case("a")
+    tr, te = z["train"].astype(np.float64), z["test"].astype(np.float64)
+    random.seed(2023); np.random.seed(2023); torch.manual_seed(2023)
+    ds = recad.dataset.from_config("explicit", "dev", device=dev, download=False, if_cache=False, remap_enable=False, train_dict=tr.copy(),
+                                   valid_dict=te.copy(), test_dict=te.copy())
+    assert type(ds).__module__.startswith("recad.")
+    att = recad.model.from_config("attacker", "aush", device=dev).I(dataset=ds)
+    assert isinstance(att, b_attacker.Aush)
+    for k, v in att.netG_state().items():                      # same torch.manual_seed -> the reference's initial networks
+        assert np.array_equal(v.cpu().numpy(), G[k]), k
+    for k, v in att.netD_state().items():
+        assert np.array_equal(v.cpu().numpy(), D[k]), k
+    st = np.random.get_state()
+    assert np.array_equal(st[1], z["a_np_key_start"]) and st[2] == int(z["a_np_pos_start"])
+    att = att.to(dev)
+    for e, gold in enumerate(z["a_losses"]):
+        loss = att.train_step(target_id_list=targets, input_describe={}, progress_bar=None)
+        assert np.allclose(loss, gold, rtol=1e-4, atol=0), (e, loss, gold)
+    fake = att.generate_fake(target_id_list=targets)
+    st = np.random.get_state()
+    assert np.array_equal(st[1], z["a_np_key_end"]) and st[2] == int(z["a_np_pos_end"])
+    assert np.mean(fake != z["a_fake"]) <= 2.0 / fake.size

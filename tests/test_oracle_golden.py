@@ -290,3 +290,26 @@ def test_recall_ndcg_known_answer():
     rec, ndcg, cnt = oev.recall_ndcg_at_k(topk, [[1, 9], [7]], 3)
     assert cnt == 2 and np.isclose(rec, 0.5)
     assert np.isclose(ndcg, (1 / np.log2(3)) / (1 + 1 / np.log2(3)))
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_aush_oracle_matches_reference(case):
+    """oracle/aush.py against the live reference run stored by tests/golden/make_golden_aush.py: epoch losses, the
+    discriminator after every epoch, the generator (never moves), the fake profiles and the numpy generator state."""
+    from oracle import aush as oa
+    mat, G, D, kw, batch, targets, z = util.aush_case(case)
+    o = oa.AushOracle(mat, G, D, batch_size=batch, **kw)
+    np.random.set_state(("MT19937", z[f"{case}_np_key_start"], int(z[f"{case}_np_pos_start"]), 0, 0.0))
+    gold = z[f"{case}_losses"]
+    for e in range(len(gold)):
+        assert np.allclose(o.train_step(targets), gold[e], rtol=1e-6, atol=0)
+        for l in range(4):
+            w = z[f"{case}_D{e + 1}__main.{2 * l}.weight"]
+            assert np.abs(o.D.W[l] - w).max() <= 5e-5 * np.abs(w).max()
+    for k in ("main.0.weight", "main.2.bias"):
+        assert np.array_equal(z[f"{case}_G1__{k}"], z[f"{case}_G0__{k}"])         # the reference's generator does not train
+    st = np.random.get_state()
+    assert np.array_equal(st[1], z[f"{case}_np_key_mid"]) and st[2] == int(z[f"{case}_np_pos_mid"])
+    assert np.array_equal(o.generate_fake(targets), z[f"{case}_fake"])
+    st = np.random.get_state()
+    assert np.array_equal(st[1], z[f"{case}_np_key_end"]) and st[2] == int(z[f"{case}_np_pos_end"])

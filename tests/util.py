@@ -39,3 +39,16 @@ def split_batches(z, names):
     sizes = z["batch_sizes"]
     offs = np.concatenate([[0], np.cumsum(sizes)])
     return [tuple(z[n][offs[k]:offs[k + 1]] for n in names) for k in range(len(sizes))]
+
+
+def aush_case(case):
+    """(train_mat, G0, D0, hyper-parameters, golden archive) of tests/golden/aush_synth.npz (make_golden_aush.py)."""
+    z = load("aush_synth.npz")
+    hp = z[f"{case}_hp"]
+    tr = z["train"].astype(np.int64)
+    mat = np.zeros((int(hp[0]), int(hp[1])), dtype=np.float32)
+    mat[tr[:, 0], tr[:, 1]] = tr[:, 2]
+    G = {k[len(case) + 5:]: z[k] for k in z.files if k.startswith(f"{case}_G0__")}
+    D = {k[len(case) + 5:]: z[k] for k in z.files if k.startswith(f"{case}_D0__")}
+    kw = dict(selected_ids=z[f"{case}_selected_ids"].tolist(), filler_num=int(hp[3]), attack_num=int(hp[4]), ZR_ratio=float(hp[5]))
+    return mat, G, D, kw, int(hp[2]), z[f"{case}_targets"].tolist(), z
