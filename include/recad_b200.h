@@ -369,15 +369,16 @@ typedef struct recad_aush_epoch {
   const float* msel;         /* [dev] float[n_rows, S] fillers_mask + selects_mask at the selected columns */
   const float* zr;           /* [dev] float[n_rows, S] ZR_mask at the selected columns (aush.py:111-117) */
   const int32_t* colptr;     /* [dev] int32[n_batches, I + 1]  column index of every batch (recad_aush_plan_columns) */
-  const int32_t* ent;        /* [dev] int32[n_rows * (F + S)] */
+  const int32_t* ent;        /* [dev] int32[n_rows * F] */
 } recad_aush_epoch;
 
 int64_t recad_aush_work_floats(int64_t n_items, int64_t n_rows, int32_t batch, int32_t n_sel);
-/* HOST: per batch, the (row, slot) pairs of the discriminator inputs grouped by item column (row-major inside a column):
- * colptr [host] int32[n_batches, I + 1] (offsets relative to the batch's first entry), ent [host] int32[n_rows * (F + S)]
- * = row_in_batch * (F + S) + slot.  This index gives the first-layer gradient a fixed summation order without atomics. */
-int recad_aush_plan_columns(const int32_t* cols, int64_t n_rows, int32_t batch, int32_t F, const int32_t* selected, int32_t S,
-                            int64_t n_items, int32_t* colptr, int32_t* ent);
+/* HOST: per batch, the (row, filler slot) pairs grouped by item column (row-major inside a column):
+ * colptr [host] int32[n_batches, I + 1] (offsets relative to the batch's first entry), ent [host] int32[n_rows * F]
+ * = row_in_batch * F + slot.  This index gives the first-layer gradient a fixed summation order without atomics (the
+ * selected columns, present in every row, are reduced on the device). */
+int recad_aush_plan_columns(const int32_t* cols, int64_t n_rows, int32_t batch, int32_t F, int64_t n_items, int32_t* colptr,
+                            int32_t* ent);
 /* One epoch of Aush.train_step (aush.py:100-170): per batch the generator's forward on the selected columns, the
  * discriminator's forward / backward on the real and the fake rows, its dense Adam step (step0 = steps taken before), and
  * the forward of the updated discriminator on the fake rows.  loss_out [dev] double[4] = the tuple train_step returns:
@@ -387,12 +388,13 @@ int recad_aush_train_epoch(const recad_aush* st, const recad_aush_epoch* ep, int
 int recad_aush_generate(const recad_aush* st, const int32_t* cols, const float* tval, int64_t n_rows, float* gen_out, void* stream);
 /* HOST: the global-generator draws of ONE batch, bit-exact (aush.py:59-76 sample_fillers = np.random.choice with
  * replacement per row from the row's candidate list; 113-117 np.random.shuffle of the argwhere'd ZR pool).
- * users [host] int64[B]; cand_ptr / cand_items: per-user candidate lists in the order of the reference's
- * list(set(nonzero columns) & filler_pool); zero_sel [host] uint8[B, S] = (real == 0) at the selected columns, slots in
- * ascending column order; cols_out [host] int32[B, F]; zr_out [host] float[B, S]. */
+ * users [host] int64[B]; cand_ptr / cand_items / cand_vals: per-user candidate lists in the order of the reference's
+ * list(set(nonzero columns) & filler_pool) and their ratings; zero_sel [host] uint8[B, S] = (real == 0) at the selected
+ * columns, slots in ascending column order; cols_out [host] int32[B, F]; tval_out [host] float[B, F] (may be NULL) = the
+ * rating at the drawn column, 0 where the row already drew that column; zr_out [host] float[B, S]. */
 int recad_mt19937_aush_batch(uint32_t* key, int32_t* pos, int64_t B, const int64_t* users, const int64_t* cand_ptr,
-                             const int32_t* cand_items, int32_t F, int32_t S, const uint8_t* zero_sel, double zr_ratio,
-                             int32_t* cols_out, float* zr_out);
+                             const int32_t* cand_items, const float* cand_vals, int32_t F, int32_t S, const uint8_t* zero_sel,
+                             double zr_ratio, int32_t* cols_out, float* tval_out, float* zr_out);
 
 /* scores[b] = <O[users[b]], O[n_users + items[b]]> (lightgcn.py:174-183 after a
  * propagate; O must be current). */

@@ -123,10 +123,10 @@ SIGNATURES = {
     "recad_wmf_backward": (C.c_int, [C.POINTER(WMF), vp, vp, i32, i64, vp, vp, vp, vp, vp, vp]),
     "recad_aush_d_layout": (C.c_int, [i64, C.POINTER(i64)]),
     "recad_aush_work_floats": (i64, [i64, i64, i32, i32]),
-    "recad_aush_plan_columns": (C.c_int, [vp, i64, i32, i32, vp, i32, i64, vp, vp]),
+    "recad_aush_plan_columns": (C.c_int, [vp, i64, i32, i32, i64, vp, vp]),
     "recad_aush_train_epoch": (C.c_int, [C.POINTER(Aush), C.POINTER(AushEpoch), i64, vp, vp]),
     "recad_aush_generate": (C.c_int, [C.POINTER(Aush), vp, vp, i64, vp, vp]),
-    "recad_mt19937_aush_batch": (C.c_int, [vp, C.POINTER(i32), i64, vp, vp, vp, i32, i32, vp, C.c_double, vp, vp]),
+    "recad_mt19937_aush_batch": (C.c_int, [vp, C.POINTER(i32), i64, vp, vp, vp, vp, i32, i32, vp, C.c_double, vp, vp, vp]),
     "recad_dot_scores": (C.c_int, [vp, i64, vp, vp, i64, i32, vp, vp]),
     "recad_mf_forward": (C.c_int, [C.POINTER(MF), vp, vp, i64, vp, vp]),
     "recad_mf_train_epoch": (C.c_int, [C.POINTER(MF), vp, vp, i64, i64, i64, vp]),

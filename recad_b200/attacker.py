@@ -30,9 +30,8 @@ _H, _HP = 150, 152
 
 def filler_filter_mat(train_mat, target_id_list=(), selected_ids=(), filler_num=0):
     """utils.py:192-196: the rows with at least filler_num rated items outside selected_ids + target_id_list."""
-    rated = train_mat > 0
     skip = np.unique(np.asarray(list(selected_ids) + list(target_id_list), dtype=np.int64))
-    counts = rated.sum(1) - (rated[:, skip].sum(1) if len(skip) else 0)
+    counts = np.count_nonzero(train_mat > 0, axis=1) - (np.count_nonzero(train_mat[:, skip] > 0, axis=1) if len(skip) else 0)
     return np.where(counts >= filler_num)[0]
 
 
@@ -179,41 +178,33 @@ class Aush(LazyMixin, torch.nn.Module):
         if key not in self._cand:
             pool = set(range(self.n_items)) - set(self.selected_ids) - set(targets)
             ptr = np.zeros(self._mat.shape[0] + 1, dtype=np.int64)
-            items = []
+            items, vals = [np.zeros(0, dtype=np.int32)], [np.zeros(0, dtype=np.float32)]
             for u in filler_filter_mat(self._mat, list(targets), self.selected_ids, 1):
-                lst = list(set(np.argwhere(self._mat[u] > 0).flatten()) & pool)
-                items.append(np.asarray(lst, dtype=np.int32))
+                lst = np.asarray(list(set(np.argwhere(self._mat[u] > 0).flatten()) & pool), dtype=np.int32)
+                items.append(lst)
+                vals.append(self._mat[u, lst])
                 ptr[u + 1] = len(lst)
             np.cumsum(ptr, out=ptr)
-            self._cand = {key: (ptr, np.concatenate(items) if items else np.zeros(0, dtype=np.int32))}
+            self._cand = {key: (ptr, np.concatenate(items), np.concatenate(vals))}
         return self._cand[key]
 
     def _draw_batch(self, users, targets, with_zr=True):
-        """One batch's draws on np.random's global state (recad_mt19937_aush_batch)."""
-        ptr, items = self._candidates(targets)
+        """One batch's draws on np.random's global state (recad_mt19937_aush_batch): the filler columns, input_template at
+        those columns (the rating, once per distinct column of a row) and the ZR mask at the selected columns."""
+        ptr, items, vals = self._candidates(targets)
         B, F, S = len(users), self.filler_num, len(self._sel) if with_zr else 0
         users = np.ascontiguousarray(users, dtype=np.int64)
         cols = np.empty((B, F), dtype=np.int32)
+        tval = np.empty((B, F), dtype=np.float32)
         zr = np.empty((B, S), dtype=np.float32)
-        zero_sel = np.ascontiguousarray(self._mat[users][:, self._sel] == 0, dtype=np.uint8) if S else None
+        zero_sel = np.ascontiguousarray(self._mat[users[:, None], self._sel[None, :]] == 0, dtype=np.uint8) if S else None
         st = np.random.get_state()
         key, pos = np.ascontiguousarray(st[1], dtype=np.uint32).copy(), C.c_int32(int(st[2]))
-        _lib.check(_lib.lib().recad_mt19937_aush_batch(_vp(key), C.byref(pos), B, _vp(users), _vp(ptr), _vp(items), F, S,
-                                                       _vp(zero_sel), float(self.ZR_ratio), _vp(cols), _vp(zr) if S else None),
+        _lib.check(_lib.lib().recad_mt19937_aush_batch(_vp(key), C.byref(pos), B, _vp(users), _vp(ptr), _vp(items), _vp(vals), F, S,
+                                                       _vp(zero_sel), float(self.ZR_ratio), _vp(cols), _vp(tval), _vp(zr) if S else None),
                    "recad_mt19937_aush_batch")
         np.random.set_state(("MT19937", key, pos.value, 0, 0.0))
-        return cols, zr
-
-    def _template(self, users, cols):
-        """input_template at the drawn columns: the rating, once per distinct column of a row."""
-        val = self._mat[users[:, None], cols]
-        order = np.argsort(cols, axis=1, kind="stable")
-        srt = np.take_along_axis(cols, order, 1)
-        dup_sorted = np.zeros(cols.shape, dtype=bool)
-        dup_sorted[:, 1:] = srt[:, 1:] == srt[:, :-1]
-        dup = np.zeros(cols.shape, dtype=bool)
-        np.put_along_axis(dup, order, dup_sorted, 1)
-        return np.where(dup, np.float32(0), val).astype(np.float32)
+        return cols, tval, zr
 
     def _state(self, work=None):
         st = _lib.Aush()
@@ -230,20 +221,19 @@ class Aush(LazyMixin, torch.nn.Module):
         self._require_instance("train_step")
         targets = list(config["target_id_list"])
         index_filter = partial(self._user_filter, targets=targets)
-        users_l, cols_l, zr_l, batch = [], [], [], 0
+        users_l, cols_l, tval_l, zr_l, batch = [], [], [], [], 0
         for dp in self.dataset.generate_batch(user_filter=index_filter, **config):
             users = dp["users"].cpu().numpy().astype(np.int64)
-            cols, zr = self._draw_batch(users, targets)
-            users_l.append(users); cols_l.append(cols); zr_l.append(zr)
+            cols, tval, zr = self._draw_batch(users, targets)
+            users_l.append(users); cols_l.append(cols); tval_l.append(tval); zr_l.append(zr)
             batch = max(batch, len(users))
         if not users_l:
             nan = float("nan")
             return (nan, nan, nan, nan)                          # np.mean([]) of the reference
         if any(len(u) != batch for u in users_l[:-1]):
             raise ops.RecadError("Aush.train_step: the dataset's batches must have one size (the last may be shorter)")
-        users, cols, zr = np.concatenate(users_l), np.concatenate(cols_l), np.concatenate(zr_l)
+        users, cols, tval, zr = np.concatenate(users_l), np.concatenate(cols_l), np.concatenate(tval_l), np.concatenate(zr_l)
         n, F, S, I = len(users), self.filler_num, len(self._sel), self.n_items
-        tval = self._template(users, cols)
         sel_hit = np.isin(cols, self._sel)
         dval = np.where(sel_hit, np.float32(0), tval)
         fm_sel = (cols[:, :, None] == self._sel[None, None, :]).any(1).astype(np.float32) if sel_hit.any() else np.zeros((n, S), np.float32)
@@ -252,10 +242,9 @@ class Aush(LazyMixin, torch.nn.Module):
         rsel = real_sel * msel
         nb = (n + batch - 1) // batch
         colptr = np.empty((nb, I + 1), dtype=np.int32)
-        ent = np.empty(n * (F + S), dtype=np.int32)
-        sel32 = self._sel.astype(np.int32)
+        ent = np.empty(n * F, dtype=np.int32)
         L = _lib.lib()
-        _lib.check(L.recad_aush_plan_columns(_vp(cols), n, batch, F, _vp(sel32), S, I, _vp(colptr), _vp(ent)), "recad_aush_plan_columns")
+        _lib.check(L.recad_aush_plan_columns(_vp(cols), n, batch, F, I, _vp(colptr), _vp(ent)), "recad_aush_plan_columns")
         dev = self.device
         with torch.cuda.device(dev):
             ints = torch.from_numpy(np.concatenate([cols.ravel(), colptr.ravel(), ent])).to(dev)
@@ -282,11 +271,9 @@ class Aush(LazyMixin, torch.nn.Module):
     def generate_fake(self, **kwargs):
         self._require_instance("generate_fake")
         targets = list(kwargs["target_id_list"])
-        available_idx = filler_filter_mat(self._mat, targets, self.selected_ids, self.filler_num)
-        available_idx = np.random.permutation(available_idx)
+        available_idx = np.random.permutation(self._eligible(self._mat, targets))
         idx = available_idx[np.random.randint(0, len(available_idx), self.attack_num)].astype(np.int64)
-        cols, _ = self._draw_batch(idx, targets, with_zr=False)
-        tval = self._template(idx, cols)
+        cols, tval, _ = self._draw_batch(idx, targets, with_zr=False)
         A, S = len(idx), len(self._sel)
         dev = self.device
         with torch.cuda.device(dev):

@@ -56,6 +56,19 @@ def implicit_defaults(name):
     }
 
 
+def explicit_defaults(name):
+    """DATASET['explicit'][name] (default.py:67-89); path_valid is the TEST file there too."""
+    root = _dataset_root()
+    return {
+        "path_train": os.path.abspath(os.path.join(root, name, f"{name}_train.csv")),
+        "path_test": os.path.abspath(os.path.join(root, name, f"{name}_test.csv")),
+        "path_valid": os.path.abspath(os.path.join(root, name, f"{name}_test.csv")),
+        "batch_size": 256, "header": None, "sep": ",", "threshold": 4, "sample": "row",
+        "logging_level": logging.INFO, "train_dict": None, "valid_dict": None, "test_dict": None, "remap_enable": False,
+        "device": DEVICE, "if_cache": False, "cache_dir": os.path.abspath(os.path.join(".", "generated")),
+    }
+
+
 MODEL = {   # default.py:104-133 (+ logging_level / device, 232-233)
     "victim": {
         "lightgcn": {

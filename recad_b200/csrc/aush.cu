@@ -30,7 +30,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace recad {
 
@@ -39,7 +39,6 @@ constexpr int kAHP = 152;       // padded row stride (16-byte rows); the two pad
 constexpr int kAG = 128;        // generator hidden width (aush.py:258)
 constexpr int kAR = 8;          // rows per block pass
 constexpr int kAThreads = 160;  // one thread per hidden unit (+ idle pad threads)
-constexpr int kAWs = 151;       // shared-memory stride of a staged 150 x 150 weight: odd -> no bank conflicts either way
 
 struct AushLayout {
   int64_t W1t, b1, W2, b2, W3, b3, w4, b4, total;
@@ -68,7 +67,9 @@ __device__ __forceinline__ void adam1(float& P, float G, float& M, float& V, con
 }
 
 // ------------------------------------------------------------------------------------------
-// generator forward on the selected columns.  One warp per row; lane l owns hidden units 4l .. 4l+3.
+// generator forward on the selected columns.  One warp per row; lane l owns hidden units 4l .. 4l+3.  The row's
+// (column, value) pairs are fetched 32 at a time with one coalesced load and handed round with shuffles, so that the
+// gathers of W1g^T rows are independent of each other (4 in flight).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 aush_gen_kernel(const float* __restrict__ W1t, const float* __restrict__ b1, const float* __restrict__ W2,
@@ -80,14 +81,25 @@ aush_gen_kernel(const float* __restrict__ W1t, const float* __restrict__ b1, con
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
   float4 h = reinterpret_cast<const float4*>(b1)[lane];
-  for (int f = 0; f < F; ++f) {
-    const float x = tval[row * F + f];
-    if (x != 0.f) {
-      const float4 w = reinterpret_cast<const float4*>(W1t + (int64_t)cols[row * F + f] * kAG)[lane];
-      h.x = fmaf(x, w.x, h.x); h.y = fmaf(x, w.y, h.y); h.z = fmaf(x, w.z, h.z); h.w = fmaf(x, w.w, h.w);
+  float4 h1 = make_float4(0.f, 0.f, 0.f, 0.f), h2 = h1, h3 = h1;
+  for (int f0 = 0; f0 < F; f0 += 32) {
+    const int my_c = f0 + lane < F ? cols[row * F + f0 + lane] : 0;
+    const float my_x = f0 + lane < F ? tval[row * F + f0 + lane] : 0.f;
+    const int n = min(32, F - f0);
+#define RECAD_AUSH_G1(acc, q)                                                                        \
+    {                                                                                                \
+      const int c = __shfl_sync(kFull, my_c, q);                                                     \
+      const float x = __shfl_sync(kFull, my_x, q);                                                   \
+      const float4 w = reinterpret_cast<const float4*>(W1t + (int64_t)c * kAG)[lane];                \
+      acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w); \
     }
+    int q = 0;
+    for (; q + 4 <= n; q += 4) { RECAD_AUSH_G1(h, q) RECAD_AUSH_G1(h1, q + 1) RECAD_AUSH_G1(h2, q + 2) RECAD_AUSH_G1(h3, q + 3) }
+    for (; q < n; ++q) RECAD_AUSH_G1(h, q)
+#undef RECAD_AUSH_G1
   }
-  h.x = sigmoidf_(h.x); h.y = sigmoidf_(h.y); h.z = sigmoidf_(h.z); h.w = sigmoidf_(h.w);
+  h.x = sigmoidf_((h.x + h1.x) + (h2.x + h3.x)); h.y = sigmoidf_((h.y + h1.y) + (h2.y + h3.y));
+  h.z = sigmoidf_((h.z + h1.z) + (h2.z + h3.z)); h.w = sigmoidf_((h.w + h1.w) + (h2.w + h3.w));
   float sh = 0.f, rc = 0.f;
   for (int s = 0; s < S; ++s) {
     const int c = sel[s];
@@ -111,8 +123,12 @@ aush_gen_kernel(const float* __restrict__ W1t, const float* __restrict__ b1, con
 
 // ------------------------------------------------------------------------------------------
 // discriminator forward (+ backward).  Virtual rows v < nv: kTrain: v < B the real row, v >= B the fake row v - B;
-// !kTrain: fake rows only.  Block of 160 threads, thread t <-> hidden unit t; activations live in shared memory as
-// [unit][row] so that the 8 rows of a pass come out of two 128-bit broadcast loads.
+// !kTrain: fake rows only.  Block of 160 threads, thread t <-> hidden unit t, 8 rows per pass held in registers;
+// activations are exchanged through shared memory as [unit][row] (two 128-bit broadcast loads per unit).  The two
+// 150 x 152 weight matrices of a phase arrive in shared memory by bulk async copies (cp.async.bulk + mbarrier, one
+// instruction each, issued a phase ahead: the forward pair while the first layer gathers, the backward pair as soon as a
+// forward layer has released its buffer) -- forward from the transposed copies Dt (input-major), backward from D
+// (output-major), so that thread t always reads word t of a 152-float row: no bank conflicts in either direction.
 // ------------------------------------------------------------------------------------------
 struct AushBatch {
   const int32_t* cols;   // [B, F]
@@ -123,20 +139,6 @@ struct AushBatch {
   int B, F, S;
 };
 
-__device__ __forceinline__ void stage_weight(float* Ws, const float* __restrict__ W, int t) {
-  // 150 x 150 (row stride kAHP in global) -> shared with stride kAWs; 4-byte cp.async keeps every copy in flight
-  for (int idx = t; idx < kAH * kAH; idx += kAThreads) {
-    const int j = idx / kAH, k = idx - j * kAH;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Ws + j * kAWs + k);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(W + j * kAHP + k) : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void stage_wait() {
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-}
-
 __device__ __forceinline__ void load8(const float* p, float* o) {
   const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
@@ -146,13 +148,20 @@ __device__ __forceinline__ void store8(float* p, const float* o) {
   reinterpret_cast<float4*>(p)[1] = make_float4(o[4], o[5], o[6], o[7]);
 }
 
-// out[r] = bias + sum_k Ws[t][k] * act[k][r]
+__device__ __forceinline__ void bulk_g2s(float* dst, const float* src, uint32_t bytes, uint32_t bar) {
+  mbar_expect_tx(bar, bytes);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// out[r] = bias + sum_k Ws[k][t] * act[k][r]      (Ws = transposed weight, input-major)
 __device__ __forceinline__ void dense_fwd(const float* Ws, const float* act, int t, float bias, float* out) {
 #pragma unroll
   for (int r = 0; r < kAR; ++r) out[r] = bias;
-#pragma unroll 5
+#pragma unroll 6
   for (int k = 0; k < kAH; ++k) {
-    const float w = Ws[t * kAWs + k];
+    const float w = Ws[k * kAHP + t];
     float a[kAR];
     load8(act + k * kAR, a);
 #pragma unroll
@@ -160,56 +169,78 @@ __device__ __forceinline__ void dense_fwd(const float* Ws, const float* act, int
   }
 }
 
-// thread t = input unit k of the layer: gW partial[j][k] (+)= sum_r dz[j][r] a_in[k][r]; returns d a_in[k][r] = sum_j W[j][k] dz[j][r]
+// thread t = input unit k of the layer (Ws = weight, output-major): gW partial[j][k] (+)= sum_r dz[j][r] a_in[k][r];
+// returns d a_in[k][r] = sum_j W[j][k] dz[j][r]
 __device__ __forceinline__ void dense_bwd(const float* Ws, const float* dz, const float* a_in_reg, int t, float* gW, bool first,
                                           float* da) {
 #pragma unroll
   for (int r = 0; r < kAR; ++r) da[r] = 0.f;
-#pragma unroll 5
-  for (int j = 0; j < kAH; ++j) {
-    float d[kAR];
-    load8(dz + j * kAR, d);
-    const float w = Ws[j * kAWs + t];
-    float g = 0.f;
+#pragma unroll 1
+  for (int j0 = 0; j0 < kAH; j0 += 10) {
+    float old[10];
 #pragma unroll
-    for (int r = 0; r < kAR; ++r) {
-      g = fmaf(d[r], a_in_reg[r], g);
-      da[r] = fmaf(w, d[r], da[r]);
+    for (int q = 0; q < 10; ++q) old[q] = first ? 0.f : gW[(j0 + q) * kAHP + t];
+#pragma unroll
+    for (int q = 0; q < 10; ++q) {
+      float d[kAR];
+      load8(dz + (j0 + q) * kAR, d);
+      const float w = Ws[(j0 + q) * kAHP + t];
+      float g = 0.f;
+#pragma unroll
+      for (int r = 0; r < kAR; ++r) {
+        g = fmaf(d[r], a_in_reg[r], g);
+        da[r] = fmaf(w, d[r], da[r]);
+      }
+      gW[(j0 + q) * kAHP + t] = old[q] + g;
     }
-    float* dst = gW + j * kAHP + t;
-    *dst = first ? g : *dst + g;
   }
 }
 
 template <bool kTrain>
-__global__ void __launch_bounds__(kAThreads, 1)
-aush_disc_kernel(const float* __restrict__ Dp, AushLayout lay, AushBatch bt, int nv, float inv_B, float* __restrict__ bce0,
-                 float* __restrict__ bce1, float* __restrict__ dz1g, float* __restrict__ partial, int64_t partial_stride) {
+__global__ void __launch_bounds__(kAThreads)
+aush_disc_kernel(const float* __restrict__ Dp, const float* __restrict__ Dt, AushLayout lay, AushBatch bt, int nv, float inv_B,
+                 float* __restrict__ bce0, float* __restrict__ bce1, float* __restrict__ dz1g, float* __restrict__ partial,
+                 int64_t partial_stride) {
   extern __shared__ __align__(16) float smem[];
-  float* Ws = smem;                                   // [150][151]
-  float* a1 = Ws + ((kAH * kAWs + 3) / 4) * 4;        // [152][8] each
+  float* WA = smem;                                   // [150][152] each
+  float* WB = WA + kAH * kAHP;
+  float* a1 = WB + kAH * kAHP;                        // [152][8] each
   float* a2 = a1 + kAHP * kAR;
-  float* a3 = a2 + kAHP * kAR;
-  float* dzA = a3 + kAHP * kAR;
+  float* dzA = a2 + kAHP * kAR;
   float* dzB = dzA + kAHP * kAR;
-  float* red = dzB + kAHP * kAR;                      // [5 warps][8] + p[8] + dz4[8]
+  float* red = dzB + kAHP * kAR;                      // [5 warps][8] + dz4[8]
   const int E = bt.F + bt.S;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 56);
   int32_t* ec = reinterpret_cast<int32_t*>(red + 64);  // [8][E]
   float* ev = reinterpret_cast<float*>(ec + kAR * E);  // [8][E]
+  const uint32_t barA = smem_u32(bars), barB = smem_u32(bars + 1);
+  constexpr uint32_t kWBytes = kAH * kAHP * sizeof(float);
+  uint32_t phA = 0, phB = 0;
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const bool unit = t < kAH;
   const float* W1t = Dp + lay.W1t;
-  float* gp = kTrain ? partial + (int64_t)blockIdx.x * partial_stride : nullptr;   // layout = Dp + lay.b1 onwards
+  const float* W2t = Dt;
+  const float* W3t = Dt + kAH * kAHP;
+  float* gp = kTrain ? partial + (int64_t)blockIdx.x * partial_stride : nullptr;   // layout = Dp + lay.b1 onwards, then [S][152]
   const int64_t o_b1 = 0, o_W2 = lay.W2 - lay.b1, o_b2 = lay.b2 - lay.b1, o_W3 = lay.W3 - lay.b1, o_b3 = lay.b3 - lay.b1,
-                o_w4 = lay.w4 - lay.b1, o_b4 = lay.b4 - lay.b1;
+                o_w4 = lay.w4 - lay.b1, o_b4 = lay.b4 - lay.b1, o_sel = lay.total - lay.b1;
   const float b1 = t < kAHP ? Dp[lay.b1 + t] : 0.f, b2 = t < kAHP ? Dp[lay.b2 + t] : 0.f, b3 = t < kAHP ? Dp[lay.b3 + t] : 0.f;
   const float w4 = t < kAHP ? Dp[lay.w4 + t] : 0.f, b4 = Dp[lay.b4];
+  const int tc = unit ? t : 0;                        // pad threads read a valid column and discard the result
   bool first = true;
+  if (t == 0) {
+    mbar_init(barA, 1);
+    mbar_init(barB, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
 
   for (int g0 = blockIdx.x * kAR; g0 < nv; g0 += gridDim.x * kAR) {
     __syncthreads();
-    stage_weight(Ws, Dp + lay.W2, t);
+    if (t == 0 && (kTrain || first)) {                // forward pair (the forward-only kernel keeps it for every pass)
+      bulk_g2s(WA, W2t, kWBytes, barA);
+      bulk_g2s(WB, W3t, kWBytes, barB);
+    }
     // the pass's sparse inputs -> shared
     for (int idx = t; idx < kAR * E; idx += kAThreads) {
       const int r = idx / E, e = idx - r * E, v = g0 + r;
@@ -225,41 +256,50 @@ aush_disc_kernel(const float* __restrict__ Dp, AushLayout lay, AushBatch bt, int
       ev[idx] = x;
     }
     __syncthreads();
-    // layer 1: gather-sum of W1^T rows
+    // layer 1: gather-sum of W1^T rows (a zero-valued entry points at column 0: the load is harmless, its weight is 0)
     float acc[kAR], av1[kAR], av2[kAR], av3[kAR];
+    {
+      float s0[kAR], s1[kAR];
 #pragma unroll
-    for (int r = 0; r < kAR; ++r) acc[r] = b1;
-    if (t < kAHP) {
+      for (int r = 0; r < kAR; ++r) s0[r] = s1[r] = 0.f;
+      int e = 0;
+      for (; e + 4 <= E; e += 4) {                      // 32 independent gathers per step
+        float w[kAR][4];
 #pragma unroll
-      for (int r = 0; r < kAR; ++r) {
-        float s0 = 0.f, s1 = 0.f;
-        int e = 0;
-        for (; e + 1 < E; e += 2) {
-          const float x0 = ev[r * E + e], x1 = ev[r * E + e + 1];
-          const float w0 = x0 != 0.f ? W1t[(int64_t)ec[r * E + e] * kAHP + t] : 0.f;
-          const float w1 = x1 != 0.f ? W1t[(int64_t)ec[r * E + e + 1] * kAHP + t] : 0.f;
-          s0 = fmaf(x0, w0, s0);
-          s1 = fmaf(x1, w1, s1);
+        for (int r = 0; r < kAR; ++r)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) w[r][q] = __ldg(W1t + (int64_t)ec[r * E + e + q] * kAHP + tc);
+#pragma unroll
+        for (int r = 0; r < kAR; ++r) {
+          s0[r] = fmaf(ev[r * E + e], w[r][0], s0[r]);
+          s1[r] = fmaf(ev[r * E + e + 1], w[r][1], s1[r]);
+          s0[r] = fmaf(ev[r * E + e + 2], w[r][2], s0[r]);
+          s1[r] = fmaf(ev[r * E + e + 3], w[r][3], s1[r]);
         }
-        if (e < E) {
-          const float x0 = ev[r * E + e];
-          if (x0 != 0.f) s0 = fmaf(x0, W1t[(int64_t)ec[r * E + e] * kAHP + t], s0);
-        }
-        acc[r] += s0 + s1;
       }
+      for (; e < E; ++e) {
+        float w[kAR];
+#pragma unroll
+        for (int r = 0; r < kAR; ++r) w[r] = __ldg(W1t + (int64_t)ec[r * E + e] * kAHP + tc);
+#pragma unroll
+        for (int r = 0; r < kAR; ++r) s0[r] = fmaf(ev[r * E + e], w[r], s0[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < kAR; ++r) acc[r] = b1 + (s0[r] + s1[r]);
     }
 #pragma unroll
     for (int r = 0; r < kAR; ++r) av1[r] = unit ? sigmoidf_(acc[r]) : 0.f;
     if (t < kAHP) store8(a1 + t * kAR, av1);
-    stage_wait();                                      // W2 staged, a1 visible
-    if (unit) dense_fwd(Ws, a1, t, b2, acc);
+    __syncthreads();
+    if (kTrain || first) { mbar_wait(barA, phA); phA ^= 1; }
+    dense_fwd(WA, a1, tc, b2, acc);
 #pragma unroll
     for (int r = 0; r < kAR; ++r) av2[r] = unit ? sigmoidf_(acc[r]) : 0.f;
     if (t < kAHP) store8(a2 + t * kAR, av2);
-    __syncthreads();
-    stage_weight(Ws, Dp + lay.W3, t);
-    stage_wait();
-    if (unit) dense_fwd(Ws, a2, t, b3, acc);
+    __syncthreads();                                   // a2 visible; WA released
+    if (kTrain && t == 0) bulk_g2s(WA, Dp + lay.W3, kWBytes, barA);
+    if (kTrain || first) { mbar_wait(barB, phB); phB ^= 1; }
+    dense_fwd(WB, a2, tc, b3, acc);
 #pragma unroll
     for (int r = 0; r < kAR; ++r) av3[r] = unit ? sigmoidf_(acc[r]) : 0.f;
     // output unit: z4[r] = b4 + sum_j w4[j] a3[j][r]
@@ -268,7 +308,9 @@ aush_disc_kernel(const float* __restrict__ Dp, AushLayout lay, AushBatch bt, int
       const float s = warp_sum(w4 * av3[r]);
       if (lane == 0) red[warp * kAR + r] = s;
     }
-    __syncthreads();
+    __syncthreads();                                   // WB released
+    if (kTrain && t == 0) bulk_g2s(WB, Dp + lay.W2, kWBytes, barB);
+    if (!kTrain) first = false;
     if (t < kAR) {
       float z = b4;
       for (int w = 0; w < kAThreads / 32; ++w) z += red[w * kAR + t];
@@ -306,9 +348,10 @@ aush_disc_kernel(const float* __restrict__ Dp, AushLayout lay, AushBatch bt, int
       if (t == 0) gp[o_b4] = first ? gb4 : gp[o_b4] + gb4;
     }
     __syncthreads();
-    // layer 3 (Ws = W3): weight gradient against a2, d a2
+    // layer 3: weight gradient against a2, d a2
     float d2[kAR], gb = 0.f;
-    if (unit) dense_bwd(Ws, dzA, av2, t, gp + o_W3, first, da);
+    mbar_wait(barA, phA); phA ^= 1;
+    if (unit) dense_bwd(WA, dzA, av2, t, gp + o_W3, first, da);
 #pragma unroll
     for (int r = 0; r < kAR; ++r) { d2[r] = unit ? da[r] * (av2[r] * (1.f - av2[r])) : 0.f; gb += d2[r]; }
     if (t < kAHP) {
@@ -316,11 +359,10 @@ aush_disc_kernel(const float* __restrict__ Dp, AushLayout lay, AushBatch bt, int
       gp[o_b2 + t] = first ? gb : gp[o_b2 + t] + gb;
     }
     __syncthreads();
-    stage_weight(Ws, Dp + lay.W2, t);
-    stage_wait();
     float d1[kAR];
     gb = 0.f;
-    if (unit) dense_bwd(Ws, dzB, av1, t, gp + o_W2, first, da);
+    mbar_wait(barB, phB); phB ^= 1;
+    if (unit) dense_bwd(WB, dzB, av1, t, gp + o_W2, first, da);
 #pragma unroll
     for (int r = 0; r < kAR; ++r) { d1[r] = unit ? da[r] * (av1[r] * (1.f - av1[r])) : 0.f; gb += d1[r]; }
     if (t < kAHP) {
@@ -328,45 +370,85 @@ aush_disc_kernel(const float* __restrict__ Dp, AushLayout lay, AushBatch bt, int
 #pragma unroll
       for (int r = 0; r < kAR; ++r)
         if (g0 + r < nv) dz1g[(int64_t)(g0 + r) * kAHP + t] = d1[r];
+      // the selected columns are dense (every row holds them): their first-layer gradient rows are block partials too
+      for (int s = 0; s < bt.S; ++s) {
+        float g = 0.f;
+#pragma unroll
+        for (int r = 0; r < kAR; ++r) g = fmaf(ev[r * E + bt.F + s], d1[r], g);
+        gp[o_sel + s * kAHP + t] = first ? g : gp[o_sel + s * kAHP + t] + g;
+      }
     }
     first = false;
   }
 }
 
-// first-layer gradient from the batch's column index, fused with the dense Adam update of W1^T (one block per item row)
+// first-layer gradient from the batch's column index (filler entries) or the block partials (selected columns), fused with
+// the dense Adam update of W1^T (one block per item row)
 __global__ void __launch_bounds__(kAThreads)
 aush_adam_w1_kernel(float* __restrict__ P, float* __restrict__ M, float* __restrict__ V, const int32_t* __restrict__ colptr,
-                    const int32_t* __restrict__ ent, AushBatch bt, const float* __restrict__ dz1g, AdamScalars a) {
+                    const int32_t* __restrict__ ent, AushBatch bt, const float* __restrict__ dz1g, const float* __restrict__ partial,
+                    int64_t partial_stride, int64_t o_sel, int n_blocks, AdamScalars a) {
   const int c = blockIdx.x, t = threadIdx.x;
   if (t >= kAHP) return;
-  const int E = bt.F + bt.S;
-  float g = 0.f;
-  for (int q = colptr[c]; q < colptr[c + 1]; ++q) {
-    const int code = ent[q], r = code / E, e = code - r * E;
-    const float dr = dz1g[(int64_t)r * kAHP + t], df = dz1g[(int64_t)(bt.B + r) * kAHP + t];
-    if (e < bt.F) {
-      g = fmaf(bt.dval[(int64_t)r * bt.F + e], dr + df, g);
-    } else {
-      g = fmaf(bt.rsel[(int64_t)r * bt.S + e - bt.F], dr, g);
-      g = fmaf(bt.fin[(int64_t)r * bt.S + e - bt.F], df, g);
-    }
+  float g0 = 0.f, g1 = 0.f;
+  const int beg = colptr[c], end = colptr[c + 1];
+  int q = beg;
+  for (; q + 2 <= end; q += 2) {
+    const int c0 = ent[q], c1 = ent[q + 1], r0 = c0 / bt.F, r1 = c1 / bt.F;
+    const float x0 = bt.dval[c0], x1 = bt.dval[c1];                       // ent = row * F + slot indexes dval directly
+    const float d0 = dz1g[(int64_t)r0 * kAHP + t] + dz1g[(int64_t)(bt.B + r0) * kAHP + t];
+    const float d1 = dz1g[(int64_t)r1 * kAHP + t] + dz1g[(int64_t)(bt.B + r1) * kAHP + t];
+    g0 = fmaf(x0, d0, g0);
+    g1 = fmaf(x1, d1, g1);
   }
+  if (q < end) {
+    const int c0 = ent[q], r0 = c0 / bt.F;
+    g0 = fmaf(bt.dval[c0], dz1g[(int64_t)r0 * kAHP + t] + dz1g[(int64_t)(bt.B + r0) * kAHP + t], g0);
+  }
+  float g = g0 + g1;
+  for (int s = 0; s < bt.S; ++s)
+    if (bt.sel[s] == c) {
+      float gs = 0.f;
+      for (int b = 0; b < n_blocks; ++b) gs += partial[(int64_t)b * partial_stride + o_sel + s * kAHP + t];
+      g += gs;
+    }
   const int64_t i = (int64_t)c * kAHP + t;
   float p = P[i], m = M[i], v = V[i];
   adam1(p, g, m, v, a);
   P[i] = p; M[i] = m; V[i] = v;
 }
 
+// the other parameters: block partials summed in block order + Adam; the two 150 x 150 matrices also refresh their
+// transposed copies (Dt) for the next forward
 __global__ void __launch_bounds__(256)
 aush_adam_small_kernel(float* __restrict__ P, float* __restrict__ M, float* __restrict__ V, const float* __restrict__ partial,
-                       int64_t partial_stride, int n_blocks, int64_t n, AdamScalars a) {
+                       int64_t partial_stride, int n_blocks, int64_t n, int64_t o_W2, int64_t o_W3, int64_t o_b4,
+                       float* __restrict__ Dt, AdamScalars a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float g = 0.f;
-  for (int b = 0; b < n_blocks; ++b) g += partial[(int64_t)b * partial_stride + i];
+  if (i >= n || i > o_b4) return;                                                  // the floats after main.6.bias are padding
+  const int64_t w = i >= o_W3 ? i - o_W3 : i - o_W2;
+  const bool mat = i >= o_W2 && w < (int64_t)kAH * kAHP;
+  const int j = mat ? (int)(w / kAHP) : 0, k = mat ? (int)(w - (int64_t)j * kAHP) : 0;
+  if (k >= kAH) return;                                                            // row padding: stays zero
+  float g0 = 0.f, g1 = 0.f;
+  int b = 0;
+  for (; b + 2 <= n_blocks; b += 2) {
+    g0 += partial[(int64_t)b * partial_stride + i];
+    g1 += partial[(int64_t)(b + 1) * partial_stride + i];
+  }
+  if (b < n_blocks) g0 += partial[(int64_t)b * partial_stride + i];
   float p = P[i], m = M[i], v = V[i];
-  adam1(p, g, m, v, a);
+  adam1(p, g0 + g1, m, v, a);
   P[i] = p; M[i] = m; V[i] = v;
+  if (mat) Dt[(i >= o_W3 ? kAH * kAHP : 0) + k * kAHP + j] = p;
+}
+
+// Dt = transposed copies of main.2.weight and main.4.weight (start of an epoch: the parameters may have been loaded)
+__global__ void aush_transpose_kernel(const float* __restrict__ Dp, AushLayout lay, float* __restrict__ Dt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * kAH * kAHP) return;
+  const int l = i / (kAH * kAHP), w = i - l * kAH * kAHP, k = w / kAHP, j = w - k * kAHP;
+  Dt[i] = j < kAH ? Dp[(l ? lay.W3 : lay.W2) + (int64_t)j * kAHP + k] : 0.f;
 }
 
 // the four values train_step returns (aush.py:171-176): means over the batches of per-batch means
@@ -405,9 +487,8 @@ aush_loss_kernel(const float* __restrict__ bce_real, const float* __restrict__ b
     for (int q = 0; q < 4; ++q) out[q] = nb ? tot[q] / (double)nb : nan("");
 }
 
-static size_t disc_smem(int E) {
-  return sizeof(float) * (size_t)(((kAH * kAWs + 3) / 4) * 4 + 5 * kAHP * kAR + 64) + (size_t)kAR * E * 8;
-}
+static size_t disc_smem(int E) { return sizeof(float) * (size_t)(2 * kAH * kAHP + 4 * kAHP * kAR + 64) + (size_t)kAR * E * 8; }
+static int64_t aush_small(const AushLayout& o, int S) { return o.total - o.b1 + (int64_t)S * kAHP; }   // floats of one block partial
 
 }  // namespace recad
 
@@ -425,15 +506,14 @@ int recad_aush_d_layout(int64_t n_items, int64_t* offsets) {
 
 int64_t recad_aush_work_floats(int64_t n_items, int64_t n_rows, int32_t batch, int32_t n_sel) {
   const AushLayout o = aush_layout(n_items);
-  const int64_t small = o.total - o.b1;
-  return 5 * n_rows + (int64_t)batch * std::max(n_sel, 1) + 8 + 2 * (int64_t)batch * kAHP + (int64_t)sm_count() * small;
+  return 5 * n_rows + (int64_t)batch * std::max(n_sel, 1) + 8 + 2 * (int64_t)batch * kAHP + 2 * kAH * kAHP +
+         (int64_t)2 * sm_count() * aush_small(o, n_sel);
 }
 
-int recad_aush_plan_columns(const int32_t* cols, int64_t n_rows, int32_t batch, int32_t F, const int32_t* selected, int32_t S,
-                            int64_t n_items, int32_t* colptr, int32_t* ent) {
-  RECAD_REQUIRE(cols && selected && colptr && ent && n_rows >= 0 && batch > 0 && F >= 0 && S >= 0 && n_items > 0, RECAD_ERR_ARG,
+int recad_aush_plan_columns(const int32_t* cols, int64_t n_rows, int32_t batch, int32_t F, int64_t n_items, int32_t* colptr,
+                            int32_t* ent) {
+  RECAD_REQUIRE(cols && colptr && ent && n_rows >= 0 && batch > 0 && F >= 0 && n_items > 0, RECAD_ERR_ARG,
                 "aush_plan_columns: bad argument");
-  const int E = F + S;
   const int64_t nb = (n_rows + batch - 1) / batch;
   std::vector<int32_t> cur((size_t)n_items + 1);
   for (int64_t k = 0; k < nb; ++k) {
@@ -446,16 +526,12 @@ int recad_aush_plan_columns(const int32_t* cols, int64_t n_rows, int32_t batch, 
         RECAD_REQUIRE(c >= 0 && c < n_items, RECAD_ERR_ARG, "aush_plan_columns: column %d out of range", c);
         ++cp[c + 1];
       }
-      for (int s = 0; s < S; ++s) ++cp[selected[s] + 1];
     }
     for (int64_t c = 0; c < n_items; ++c) cp[c + 1] += cp[c];
     std::copy(cp, cp + n_items, cur.begin());
-    int32_t* out = ent + lo * E;
+    int32_t* out = ent + lo * F;
     for (int64_t r = 0; r < Bk; ++r)
-      for (int e = 0; e < E; ++e) {
-        const int32_t c = e < F ? cols[(lo + r) * F + e] : selected[e - F];
-        out[cur[c]++] = (int32_t)(r * E + e);
-      }
+      for (int e = 0; e < F; ++e) out[cur[cols[(lo + r) * F + e]]++] = (int32_t)(r * F + e);
   }
   return RECAD_OK;
 }
@@ -490,7 +566,8 @@ int recad_aush_train_epoch(const recad_aush* st, const recad_aush_epoch* ep, int
   RECAD_REQUIRE(n == 0 || (ep->cols && ep->tval && ep->dval && ep->rsel && ep->tsel && ep->msel && ep->zr && ep->colptr && ep->ent),
                 RECAD_ERR_ARG, "aush_train_epoch: missing epoch array");
   const AushLayout lay = aush_layout(I);
-  const int64_t small = lay.total - lay.b1;
+  const int64_t small = aush_small(lay, S), n_adam = lay.total - lay.b1;
+  const int sms = sm_count();
   float* w = st->work;
   float* bce_real = w; w += n;
   float* bce_fake = w; w += n;
@@ -498,18 +575,23 @@ int recad_aush_train_epoch(const recad_aush* st, const recad_aush_epoch* ep, int
   float* shil = w; w += n;
   float* rec = w; w += n;
   float* fin = w; w += (int64_t)batch * std::max(S, 1);
+  w += (4 - ((w - st->work) & 3)) & 3;
   float* dz1 = w; w += 2 * (int64_t)batch * kAHP;
-  float* partial = w;
+  float* Dt = w; w += 2 * kAH * kAHP;
+  float* partial = w;                                 // [<= 2 * sms][small]
   const size_t smem = disc_smem(E);
-  RECAD_REQUIRE(smem <= 220 * 1024, RECAD_ERR_ARG, "aush_train_epoch: filler_num + |selected| = %d is too large", E);
+  RECAD_REQUIRE(smem <= 226 * 1024, RECAD_ERR_ARG, "aush_train_epoch: filler_num + |selected| = %d is too large", E);
   static bool attr = false;
   if (!attr) {
-    RECAD_CUDA_CHECK(cudaFuncSetAttribute(aush_disc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    RECAD_CUDA_CHECK(cudaFuncSetAttribute(aush_disc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    RECAD_CUDA_CHECK(cudaFuncSetAttribute(aush_disc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    RECAD_CUDA_CHECK(cudaFuncSetAttribute(aush_disc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr = true;
   }
-  const int sms = sm_count();
   const int64_t nb = (n + batch - 1) / batch;
+  if (nb) {
+    aush_transpose_kernel<<<(2 * kAH * kAHP + 255) / 256, 256, 0, s>>>(st->D, lay, Dt);
+    RECAD_LAUNCH_CHECK();
+  }
   for (int64_t k = 0; k < nb; ++k) {
     const int64_t lo = k * batch;
     const int B = (int)std::min<int64_t>(batch, n - lo);
@@ -519,17 +601,19 @@ int recad_aush_train_epoch(const recad_aush* st, const recad_aush_epoch* ep, int
                                                              B, nullptr, fin, shil + lo, rec + lo);
     RECAD_LAUNCH_CHECK();
     const int g_train = std::min(sms, (2 * B + kAR - 1) / kAR), g_fwd = std::min(sms, (B + kAR - 1) / kAR);
-    aush_disc_kernel<true><<<g_train, kAThreads, smem, s>>>(st->D, lay, bt, 2 * B, 1.f / (float)B, bce_real + lo, bce_fake + lo, dz1,
-                                                            partial, small);
+    aush_disc_kernel<true><<<g_train, kAThreads, smem, s>>>(st->D, Dt, lay, bt, 2 * B, 1.f / (float)B, bce_real + lo, bce_fake + lo,
+                                                            dz1, partial, small);
     RECAD_LAUNCH_CHECK();
     const AdamScalars a = adam_scalars(st->lr, st->beta1, st->beta2, st->eps, step0 + k + 1);
     aush_adam_w1_kernel<<<(unsigned)I, kAThreads, 0, s>>>(st->D + lay.W1t, st->Dm + lay.W1t, st->Dv + lay.W1t,
-                                                          ep->colptr + k * (I + 1), ep->ent + lo * E, bt, dz1, a);
+                                                          ep->colptr + k * (I + 1), ep->ent + lo * F, bt, dz1, partial, small,
+                                                          n_adam, g_train, a);
     RECAD_LAUNCH_CHECK();
-    aush_adam_small_kernel<<<(unsigned)((small + 255) / 256), 256, 0, s>>>(st->D + lay.b1, st->Dm + lay.b1, st->Dv + lay.b1, partial,
-                                                                            small, g_train, small, a);
+    aush_adam_small_kernel<<<(unsigned)((n_adam + 255) / 256), 256, 0, s>>>(st->D + lay.b1, st->Dm + lay.b1, st->Dv + lay.b1, partial,
+                                                                             small, g_train, n_adam, lay.W2 - lay.b1, lay.W3 - lay.b1,
+                                                                             lay.b4 - lay.b1, Dt, a);
     RECAD_LAUNCH_CHECK();
-    aush_disc_kernel<false><<<g_fwd, kAThreads, smem, s>>>(st->D, lay, bt, B, 1.f / (float)B, bce_gan + lo, nullptr, nullptr, nullptr, 0);
+    aush_disc_kernel<false><<<g_fwd, kAThreads, smem, s>>>(st->D, Dt, lay, bt, B, 1.f / (float)B, bce_gan + lo, nullptr, nullptr, nullptr, 0);
     RECAD_LAUNCH_CHECK();
   }
   aush_loss_kernel<<<1, 256, 0, s>>>(bce_real, bce_fake, bce_gan, shil, rec, n, batch, I, loss_out);

@@ -1288,8 +1288,8 @@ int recad_permutation_apply(int64_t n, const uint32_t* j, int64_t* perm) {
 // (row, selected column) pairs with real == 0 in row-major order, aush.py:113-117); the first floor(P * (1 - ZR_ratio))
 // pairs of the shuffled pool leave the mask.
 int recad_mt19937_aush_batch(uint32_t* key, int32_t* pos, int64_t B, const int64_t* users, const int64_t* cand_ptr,
-                             const int32_t* cand_items, int32_t F, int32_t S, const uint8_t* zero_sel, double zr_ratio,
-                             int32_t* cols_out, float* zr_out) {
+                             const int32_t* cand_items, const float* cand_vals, int32_t F, int32_t S, const uint8_t* zero_sel,
+                             double zr_ratio, int32_t* cols_out, float* tval_out, float* zr_out) {
   if (!key || !pos || B < 0 || F < 0 || S < 0 || (B && (!users || !cand_ptr || !cand_items || !cols_out)) || (B && S && (!zero_sel || !zr_out))) {
     recad::set_error("mt19937_aush_batch: bad argument");
     return RECAD_ERR_ARG;
@@ -1302,7 +1302,16 @@ int recad_mt19937_aush_batch(uint32_t* key, int32_t* pos, int64_t B, const int64
       return RECAD_ERR_ARG;
     }
     const uint32_t r = (uint32_t)(len - 1), mask = MT::mask_of(r);
-    for (int f = 0; f < F; ++f) cols_out[b * F + f] = cand_items[lo + (r ? mt.masked_with(r, mask) : 0u)];
+    for (int f = 0; f < F; ++f) {
+      const int64_t at = lo + (r ? mt.masked_with(r, mask) : 0u);
+      const int32_t c = cand_items[at];
+      cols_out[b * F + f] = c;
+      if (tval_out && cand_vals) {            // input_template carries a rating once per distinct column: a repeat adds 0
+        bool seen = false;
+        for (int g = 0; g < f; ++g) seen |= cols_out[b * F + g] == c;
+        tval_out[b * F + f] = seen ? 0.f : cand_vals[at];
+      }
+    }
   }
   std::vector<int64_t> pool;
   for (int64_t q = 0; q < B * S; ++q) {

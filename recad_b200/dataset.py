@@ -683,7 +683,9 @@ class ArrayImplicitData:
         return infos
 
 
-factories = {"implicit": ImplicitData}    # recad/dataset/__init__.py:13
+from .explicit import ExplicitData  # noqa: E402
+
+factories = {"implicit": ImplicitData, "explicit": ExplicitData}    # recad/dataset/__init__.py:13
 
 
 def from_config(scope, *args, **kwargs):

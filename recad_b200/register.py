@@ -2,8 +2,8 @@
 registries -- no reference file is edited:
 
     import recad, recad_b200.register
-    recad_b200.register.install()            # adds 'lightgcn_b200', 'mf_b200', 'ncf_b200', attacker 'aush_b200', dataset 'implicit_b200'
-    recad_b200.register.install(override=True)   # ALSO rebinds 'lightgcn'/'mf'/'ncf'/'aush'/'implicit' and the evaluator,
+    recad_b200.register.install()            # adds 'lightgcn_b200', 'mf_b200', 'ncf_b200', attacker 'aush_b200', datasets 'implicit_b200' / 'explicit_b200'
+    recad_b200.register.install(override=True)   # ALSO rebinds 'lightgcn'/'mf'/'ncf'/'aush'/'implicit'/'explicit' and the evaluator,
                                                  # so an unmodified `recad_runner ...` runs on the CUDA kernels
 
 Registries touched: recad.model.factories['victim'] / ['attacker'] (recad/model/__init__.py:3-18),
@@ -31,9 +31,12 @@ def install(override=False):
     for key in (["aush_b200", "aush"] if override else ["aush_b200"]):
         ref_model.factories["attacker"][key] = Aush
         ref_default.MODEL["attacker"].setdefault(key, dict(MODEL["attacker"]["aush"]))
+    from .explicit import ExplicitData
     ref_dataset.factories["implicit_b200"] = ImplicitData
+    ref_dataset.factories["explicit_b200"] = ExplicitData
     if override:
         ref_dataset.factories["implicit"] = ImplicitData
+        ref_dataset.factories["explicit"] = ExplicitData
 
         def _normal_evaluate(self, model, model_fake, dataset, target_id_list, topks):
             return evaluate.normal_evaluate(model, model_fake, dataset, target_id_list, topks)

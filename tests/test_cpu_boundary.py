@@ -54,8 +54,8 @@ def test_host_error_paths_report_through_last_error():
     assert lib.recad_mt19937_permutation_draw(None, None, 5, None) < 0 and b"permutation_draw" in lib.recad_last_error()
     assert lib.recad_permutation_apply(5, None, None) < 0 and b"permutation_apply" in lib.recad_last_error()
     assert lib.recad_aush_train_epoch(None, None, 0, None, None) < 0 and b"aush_train_epoch" in lib.recad_last_error()
-    assert lib.recad_aush_generate(None, None, None, 4, None, None) < 0 and lib.recad_aush_plan_columns(None, 4, 2, 3, None, 1, 10, None, None) < 0
-    assert lib.recad_mt19937_aush_batch(None, None, 4, None, None, None, 3, 1, None, 0.2, None, None) < 0
+    assert lib.recad_aush_generate(None, None, None, 4, None, None) < 0 and lib.recad_aush_plan_columns(None, 4, 2, 3, 10, None, None) < 0
+    assert lib.recad_mt19937_aush_batch(None, None, 4, None, None, None, None, 3, 1, None, 0.2, None, None, None) < 0
     assert lib.recad_fullrank_eval_tc(None, None, 10, 64, None, 4, None, None, None, 0, 20, None, None, None, None, None, None, 0,
                                       None) < 0 and b"fullrank_tc" in lib.recad_last_error()
 
@@ -508,13 +508,12 @@ def test_aush_host_draws_and_column_plan_match_the_oracle():
     zr = oa.draw_zr(real, sel, a.ZR_ratio)
     after = np.random.get_state()
     np.random.set_state(st)
-    cols, zr2 = a._draw_batch(users, targets)
+    cols, tval, zr2 = a._draw_batch(users, targets)
     mine = np.random.get_state()
     assert np.array_equal(after[1], mine[1]) and after[2] == mine[2]
     f2 = np.zeros_like(fill)
     f2[np.arange(len(users))[:, None], cols] = 1
     assert np.array_equal(fill, f2) and np.array_equal(zr[:, a._sel], zr2)
-    tval = a._template(users, cols)
     dense = np.zeros_like(fill)
     np.add.at(dense, (np.arange(len(users))[:, None], cols), tval)           # repeats carry 0: the sum IS the template
     assert np.array_equal(dense, real * fill)
@@ -522,13 +521,31 @@ def test_aush_host_draws_and_column_plan_match_the_oracle():
     F, S, I, n = a.filler_num, len(a._sel), a.n_items, len(users)
     b2 = 64
     nb = (n + b2 - 1) // b2
-    colptr, ent = np.empty((nb, I + 1), dtype=np.int32), np.empty(n * (F + S), dtype=np.int32)
-    sel32 = a._sel.astype(np.int32)
+    colptr, ent = np.empty((nb, I + 1), dtype=np.int32), np.empty(n * F, dtype=np.int32)
     vp = lambda x: C.c_void_p(x.ctypes.data)
-    _lib.check(_lib.lib().recad_aush_plan_columns(vp(cols), n, b2, F, vp(sel32), S, I, vp(colptr), vp(ent)), "plan")
+    _lib.check(_lib.lib().recad_aush_plan_columns(vp(cols), n, b2, F, I, vp(colptr), vp(ent)), "plan")
     for k in range(nb):
         lo, hi = k * b2, min(n, (k + 1) * b2)
-        allc = np.concatenate([cols[lo:hi], np.broadcast_to(sel32, (hi - lo, S))], 1)
-        order = np.argsort(allc.ravel(), kind="stable")
-        assert np.array_equal(ent[lo * (F + S):hi * (F + S)], order)
-        assert np.array_equal(colptr[k], np.concatenate([[0], np.cumsum(np.bincount(allc.ravel(), minlength=I))]))
+        order = np.argsort(cols[lo:hi].ravel(), kind="stable")
+        assert np.array_equal(ent[lo * F:hi * F], order)
+        assert np.array_equal(colptr[k], np.concatenate([[0], np.cumsum(np.bincount(cols[lo:hi].ravel(), minlength=I))]))
+
+
+def test_explicit_dataset_batches_are_lazy_and_sum_repeated_rows():
+    """explicit.py:110-119 builds the rating matrix with scipy's csr (repeated (user, item) rows add up); the batch dict
+    makes `users_mat` only when a consumer asks for it."""
+    from recad_b200 import explicit
+    ex = util.load("dev_explicit.npz")
+    d = explicit.ExplicitData.from_config("dev", device=CPU, train_dict=ex["train"].copy(), valid_dict=ex["valid"].copy(),
+                                          test_dict=ex["test"].copy())
+    assert (d.n_users, d.n_items) == (int(ex["n_users"]), int(ex["n_items"]))
+    kvr = np.array([[0, 1, 3], [0, 1, 2], [2, 0, 5]], dtype=np.float64)
+    assert np.array_equal(explicit.ExplicitData.to_matrix(kvr, 3, 2), np.array([[0, 5], [0, 0], [5, 0]], dtype=np.float32))
+    np.random.seed(0)
+    batches = list(d.generate_batch())
+    assert len(batches) == (d.n_users + 255) // 256 and sum(len(b["users"]) for b in batches) == d.n_users
+    b = batches[0]
+    assert not dict.__contains__(b, "users_mat") and "users_mat" in b and set(b.keys()) == {"users", "users_mat"}
+    assert np.array_equal(b["users_mat"].numpy(), d.train_mat[b["users"].numpy()])
+    with pytest.raises(KeyError):
+        b["nope"]

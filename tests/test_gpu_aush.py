@@ -120,3 +120,26 @@ def test_aush_construction_draws_the_reference_init_stream():
         assert torch.equal(v.cpu(), D.state_dict()[k[len("main."):]])
     with pytest.raises(Exception):
         model.from_config("attacker", "aush", device=torch.device("cpu"), **kw).I(dataset=StubExplicit(mat, batch, dev))
+
+
+def test_aush_over_the_b200_explicit_dataset_matches_the_reference():
+    """Same golden run, batches from recad_b200.explicit.ExplicitData (device-side lazy `users_mat`): the epoch losses and
+    the generator state must not depend on which dataset class hands out the rows."""
+    from recad_b200 import dataset, model
+    dev = torch.device("cuda:0")
+    mat, G, D, kw, batch, targets, z = util.aush_case("b")
+    tr, te = z["train"].astype(np.float64), z["test"].astype(np.float64)
+    ds = dataset.from_config("explicit", "dev", device=dev, batch_size=batch, train_dict=tr.copy(), valid_dict=te.copy(), test_dict=te.copy())
+    assert np.array_equal(ds.train_mat, mat)
+    np.random.seed(1)
+    b0 = next(iter(ds.generate_batch()))
+    assert b0["users"].is_cuda and not dict.__contains__(b0, "users_mat")
+    assert np.array_equal(b0["users_mat"].cpu().numpy(), mat[b0["users"].cpu().numpy()])
+    att = model.from_config("attacker", "aush", device=dev, **kw).I(dataset=ds)
+    att.load_netG_state(G)
+    att.load_netD_state(D)
+    np.random.set_state(("MT19937", z["b_np_key_start"], int(z["b_np_pos_start"]), 0, 0.0))
+    for e, gold in enumerate(z["b_losses"]):
+        assert np.allclose(att.train_step(target_id_list=targets), gold, rtol=1e-4, atol=0), e
+    st = np.random.get_state()
+    assert np.array_equal(st[1], z["b_np_key_mid"]) and st[2] == int(z["b_np_pos_mid"])

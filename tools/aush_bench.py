@@ -1,8 +1,8 @@
 """AUSH attacker training at the ml1m shape (BASELINE config 2's attacker phase): `train_step` =
 one pass over the eligible users in batches of 256 (aush.py:78-180), 5 950 users x 3 702 items, ~79 ratings per user,
 filler_num 36, one selected item.  CUDA path (recad_b200/attacker.py + csrc/aush.cu) with its host / device split, next to
- * the UNMODIFIED reference class (baseline/_ref, if present) on the host cores and on the same GPU through its own
-   torch code (the GPU-library baseline), and
+ * the UNMODIFIED reference attacker on the reference's own ExplicitData (baseline/_ref, if present) on the host cores and
+   on the same GPU through its own torch code (the GPU-library baseline), and
  * the oracle's numpy restatement (bounded sample: 1 epoch).
 
     python tools/aush_bench.py [--epochs 10] [--no-ref]
@@ -18,26 +18,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from recad_b200 import model  # noqa: E402
-
-
-class Explicit:
-    """The part of recad/dataset/explicit.py an attacker touches (info_describe, train-mode generate_batch)."""
-
-    def __init__(self, mat, batch, device):
-        self.train_mat, self.batch, self.device = mat, batch, device
-        self.config = {"batch_size": batch, "device": device}
-
-    def info_describe(self):
-        return {"n_users": self.train_mat.shape[0], "n_items": self.train_mat.shape[1], "train_mat": self.train_mat}
-
-    def generate_batch(self, **config):
-        f = config.get("user_filter")
-        idx = np.random.permutation(f(train_mat=self.train_mat) if f is not None else list(range(len(self.train_mat))))
-        for b in range((len(idx) + self.batch - 1) // self.batch):
-            rows = idx[b * self.batch:(b + 1) * self.batch]
-            yield {"users": torch.tensor(rows, dtype=torch.int64).to(self.device),
-                   "users_mat": torch.tensor(self.train_mat[rows, :].astype("float"), dtype=torch.float32).to(self.device)}
+from recad_b200 import dataset, model  # noqa: E402
 
 
 def timed(fn, n):
@@ -64,14 +45,19 @@ def main():
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(0)
     mat = ((rng.random((a.users, a.items)) < 0.0213) * rng.integers(1, 6, (a.users, a.items))).astype(np.float32)
+    mat[-1, -1] = 3                                   # pins n_users / n_items of the datasets built from the rows
     targets = [0]
+    uu, ii = np.nonzero(mat)
+    kvr = np.stack([uu, ii, mat[uu, ii]], 1).astype(np.float64)
     torch.manual_seed(2023); np.random.seed(2023)
-    ds = Explicit(mat, a.batch, dev)
+    ds = dataset.from_config("explicit", "ml1m", device=dev, batch_size=a.batch, train_dict=kvr.copy(), valid_dict=kvr[:8].copy(),
+                             test_dict=kvr[:8].copy())
+    assert np.array_equal(ds.train_mat, mat)
     att = model.from_config("attacker", "aush", device=dev).I(dataset=ds)
     G0, D0 = att.netG_state(), att.netD_state()
     t_first, _ = timed(lambda: att.train_step(target_id_list=targets), 1)         # includes the one-off candidate lists
     ts, loss = timed(lambda: att.train_step(target_id_list=targets), a.epochs)
-    n_elig = len(att._eligible(mat, targets))
+    n_elig = len(att._eligible(ds.train_mat, targets))
     nb = (n_elig + a.batch - 1) // a.batch
     # device share: the epoch call alone, CUDA events on the launching stream
     import ctypes as C
@@ -104,8 +90,11 @@ def main():
             import recad
             from recad.model.attacker.aush import Aush as RefAush
             torch.set_num_threads(os.cpu_count() or 1)
+            os.chdir(__import__("tempfile").mkdtemp())
             for name, d in (("reference_cpu", torch.device("cpu")), ("reference_torch_cuda", dev)):
-                dsr = Explicit(mat, a.batch, d)
+                dsr = recad.dataset.from_config("explicit", "ml1m", device=d, download=False, batch_size=a.batch, train_dict=kvr.copy(),
+                                                valid_dict=kvr[:8].copy(), test_dict=kvr[:8].copy())
+                assert type(dsr).__module__.startswith("recad.")
                 torch.manual_seed(2023); np.random.seed(2023)
                 r = recad.model.from_config("attacker", "aush", device=d).I(dataset=dsr)
                 assert isinstance(r, RefAush) or type(r).__module__.startswith("recad.")
