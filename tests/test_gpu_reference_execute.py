@@ -56,7 +56,7 @@ def test_reference_execute_runs_on_the_cuda_path(ref_recad, victim, kw, sample):
         # the reference's own factories (recad/dataset/__init__.py:13, recad/model/__init__.py:3-21)
         "victim_data": recad.dataset.from_config("implicit", "dev", need_graph=victim == "lightgcn", sample=sample, device=dev,
                                                  train_dict=tr, valid_dict=va, test_dict=te),
-        "attack_data": recad.dataset.from_config("explicit", "dev", device=torch.device("cpu"), download=False, train_dict=ex["train"].copy(),
+        "attack_data": recad.dataset.explicit.ExplicitData.from_config("dev", device=torch.device("cpu"), download=False, train_dict=ex["train"].copy(),
                                                  valid_dict=ex["valid"].copy(), test_dict=ex["test"].copy()).partial_sample(user_ratio=0.2),
         "victim": recad.model.from_config("victim", victim, device=dev, **kw),
         "attacker": recad.model.from_config("attacker", "random", filler_num=36, device=torch.device("cpu")),
@@ -155,7 +155,7 @@ def test_reference_dataset_and_factory_drive_the_cuda_aush(ref_recad):
     mat, G, D, kw, batch, targets, z = util.aush_case("a")
     tr, te = z["train"].astype(np.float64), z["test"].astype(np.float64)
     random.seed(2023); np.random.seed(2023); torch.manual_seed(2023)
-    ds = recad.dataset.from_config("explicit", "dev", device=dev, download=False, if_cache=False, remap_enable=False, train_dict=tr.copy(),
+    ds = recad.dataset.explicit.ExplicitData.from_config("dev", device=dev, download=False, if_cache=False, remap_enable=False, train_dict=tr.copy(),
                                    valid_dict=te.copy(), test_dict=te.copy())
     assert type(ds).__module__.startswith("recad.")
     att = recad.model.from_config("attacker", "aush", device=dev).I(dataset=ds)

@@ -27,6 +27,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--rec-epoch", type=int, default=20)
     ap.add_argument("--attack-epoch", type=int, default=5)
+    ap.add_argument("--attacker", choices=["b200", "reference"], default="b200",
+                    help="b200: the registered CUDA Aush + explicit dataset; reference: the reference's own classes")
     a = ap.parse_args()
     os.chdir(tempfile.mkdtemp())                       # the reference resolves ./data and ./generated against cwd
     sys.path.insert(0, REF)
@@ -49,15 +51,19 @@ def main():
     t0 = time.time()
     victim_data = recad.dataset.from_config("implicit", "ml1m", need_graph=True, sample="pairwise", device=dev, download=False,
                                             train_dict=tr, valid_dict=va, test_dict=te, graph_edges="train")
-    attack_data = recad.dataset.from_config("explicit", "ml1m", device=dev, download=False, train_dict=ex_train,
-                                            valid_dict=kvr(va, 4), test_dict=kvr(te, 4)).partial_sample(user_ratio=0.2)
+    explicit_cls = recad.dataset.factories["explicit"] if a.attacker == "b200" else recad.dataset.explicit.ExplicitData
+    aush_cls = recad.model.factories["attacker"]["aush"] if a.attacker == "b200" else recad.model.attacker.Aush
+    attack_data = explicit_cls.from_config("ml1m", device=dev, download=False, train_dict=ex_train.astype(np.float64),
+                                           valid_dict=kvr(va, 4).astype(np.float64), test_dict=kvr(te, 4).astype(np.float64)
+                                           ).partial_sample(user_ratio=0.2)
     cfg = {"victim_data": victim_data, "attack_data": attack_data,
            "victim": recad.model.from_config("victim", "lightgcn", latent_dim_rec=64, lightGCN_n_layers=3, device=dev),
-           "attacker": recad.model.from_config("attacker", "aush", device=dev),       # the reference's own torch code, moved by execute()
+           "attacker": aush_cls.from_config(device=dev),
            "rec_epoch": a.rec_epoch, "attack_epoch": a.attack_epoch, "device": dev}
     wf = recad.workflow.from_config("no defense", **cfg)
     t_build = time.time() - t0
-    assert type(wf).__module__ == "recad.workflow.normal" and type(wf.attacker).__module__.startswith("recad.")
+    assert type(wf).__module__ == "recad.workflow.normal"
+    assert type(wf.attacker).__module__.startswith("recad." if a.attacker == "reference" else "recad_b200.")
     phases, seen = {}, {}
     nt = type(wf).normal_train
 
@@ -65,7 +71,7 @@ def main():
         torch.cuda.synchronize(); t = time.time()
         out = nt(self, **kw)
         torch.cuda.synchronize()
-        key = "attacker_train_s (reference AUSH: its own torch code + numpy masks)" if kw["model"] is self.attacker else f"victim_train_s[{len([k for k in phases if k.startswith('victim')])}]"
+        key = f"attacker_train_s ({a.attacker} AUSH)" if kw["model"] is self.attacker else f"victim_train_s[{len([k for k in phases if k.startswith('victim')])}]"
         phases[key] = round(time.time() - t, 3)
         return out
     ev = type(wf).normal_evaluate
@@ -82,7 +88,7 @@ def main():
     torch.cuda.synchronize()
     total = time.time() - t0
     print(json.dumps({"tool": "config2_execute", "workload": f"ml1m-shaped {U} x {I}, {synthetic.ML1M['train']} train interactions; LightGCN D=64 L=3, "
-                      f"rec_epoch={a.rec_epoch}, AUSH attacker (reference code, attack_epoch={a.attack_epoch}), 50 fake users",
+                      f"rec_epoch={a.rec_epoch}, AUSH attacker ({a.attacker} classes, attack_epoch={a.attack_epoch}), 50 fake users",
                       "execute_s": round(total, 3), "build_s (datasets + graph + models)": round(t_build, 3), "phases": phases,
                       "victim_epoch_s": round(phases.get("victim_train_s[0]", 0) / max(a.rec_epoch, 1), 4),
                       "table": {k: float(v) for k, v in seen["table"].items()}}))
