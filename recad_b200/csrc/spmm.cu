@@ -290,6 +290,8 @@ extern "C" int recad_spmm(const recad_csr* A, const float* X, float* Y, const fl
   const SpmmArgs a = make_args(A, X, Y, C, Z, alpha);
   const RowScatter none{};
   switch (D) {
+    case 8: return launch_spmm<8, false>(a, none, s);        // narrow tables (a column shard of D = 64 over 8 ranks)
+    case 16: return launch_spmm<16, false>(a, none, s);
     case 32: return launch_spmm<32, false>(a, none, s);
     case 64: return launch_spmm<64, false>(a, none, s);
     case 128: return launch_spmm<128, false>(a, none, s);

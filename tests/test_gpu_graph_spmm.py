@@ -137,7 +137,7 @@ def _rand_graph(U, I, E, seed, seg_len=256):
     return _build(u, i, U, I, seg_len=seg_len), og.norm_adj_csr(u, i, U, I)
 
 
-@pytest.mark.parametrize("D", [32, 64, 128, 20, 256])
+@pytest.mark.parametrize("D", [8, 16, 32, 64, 128, 20, 256])
 def test_spmm_matches_oracle(D):
     from recad_b200 import ops
     g, (ptr, col, val, _, _) = _rand_graph(700, 300, 20000, seed=D, seg_len=64)   # item rows ~67 long: multi-segment

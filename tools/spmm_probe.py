@@ -24,11 +24,12 @@ def main():
     ap.add_argument("--ncu", action="store_true")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--check", action="store_true", help="compare with torch.sparse.mm (fp64 accumulate)")
+    ap.add_argument("--dim", type=int, default=0, help="table width (default: the workload's D); 8 / 16 / 32 = a column shard")
     a = ap.parse_args()
     w = bench.WORKLOADS[a.workload]
     dev = torch.device("cuda:0")
     eu, ei = bench.synth_edges(w, dev)
-    U, I, D = w["n_users"], w["n_items"], w["D"]
+    U, I, D = w["n_users"], w["n_items"], a.dim or w["D"]
     g = ops.Graph.from_edges(eu, ei, U, I)
     del eu, ei
     N = U + I
@@ -66,7 +67,7 @@ def main():
                 run(s)
         torch.cuda.synchronize()
         return
-    out = {"workload": a.workload, "nnz": g.nnz, "n_seg": g.n_seg, "n_mrow": g.n_mrow, "n_slot": g.n_slot, "seg_len": g.seg_len,
+    out = {"workload": a.workload, "D": D, "nnz": g.nnz, "n_seg": g.n_seg, "n_mrow": g.n_mrow, "n_slot": g.n_slot, "seg_len": g.seg_len,
            "group_segs": g.plan.group_segs, "algorithmic_bytes": g.algorithmic_bytes(D) + 2 * N * 4 * D}
     for k, s in structs.items():
         out[k + "_ms"] = round(t_ms(s, a.reps), 4)
