@@ -18,6 +18,11 @@ if [ "${1:-}" = "dist" ]; then
   run dist memcheck --target-processes all --report-api-errors no python -m pytest tests/test_gpu_dist.py -x -q -k sharded
   exit 0
 fi
+if [ "${1:-}" = "aush" ]; then
+  run aush memcheck python -m pytest tests/test_gpu_aush.py -x -q -k "bit_stable or train_step"
+  run aush racecheck python -m pytest tests/test_gpu_aush.py -x -q -k "bit_stable"
+  exit 0
+fi
 run smoke memcheck python -c "import __graft_entry__ as g; g.smoke()"
 run wmf memcheck python -m pytest tests/test_gpu_wmf.py -x -q -k "unrolled or plain"
 run models memcheck python -m pytest tests/test_gpu_models.py -x -q -k "small or mf or bit_stable"
@@ -26,3 +31,5 @@ run graph memcheck python -m pytest tests/test_gpu_graph_spmm.py -x -q -k "not s
 run smoke racecheck python -c "import __graft_entry__ as g; g.smoke()"
 run wmf racecheck python -m pytest tests/test_gpu_wmf.py -x -q -k "unrolled"
 run models racecheck python -m pytest tests/test_gpu_models.py -x -q -k "small and fp32"
+run aush memcheck python -m pytest tests/test_gpu_aush.py -x -q -k "bit_stable or train_step"
+run aush racecheck python -m pytest tests/test_gpu_aush.py -x -q -k "bit_stable"
