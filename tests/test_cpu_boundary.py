@@ -549,3 +549,26 @@ def test_explicit_dataset_batches_are_lazy_and_sum_repeated_rows():
     assert np.array_equal(b["users_mat"].numpy(), d.train_mat[b["users"].numpy()])
     with pytest.raises(KeyError):
         b["nope"]
+
+
+def test_csv_loader_index_arithmetic_equals_the_row_loop(tmp_path):
+    """csv2dict (implicit.py:94-104) on a CSV with timestamp ties, repeated (user, item) pairs and ratings below the filter:
+    the vectorised form must give the dict of the reference's row loop -- same key order, same item order."""
+    import pandas as pd
+    rng = np.random.default_rng(5)
+    n = 20000
+    df = pd.DataFrame({"user_id": rng.integers(0, 300, n), "item_id": (rng.random(n) ** 2 * 200).astype(int),
+                       "rating": rng.integers(1, 6, n), "timestamp": rng.integers(0, 500, n)})
+    path = tmp_path / "x.csv"
+    df.to_csv(path, index=False)
+    got = dataset.csv2dict(str(path), 4)
+    want = {}
+    d = pd.read_csv(path).sort_values("timestamp")
+    for u, i in zip(d[d["rating"] >= 4]["user_id"], d[d["rating"] >= 4]["item_id"]):
+        lst = want.setdefault(int(u), [])
+        if int(i) not in lst:
+            lst.append(int(i))
+    assert list(got) == list(want) and all(got[k] == want[k] for k in want)
+    assert all(type(k) is int and all(type(x) is int for x in v) for k, v in got.items())
+    (tmp_path / "empty.csv").write_text("user_id,item_id,rating,timestamp\n1,2,1,5\n")
+    assert dataset.csv2dict(str(tmp_path / "empty.csv"), 4) == {}
