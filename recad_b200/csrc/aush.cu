@@ -563,7 +563,8 @@ int recad_aush_train_epoch(const recad_aush* st, const recad_aush_epoch* ep, int
   cudaStream_t s = as_stream(stream);
   const int64_t n = ep->n_rows, I = st->n_items;
   const int F = st->filler_num, S = st->n_sel, E = F + S, batch = ep->batch;
-  RECAD_REQUIRE(n == 0 || (ep->cols && ep->tval && ep->dval && ep->rsel && ep->tsel && ep->msel && ep->zr && ep->colptr && ep->ent),
+  RECAD_REQUIRE(n == 0 || ((F == 0 || (ep->cols && ep->tval && ep->dval && ep->ent)) && ep->colptr &&
+                           (S == 0 || (ep->rsel && ep->tsel && ep->msel && ep->zr))),
                 RECAD_ERR_ARG, "aush_train_epoch: missing epoch array");
   const AushLayout lay = aush_layout(I);
   const int64_t small = aush_small(lay, S), n_adam = lay.total - lay.b1;

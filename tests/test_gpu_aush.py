@@ -143,3 +143,27 @@ def test_aush_over_the_b200_explicit_dataset_matches_the_reference():
         assert np.allclose(att.train_step(target_id_list=targets), gold, rtol=1e-4, atol=0), e
     st = np.random.get_state()
     assert np.array_equal(st[1], z["b_np_key_mid"]) and st[2] == int(z["b_np_pos_mid"])
+
+
+def test_aush_without_selected_items_matches_the_oracle():
+    """selected_ids = []: no generated column, empty ZR pool (no shuffle draws), the discriminator still trains on the fillers."""
+    from oracle import aush as oa
+    from recad_b200 import model
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(9)
+    mat = ((rng.random((150, 260)) < 0.15) * rng.integers(1, 6, (150, 260))).astype(np.float32)
+    kw = dict(selected_ids=[], filler_num=9, attack_num=5, ZR_ratio=0.2)
+    torch.manual_seed(1)
+    att = model.from_config("attacker", "aush", device=dev, **kw).I(dataset=StubExplicit(mat, 64, dev))
+    G0, D0 = {k: v.cpu().numpy() for k, v in att.netG_state().items()}, {k: v.cpu().numpy() for k, v in att.netD_state().items()}
+    o = oa.AushOracle(mat, G0, D0, batch_size=64, **kw)
+    np.random.seed(2)
+    mine = [att.train_step(target_id_list=[4]) for _ in range(2)]
+    s1 = np.random.get_state()
+    np.random.seed(2)
+    ref = [o.train_step([4]) for _ in range(2)]
+    s2 = np.random.get_state()
+    assert s1[2] == s2[2] and np.array_equal(s1[1], s2[1])
+    for a, b in zip(mine, ref):
+        assert np.allclose(a[0], b[0], rtol=1e-4) and np.allclose(a[3], b[3], rtol=1e-4) and a[1] == b[1] == 0.0 and a[2] == b[2] == 0.0
+    assert np.array_equal(att.generate_fake(target_id_list=[4]), o.generate_fake([4]))
