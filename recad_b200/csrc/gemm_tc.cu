@@ -13,6 +13,7 @@
 // Transposed operands (weight^T for dgrad, activation^T for wgrad) are produced by small split/transpose kernels;
 // TMA zero-fills out-of-range rows / k, so M, N need no padding and K only to a multiple of 4 floats.
 #include <math.h>
+#include <stdlib.h>
 
 #include <map>
 #include <tuple>
@@ -222,7 +223,12 @@ int gemm_tc(const float* A_hi, const float* A_lo, int M, int lda, const float* B
             float* Cm, int ldc, const float* bias, bool relu, float* out_hi, float* out_lo, int ld_split, cudaStream_t s) {
   RECAD_REQUIRE(M > 0 && N > 0 && K > 0 && lda % 4 == 0 && ldb % 4 == 0 && lda >= K && ldb >= K, RECAD_ERR_ARG,
                 "gemm_tc: bad shape M=%d N=%d K=%d lda=%d ldb=%d", M, N, K, lda, ldb);
-  const int BN = N > 64 ? 128 : 64;
+  // 128-wide tiles only when they fill the chip: at the reference's batch of 1024 a tower GEMM has 8-32 of them, and a CTA's
+  // time is set by the operand bytes it streams per k-block (64 KB at BN = 128, 48 KB at BN = 64) -- the narrow tile puts
+  // twice as many SMs to work on shorter k-steps
+  static const int bn_env = getenv("RECAD_GEMM_BN") ? atoi(getenv("RECAD_GEMM_BN")) : 0;
+  const int64_t tiles128 = (int64_t)((N + 127) / 128) * ((M + kGM - 1) / kGM);
+  const int BN = bn_env ? (bn_env >= 128 && N > 64 ? 128 : 64) : (N > 64 && tiles128 >= sm_count() ? 128 : 64);
   int rc;
   GemmMaps maps;
   const CUtensorMap* p;
