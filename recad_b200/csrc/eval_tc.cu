@@ -132,14 +132,17 @@ fullrank_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict_
         const uint32_t d = tmem_base + a * kTcN;
         const uint32_t bst = sB + s * kStageBytes;
         uint32_t acc = 0;
+        // (dbg 3: profiling aid, ranking epilogue + TMA only: only the first of a tile's 24 MMAs is issued, so the accumulator
+        //  holds a real -- coarser -- score tile and the epilogue sees realistic data)
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {      // hi*hi, lo*hi, hi*lo
+        for (int pass = 0; pass < (dbg == 3 && j >= 1 ? 1 : 3); ++pass) {      // hi*hi, lo*hi, hi*lo
           const uint32_t ta = tmem_base + kTcColA + (pass == 1 ? kTcK : 0);
           const uint32_t bo = bst + (pass == 2 ? kOperandBytes : 0);
 #pragma unroll
           for (int kb = 0; kb < kTcKB; ++kb)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+              if (dbg == 3 && j >= 1 && (kb | k)) continue;
               tc_mma_tf32_ts(d, ta + kb * 32 + k * 8, umma_desc(bo + kb * kKbBytes + k * 32), idesc, acc);
               acc = 1;
             }
