@@ -468,6 +468,22 @@ typedef struct recad_ncf {
 /* pred[b] = NeuMF(users[b], items[b]) (ncf.py:112-131, dropout 0), B <= max_batch. */
 int recad_ncf_forward(const recad_ncf* st, const int64_t* users, const int64_t* items, int64_t B,
                       float* pred, void* stream);
+/* Full ranking (normal.py:57-93 scores every (user, item) pair): the first tower layer is linear in cat(um[u], im[i]), so it
+ * is evaluated once per user and once per item instead of once per pair (75 % of the tower's multiply-adds).
+ *   recad_ncf_rank_work_floats  size of the path's own workspace for blocks of up to max_pairs pairs
+ *   recad_ncf_rank_floats       size of PUI for n_eval_users users (negative: bad argument)
+ *   recad_ncf_rank_prepare      PUI [dev] = [PU (n_eval_users x w) | PI (n_items x w)], PU = um[users] W_0[:, :w]^T,
+ *                               PI = im W_0[:, w:]^T + b_0; also stages every layer's split weights in `work`.
+ *                               RECAD_ERR_UNSUPPORTED when the model has to use recad_ncf_forward (exact fp32 tower, a
+ *                               single layer)
+ *   recad_ncf_rank_block        scores [dev] float[nu, n_items] of the evaluation users u0 .. u0 + nu (slots of `users`)
+ *                               against every item; nu * n_items <= max_pairs; same work / PUI as the prepare call */
+int64_t recad_ncf_rank_work_floats(int32_t factor, int32_t n_layers, int64_t max_pairs);
+int64_t recad_ncf_rank_floats(const recad_ncf* st, int64_t n_eval_users);
+int recad_ncf_rank_prepare(const recad_ncf* st, const int64_t* users, int64_t n_eval_users, float* PUI, float* work,
+                           int64_t work_floats, int64_t max_pairs, void* stream);
+int recad_ncf_rank_block(const recad_ncf* st, const float* PUI, const int64_t* users, int64_t n_eval_users, int64_t u0, int64_t nu,
+                         float* scores, float* work, int64_t work_floats, int64_t max_pairs, void* stream);
 /* One epoch of NCF.train_step (ncf.py:133-153); loss bookkeeping as in the MF epoch. */
 int recad_ncf_train_epoch(const recad_ncf* st, const int64_t* samples, const int64_t* perm,
                           int64_t n_samples, int64_t batch, int64_t step0, void* stream);

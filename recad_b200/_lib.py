@@ -134,6 +134,10 @@ SIGNATURES = {
     "recad_ncf_layout": (C.c_int, [i32, i32, i64, i64, C.POINTER(i64)]),
     "recad_ncf_work_floats": (i64, [i32, i32, i64]),
     "recad_ncf_forward": (C.c_int, [C.POINTER(NCF), vp, vp, i64, vp, vp]),
+    "recad_ncf_rank_work_floats": (i64, [i32, i32, i64]),
+    "recad_ncf_rank_floats": (i64, [C.POINTER(NCF), i64]),
+    "recad_ncf_rank_prepare": (C.c_int, [C.POINTER(NCF), vp, i64, vp, vp, i64, i64, vp]),
+    "recad_ncf_rank_block": (C.c_int, [C.POINTER(NCF), vp, vp, i64, i64, i64, vp, vp, i64, i64, vp]),
     "recad_ncf_train_epoch": (C.c_int, [C.POINTER(NCF), vp, vp, i64, i64, i64, vp]),
     "recad_ncf_grad": (C.c_int, [C.POINTER(NCF), vp, vp, i64, i64, vp]),
     "recad_gemm_tn_tf32x3": (C.c_int, [vp, vp, i32, i32, i32, vp, i32, vp, vp, vp]),

@@ -5,6 +5,7 @@ attributes of the reference (`embed_user_GMF`, `MLP_layers`, `predict_layer`, ..
 Parameter views into it.
 """
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -13,6 +14,7 @@ from .. import _lib, ops
 from .base import BaseVictim
 
 EVAL_CHUNK = 1 << 20   # (user, item) pairs scored per forward call during full-rank evaluation
+RANK_PAIRS = 1 << 19   # pairs per block of the factored full-rank path (its workspace: 8.3 KB per pair at the default tower)
 
 
 def _linear_view(weight, bias):
@@ -183,20 +185,56 @@ class NCF(BaseVictim):
             pbar.set_description(f"loss: {out[0]:.5f}")
         return out
 
+    def _rank_work(self):
+        """Workspace of the factored full-rank path: blocks of RANK_PAIRS (user, item) pairs, 8.3 KB per pair at the default
+        tower (recad_ncf_rank_work_floats)."""
+        mb = max(RANK_PAIRS, self.num_items)
+        if getattr(self, "_rank_ws", None) is None or self._rank_ws[1] != mb:
+            wf = int(_lib.lib().recad_ncf_rank_work_floats(self.f, self.L, mb))
+            with torch.cuda.device(self._dev):
+                self._rank_ws = (torch.empty(wf, dtype=torch.float32, device=self._dev), mb, wf)
+        return self._rank_ws
+
     def full_rank(self, user_ids, targets, K, train_rowptr, train_col):
-        """NCF scores are not an inner product: score blocks [users x all items] are materialised
-        chunk by chunk through the forward kernels and ranked by recad_rank_from_scores."""
+        """NCF scores are not an inner product: score blocks [users x all items] are materialised block by block and ranked
+        by recad_rank_from_scores.  The first tower layer is evaluated once per user and once per item
+        (recad_ncf_rank_prepare), a block then costs the remaining layers only; models the factored path does not cover
+        (exact fp32 tower, a single layer) go through forward() pair by pair."""
         self._require_instance("full_rank")
         I, dev = self.num_items, self._dev
-        per = max(1, EVAL_CHUNK // I)
-        all_items = torch.arange(I, device=dev)
+        n = int(user_ids.numel())
+        L = _lib.lib()
+        factored = (self.variant == 1 or (self.tower_precision != "fp32" and self.L >= 2 and self.f % 4 == 0)) \
+            and not os.environ.get("RECAD_NCF_EXACT") and os.environ.get("RECAD_NCF_RANK_FACTORED", "1") != "0" and n > 0
         outs = []
-        for s in range(0, user_ids.numel(), per):
-            ub = user_ids[s:s + per]
-            uu = ub.repeat_interleave(I)
-            ii = all_items.repeat(ub.numel())
-            scores = self.forward(uu, ii).view(ub.numel(), I)
-            outs.append(ops.rank_from_scores(scores, ub, train_rowptr, train_col, targets, K))
+        if factored:
+            st = self._st
+            work, mb, wf = self._rank_work()
+            users = user_ids.to(dev).long().contiguous()
+            with torch.cuda.device(dev):
+                pui = torch.empty(max(int(L.recad_ncf_rank_floats(C.byref(st), n)), 1), dtype=torch.float32, device=dev)
+                self._check(L.recad_ncf_rank_prepare(C.byref(st), self._vp(users), n, self._vp(pui), self._vp(work), wf, mb,
+                                                     ops._stream(dev)), "recad_ncf_rank_prepare")
+                per = max(1, mb // I)
+                scores = torch.empty((per, I), dtype=torch.float32, device=dev)
+                for s in range(0, n, per):
+                    nu = min(per, n - s)
+                    self._check(L.recad_ncf_rank_block(C.byref(st), self._vp(pui), self._vp(users), n, s, nu, self._vp(scores),
+                                                       self._vp(work), wf, mb, ops._stream(dev)), "recad_ncf_rank_block")
+                    outs.append(ops.rank_from_scores(scores[:nu], users[s:s + nu], train_rowptr, train_col, targets, K))
+            bad = self.loss_acc[3:4].view(torch.int64)
+            if int(bad.item()):
+                bad.zero_()
+                raise ops.RecadError("NCF.full_rank: a user id is out of range")
+        else:
+            per = max(1, EVAL_CHUNK // I)
+            all_items = torch.arange(I, device=dev)
+            for s in range(0, n, per):
+                ub = user_ids[s:s + per]
+                uu = ub.repeat_interleave(I)
+                ii = all_items.repeat(ub.numel())
+                scores = self.forward(uu, ii).view(ub.numel(), I)
+                outs.append(ops.rank_from_scores(scores, ub, train_rowptr, train_col, targets, K))
         return tuple(torch.cat([o[k] for o in outs]) for k in range(4)) + (0.0,)
 
     def input_describe(self):

@@ -347,3 +347,34 @@ def test_tensor_core_gemm_is_fp32_accurate(M, N, K, bias, relu):
     if relu:
         ref = ref.clamp_min(0)
     assert float(((C - ref).abs() / mag).max()) < 4e-6     # 3xTF32: ~2^-21 of sum |a||b|
+
+
+@pytest.mark.parametrize("variant,f,L", [("NeuMF-end", 32, 5), ("NeuMF-end", 8, 3), ("MLP", 8, 2), ("GMF", 8, 3)])
+def test_ncf_factored_full_rank_equals_the_pairwise_forward(variant, f, L, monkeypatch):
+    """Full ranking with the first tower layer evaluated once per user and once per item (recad_ncf_rank_prepare / _block)
+    against the same model scored pair by pair through forward(): scores 1e-5 of the score scale (summation order of the first
+    layer differs), target ranks and top-K lists equal except at near-ties."""
+    from recad_b200 import model
+    from recad_b200.victim import ncf as ncf_mod
+    U, I = 300, 517
+    rng = np.random.default_rng(1)
+    data = StubData(U, I, [], ("users", "items", "labels"))
+    torch.manual_seed(5)
+    m = model.from_config("victim", "ncf", factor_num=f, num_layers=L, model=variant, device=torch.device(DEV)).I(dataset=data)
+    with torch.no_grad():
+        for p in m.parameters():                       # embeddings are N(0, 0.01) at init: widen the score spread
+            p.mul_(3.0)
+    deg = 12
+    ptr = torch.arange(0, (U + 1) * deg, deg, device=DEV)
+    col = torch.sort(torch.as_tensor(rng.integers(0, I, (U, deg)), device=DEV), 1)[0].int().flatten()
+    users = torch.as_tensor(rng.permutation(U)[:211], device=DEV)
+    targets = [3, 400]
+    monkeypatch.setattr(ncf_mod, "RANK_PAIRS", 7 * I + 5)            # several blocks, the last one ragged
+    got = m.full_rank(users, targets, 10, ptr, col)
+    monkeypatch.setenv("RECAD_NCF_RANK_FACTORED", "0")
+    ref = m.full_rank(users, targets, 10, ptr, col)
+    scale = float(ref[3].abs().max())
+    assert torch.allclose(got[3], ref[3], rtol=0, atol=2e-5 * scale)                       # target scores
+    assert float((got[2] != ref[2]).float().mean()) < 0.01 and int((got[2] - ref[2]).abs().max()) <= 2
+    assert float((got[0] != ref[0]).float().mean()) < 0.01                                 # top-K ids
+    assert torch.allclose(got[1], ref[1], rtol=0, atol=2e-5 * scale)
