@@ -487,6 +487,8 @@ int recad_ncf_rank_block(const recad_ncf* st, const float* PUI, const int64_t* u
 /* One epoch of NCF.train_step (ncf.py:133-153); loss bookkeeping as in the MF epoch. */
 int recad_ncf_train_epoch(const recad_ncf* st, const int64_t* samples, const int64_t* perm,
                           int64_t n_samples, int64_t batch, int64_t step0, void* stream);
+/* Batches replayed from the captured graph so far in this process (diagnostic: tests check that the graph path ran). */
+int64_t recad_ncf_graph_launches(void);
 /* The gradient half of ONE step (ncf.py:139-148): as recad_mf_grad, into st->grads (layout of recad_ncf_layout). */
 int recad_ncf_grad(const recad_ncf* st, const int64_t* samples, const int64_t* perm, int64_t B, int64_t B_norm,
                    void* stream);

@@ -139,6 +139,7 @@ SIGNATURES = {
     "recad_ncf_rank_prepare": (C.c_int, [C.POINTER(NCF), vp, i64, vp, vp, i64, i64, vp]),
     "recad_ncf_rank_block": (C.c_int, [C.POINTER(NCF), vp, vp, i64, i64, i64, vp, vp, i64, i64, vp]),
     "recad_ncf_train_epoch": (C.c_int, [C.POINTER(NCF), vp, vp, i64, i64, i64, vp]),
+    "recad_ncf_graph_launches": (i64, []),
     "recad_ncf_grad": (C.c_int, [C.POINTER(NCF), vp, vp, i64, i64, vp]),
     "recad_gemm_tn_tf32x3": (C.c_int, [vp, vp, i32, i32, i32, vp, i32, vp, vp, vp]),
     "recad_transpose_items": (C.c_int, [vp, i64, i32, vp, i64, vp]),

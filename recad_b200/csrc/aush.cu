@@ -546,7 +546,8 @@ static int aush_check(const recad_aush* st, const char* who) {
 int recad_aush_generate(const recad_aush* st, const int32_t* cols, const float* tval, int64_t n_rows, float* gen_out, void* stream) {
   int rc;
   if ((rc = aush_check(st, "aush_generate"))) return rc;
-  RECAD_REQUIRE(cols && tval && gen_out && n_rows >= 0, RECAD_ERR_ARG, "aush_generate: bad argument");
+  RECAD_REQUIRE(cols && tval && n_rows >= 0 && (gen_out || n_rows == 0 || st->n_sel == 0), RECAD_ERR_ARG,
+                "aush_generate: bad argument");      // (an empty [n_rows, 0] output has no address)
   if (n_rows == 0 || st->n_sel == 0) return RECAD_OK;
   aush_gen_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, as_stream(stream)>>>(st->G_W1t, st->G_b1, st->G_W2, st->G_b2, st->selected,
                                                                                st->n_sel, cols, tval, st->filler_num, nullptr, nullptr,

@@ -221,12 +221,10 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, const float* __r
       const float r = reg_scale * cnt[i / vec_per_row];
       G.x = fmaf(r, P.x, G.x); G.y = fmaf(r, P.y, G.y); G.z = fmaf(r, P.z, G.z); G.w = fmaf(r, P.w, G.w);
     }
-#define RECAD_ADAM1(c)                                            \
-    M.c = M.c + a.w1 * (G.c - M.c);                               \
-    V.c = V.c * a.b2 + (a.w2 * G.c) * G.c;                        \
-    P.c = P.c - a.step_size * (M.c / (sqrtf(V.c) / a.bc2_sqrt + a.eps));
-    RECAD_ADAM1(x) RECAD_ADAM1(y) RECAD_ADAM1(z) RECAD_ADAM1(w)
-#undef RECAD_ADAM1
+    adam_update(P.x, G.x, M.x, V.x, a);
+    adam_update(P.y, G.y, M.y, V.y, a);
+    adam_update(P.z, G.z, M.z, V.z, a);
+    adam_update(P.w, G.w, M.w, V.w, a);
     reinterpret_cast<float4*>(p)[i] = P;
     reinterpret_cast<float4*>(m)[i] = M;
     reinterpret_cast<float4*>(v)[i] = V;
@@ -244,9 +242,7 @@ __global__ void adam_tail_kernel(float* p, const float* g, float* m, float* v, i
   int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float G = g[i], M = m[i], V = v[i], P = p[i];
-  M = M + a.w1 * (G - M);
-  V = V * a.b2 + (a.w2 * G) * G;
-  P = P - a.step_size * (M / (sqrtf(V) / a.bc2_sqrt + a.eps));
+  adam_update(P, G, M, V, a);
   p[i] = P; m[i] = M; v[i] = V;
 }
 

@@ -92,6 +92,15 @@ struct AdamScalars {
   float bc2_sqrt;   // sqrt(1 - beta2^t)
   float eps;
 };
+// One element's Adam step, with every rounding spelled out: the dense kernels, the scalar tail, the graph-replayed NCF step
+// and the lazy embedding rows must produce the SAME bits (left to the compiler, `V * b2 + (w2 * G) * G` was contracted
+// around the first product in one kernel and around the second in another: the graph-replayed NCF epoch differed from the
+// plain loop in the last bit of a few parameters).
+__device__ __forceinline__ void adam_update(float& P, float G, float& M, float& V, const AdamScalars& a) {
+  M = __fmaf_rn(a.w1, __fsub_rn(G, M), M);
+  V = __fmaf_rn(V, a.b2, __fmul_rn(__fmul_rn(a.w2, G), G));
+  P = __fmaf_rn(-a.step_size, __fdiv_rn(M, __fadd_rn(__fdiv_rn(__fsqrt_rn(V), a.bc2_sqrt), a.eps)), P);
+}
 // optional end-of-batch bookkeeping done by thread 0 of the Adam launch:
 //   acc[2] += acc[0] * inv_B + half_lambda * acc[1] * inv_B;  acc[0] = acc[1] = 0
 struct LossFold {

@@ -378,3 +378,90 @@ def test_ncf_factored_full_rank_equals_the_pairwise_forward(variant, f, L, monke
     assert float((got[2] != ref[2]).float().mean()) < 0.01 and int((got[2] - ref[2]).abs().max()) <= 2
     assert float((got[0] != ref[0]).float().mean()) < 0.01                                 # top-K ids
     assert torch.allclose(got[1], ref[1], rtol=0, atol=2e-5 * scale)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_ncf_lazy_embedding_adam_and_graph_replay_equal_the_plain_dense_loop_bit_for_bit(precision, monkeypatch):
+    """Two execution strategies of the NCF epoch against the plain loop (dense torch.optim.Adam step, one launch sequence per
+    batch), every combination: (a) lazy embedding Adam (ncf.cu: rows a batch does not touch take their zero-gradient steps
+    later, in registers) and (b) the full batches replayed from ONE captured graph driven by a device control block.  Every
+    parameter, both moments and the epoch losses must be IDENTICAL -- an element's update sequence is the same, only its
+    timing moves.  Batches of 64 over 120 users / 90 items: rows are touched at irregular intervals, some never; the last
+    batch is ragged.  The graph path must really have run (it needs a capturable stream: the library leaves the legacy
+    default stream for its own when asked to capture)."""
+    from recad_b200 import _lib, model
+    U, I = 120, 90
+    rng = np.random.default_rng(3)
+    n = 64 * 9 + 17
+    samples = np.stack([rng.integers(0, U, n), rng.integers(0, I - 7, n), rng.integers(0, 2, n)], 1)     # items 83.. never touched
+    batches = [(samples[k:k + 64, 0], samples[k:k + 64, 1], samples[k:k + 64, 2]) for k in range(0, n, 64)]
+    runs = {}
+    for lazy in ("0", "1"):
+        for graph in ("0", "1"):
+            monkeypatch.setenv("RECAD_NCF_LAZY_ADAM", lazy)
+            monkeypatch.setenv("RECAD_NCF_LAZY_PERIOD", "4")          # all rows are brought up to date every 4 batches
+            monkeypatch.setenv("RECAD_NCF_GRAPH", graph)
+            data = StubData(U, I, batches * 3, ("users", "items", "labels"), bs=64)
+            data.per_epoch = len(batches)
+            torch.manual_seed(11)
+            m = model.from_config("victim", "ncf", factor_num=8, num_layers=3, tower_precision=precision, device=torch.device(DEV)).I(dataset=data)
+            before = _lib.lib().recad_ncf_graph_launches()
+            losses = [m.train_step()[0] for _ in range(3)]
+            replayed = _lib.lib().recad_ncf_graph_launches() - before
+            assert replayed == (3 * 9 if graph == "1" else 0), (lazy, graph, replayed)
+            runs[(lazy, graph)] = (losses, m.flat.clone(), m.m.clone(), m.v.clone())
+    ref = runs[("0", "0")]
+    assert float(ref[2].abs().max()) > 0
+    for key, r in runs.items():
+        assert r[0] == pytest.approx(ref[0], rel=1e-12, abs=0), key        # (the batch's BCE sum is a double atomicAdd over 8 blocks)
+        for a, b in zip(r[1:], ref[1:]):
+            assert torch.equal(a, b), key
+
+
+@pytest.mark.parametrize("lazy", ["0", "1"])
+def test_ncf_epoch_reports_an_out_of_range_id_and_touches_nothing_out_of_range(lazy, monkeypatch):
+    """A sample id outside its table (ncf.py:112-119 would raise an IndexError in the embedding lookup): the epoch finishes with
+    the row replaced by row 0, nothing is addressed out of range (gradient rows, lazy-Adam progress counters), and train_step
+    raises."""
+    from recad_b200 import model, ops
+    monkeypatch.setenv("RECAD_NCF_LAZY_ADAM", lazy)
+    U, I = 50, 40
+    rng = np.random.default_rng(5)
+    users, items, labels = rng.integers(0, U, 200), rng.integers(0, I, 200), rng.integers(0, 2, 200)
+    users[77] = U + 1000000
+    batches = [(users[k:k + 64], items[k:k + 64], labels[k:k + 64]) for k in range(0, 200, 64)]
+    data = StubData(U, I, batches, ("users", "items", "labels"), bs=64)
+    torch.manual_seed(1)
+    m = model.from_config("victim", "ncf", factor_num=8, num_layers=3, device=torch.device(DEV)).I(dataset=data)
+    with pytest.raises(ops.RecadError, match="out of range"):
+        m.train_step()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(m.flat).all())
+
+
+def test_ncf_lazy_adam_rows_left_alone_for_a_thousand_steps_match_the_dense_loop_bit_for_bit(monkeypatch):
+    """The zero-gradient steps of the lazy embedding Adam are hand-written fast paths of sqrt and divide with a value-range
+    window (ncf.cu: adam_zero_step); outside the window they fall back to the dense kernel's own arithmetic.  One user and one
+    item appear in the first batch only and then decay for 1 200 steps: their m runs through the window's lower edge (2^-90),
+    through the subnormals and reaches exactly zero, so all three regimes -- and the columns that never saw a gradient
+    (m = v = 0) -- are compared with the dense loop."""
+    from recad_b200 import model
+    U, I, bs, nb = 40, 30, 8, 900
+    rng = np.random.default_rng(9)
+    users, items, labels = rng.integers(0, U - 2, bs * nb), rng.integers(0, I - 2, bs * nb), rng.integers(0, 2, bs * nb)
+    users[0], items[0] = U - 1, I - 1                      # never again; user U - 2 and item I - 2 never at all
+    batches = [(users[k:k + bs], items[k:k + bs], labels[k:k + bs]) for k in range(0, bs * nb, bs)]
+    runs = {}
+    for lazy in ("0", "1"):
+        monkeypatch.setenv("RECAD_NCF_LAZY_ADAM", lazy)
+        monkeypatch.setenv("RECAD_NCF_LAZY_PERIOD", "50")
+        data = StubData(U, I, batches, ("users", "items", "labels"), bs=bs)
+        torch.manual_seed(4)
+        m = model.from_config("victim", "ncf", factor_num=8, num_layers=2, tower_precision="fp32", device=torch.device(DEV)).I(dataset=data)
+        loss = m.train_step()[0]
+        runs[lazy] = (loss, m.flat.clone(), m.m.clone(), m.v.clone())
+    assert runs["1"][0] == pytest.approx(runs["0"][0], rel=1e-12, abs=0)
+    for a, b in zip(runs["1"][1:], runs["0"][1:]):
+        assert torch.equal(a, b)
+    lone = runs["0"][2][(U - 1) * 8:U * 8]                 # m of the lone user's GMF row (the first table of the layout)
+    assert float(lone.abs().max()) < 2.0 ** -90 and float(runs["0"][3][(U - 1) * 8:U * 8].max()) > 0
