@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <map>
 #include <tuple>
 
@@ -183,6 +184,53 @@ __global__ void split_transpose_kernel(const float* __restrict__ src, int R, int
       lo[(int64_t)c * ldo + r] = l;
     }
   }
+}
+
+// The three operand splits of one backward layer in ONE launch (they were three of a layer's six launches; the NCF step is
+// launch bound): blockIdx.z = 0: dz [R, C0] -> dz^T hi / lo [C0, ldo] AND the row split dz hi / lo [R, C0];
+// blockIdx.z = 1: h [R, C1] -> h^T hi / lo [C1, ldo].  Columns R..ldo of the transposes are zeroed.
+__global__ void split_dz_h_kernel(const float* __restrict__ dz, int R, int C0, const float* __restrict__ h, int C1,
+                                  float* __restrict__ dzt_hi, float* __restrict__ dzt_lo, float* __restrict__ ht_hi,
+                                  float* __restrict__ ht_lo, int ldo, float* __restrict__ dz_hi, float* __restrict__ dz_lo) {
+  __shared__ float t[32][33];
+  const bool second = blockIdx.z == 1;
+  const float* __restrict__ src = second ? h : dz;
+  const int Cc = second ? C1 : C0;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  if (c0 >= Cc) return;                                     // (whole block: the grid is sized for the wider matrix)
+  float* __restrict__ hi = second ? ht_hi : dzt_hi;
+  float* __restrict__ lo = second ? ht_lo : dzt_lo;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    const bool in = r < R && c < Cc;
+    const float v = in ? src[(int64_t)r * Cc + c] : 0.f;
+    t[i][threadIdx.x] = v;
+    if (!second && in) {
+      float a, b;
+      split_tf32(v, a, b);
+      dz_hi[(int64_t)r * Cc + c] = a;
+      dz_lo[(int64_t)r * Cc + c] = b;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;             // output row c, output column r
+    if (c < Cc && r < ldo) {
+      float a, b;
+      split_tf32(t[threadIdx.x][i], a, b);
+      hi[(int64_t)c * ldo + r] = a;
+      lo[(int64_t)c * ldo + r] = b;
+    }
+  }
+}
+
+int tc_split_dz_h(const float* dz, int R, int C0, const float* h, int C1, float* dzt_hi, float* dzt_lo, float* ht_hi, float* ht_lo,
+                  int ldo, float* dz_hi, float* dz_lo, cudaStream_t s) {
+  if (R == 0 || C0 == 0 || C1 == 0) return RECAD_OK;
+  dim3 grid((std::max(C0, C1) + 31) / 32, (ldo + 31) / 32, 2);
+  split_dz_h_kernel<<<grid, dim3(32, 8), 0, s>>>(dz, R, C0, h, C1, dzt_hi, dzt_lo, ht_hi, ht_lo, ldo, dz_hi, dz_lo);
+  RECAD_LAUNCH_CHECK();
+  return RECAD_OK;
 }
 
 int tc_split_rows(const float* src, int R, int Cc, int ld, float* hi, float* lo, int ldo, cudaStream_t s) {
