@@ -197,6 +197,9 @@ typedef struct recad_lightgcn {
   float* g;                /* [dev] float[N, D] work: gradient wrt the layer sum */
   float* cnt;              /* [dev] float[N]    work: batch multiplicities */
   double* loss_acc;        /* [dev] double[4]   {sum softplus, sum sq, epoch loss sum, spare} */
+  const recad_csr* graph_t;/* NULL (the usual case: A_hat is symmetric, the backward is the same product), or the TRANSPOSE of
+                            * `graph` for the backward pass -- graph dropout (lightgcn.py:62-80) drops (u, i) and (i, u)
+                            * independently, so the dropped matrix is not symmetric */
 } recad_lightgcn;
 
 /* O = mean_k A^k E (lightgcn.py:82-113).  L fused SpMMs, nothing else. */

@@ -4,6 +4,7 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
 Restates:
   * ``LightGCN.computer``      recad/model/victim/lightgcn.py:82-113
+  * ``LightGCN.__dropout_x``   recad/model/victim/lightgcn.py:62-72 (graph dropout, off by default)
   * ``LightGCN.getEmbedding``  recad/model/victim/lightgcn.py:122-130
   * ``LightGCN.train_step``    recad/model/victim/lightgcn.py:132-172
   * ``LightGCN.forward``       recad/model/victim/lightgcn.py:174-183
@@ -36,6 +37,14 @@ def csr_to_torch_coo(indptr, indices, data, n):
     return torch.sparse_coo_tensor(idx, torch.as_tensor(np.asarray(data), dtype=torch.float32), (n, n)).coalesce()
 
 
+def dropout_graph(graph_coo, keep_prob):
+    """__dropout_x (lightgcn.py:62-72) on the coalesced COO graph: one torch.rand(nnz) draw of the global CPU generator;
+    an entry stays when int(rand + keep_prob) is 1 and is rescaled by 1 / keep_prob."""
+    index, values = graph_coo.indices().t(), graph_coo.values()
+    keep = (torch.rand(len(values)) + keep_prob).int().bool()
+    return torch.sparse_coo_tensor(index[keep].t(), values[keep] / keep_prob, graph_coo.shape)
+
+
 def propagate(graph, user_emb, item_emb, n_layers):
     """computer(): E0 = cat(U, I); E(k+1) = A_hat E(k); out = mean_k E(k)."""
     all_emb = torch.cat([user_emb, item_emb])
@@ -62,8 +71,11 @@ def bpr_loss(graph, user_emb, item_emb, n_layers, users, pos, neg, lam):
 class LightGCNOracle:
     """Holds the two tables + Adam exactly as the reference module does."""
 
-    def __init__(self, graph, user_emb, item_emb, n_layers=3, lam=1e-4, lr=1e-3):
+    def __init__(self, graph, user_emb, item_emb, n_layers=3, lam=1e-4, lr=1e-3, keep_prob=None):
+        """keep_prob: graph dropout as the reference applies it with config['dropout'] on and the module in training mode
+        (graph must then be the coalesced COO tensor): every propagation draws a fresh mask (lightgcn.py:90-96)."""
         self.graph = graph
+        self.keep_prob, self.training = keep_prob, True
         self.user_emb = torch.nn.Parameter(torch.as_tensor(user_emb, dtype=torch.float32).clone())
         self.item_emb = torch.nn.Parameter(torch.as_tensor(item_emb, dtype=torch.float32).clone())
         self.n_layers, self.lam = n_layers, lam
@@ -71,11 +83,14 @@ class LightGCNOracle:
 
     def step(self, users, pos, neg):
         users, pos, neg = (torch.as_tensor(np.asarray(x), dtype=torch.int64) for x in (users, pos, neg))
-        loss = bpr_loss(self.graph, self.user_emb, self.item_emb, self.n_layers, users, pos, neg, self.lam)
+        loss = bpr_loss(self._graph(), self.user_emb, self.item_emb, self.n_layers, users, pos, neg, self.lam)
         self.optimizer.zero_grad()
         loss.backward()
         self.optimizer.step()
         return loss.item()
+
+    def _graph(self):
+        return dropout_graph(self.graph, self.keep_prob) if self.keep_prob is not None and self.training else self.graph
 
     def train_epoch(self, batches):
         """train_step (lightgcn.py:132-172): returns the mean of per-batch final_loss."""
@@ -88,7 +103,7 @@ class LightGCNOracle:
     @torch.no_grad()
     def forward(self, users, items):
         """forward (lightgcn.py:174-183): <O_u, O_i>, no sigmoid."""
-        au, ai = propagate(self.graph, self.user_emb, self.item_emb, self.n_layers)
+        au, ai = propagate(self._graph(), self.user_emb, self.item_emb, self.n_layers)
         users = torch.as_tensor(np.asarray(users), dtype=torch.int64)
         items = torch.as_tensor(np.asarray(items), dtype=torch.int64)
         return torch.sum(au[users] * ai[items], dim=1)

@@ -30,6 +30,7 @@ class LightGCN(C.Structure):
         ("graph", C.POINTER(CSR)), ("n_users", i64), ("n_items", i64), ("D", i32), ("n_layers", i32),
         ("lam", f32), ("lr", f32), ("beta1", f32), ("beta2", f32), ("eps", f32), ("_pad", i32),
         ("E", vp), ("m", vp), ("v", vp), ("O", vp), ("X0", vp), ("X1", vp), ("g", vp), ("cnt", vp), ("loss_acc", vp),
+        ("graph_t", C.POINTER(CSR)),
     ]
 
 

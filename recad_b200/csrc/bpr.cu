@@ -437,7 +437,7 @@ static int lightgcn_train_epoch_t(const recad_lightgcn* st, const IdxT* samples,
     const float* t = st->g;
     for (int k = 0; k < L; ++k) {
       float* z = (k & 1) ? st->X1 : st->X0;
-      rc = recad_spmm(st->graph, t, nullptr, st->g, z, 1.0f, D, stream);
+      rc = recad_spmm(st->graph_t ? st->graph_t : st->graph, t, nullptr, st->g, z, 1.0f, D, stream);
       if (rc) return rc;
       t = z;
     }

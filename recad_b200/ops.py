@@ -290,6 +290,41 @@ class Graph:
             self._structs[D] = s
         return self._structs[D]
 
+    def with_values(self, vals=None):
+        """A matrix with this one's structure and PLAN but values of its own (graph dropout: the kept entries rescaled, the
+        dropped ones zero).  Only vals / cv and the partial-sum scratch are new; call `set_values` to refill them in place
+        (the structs handed out stay valid).  Shares row_cnt with its parent: never launch both at the same time."""
+        g = object.__new__(Graph)
+        g.__dict__.update(self.__dict__)
+        g._partials, g._structs = {}, {}
+        with torch.cuda.device(self.device):
+            g.vals = torch.empty_like(self.vals)
+            g.cv = torch.empty_like(self.cv)
+        g.set_values(self.vals if vals is None else vals)
+        return g
+
+    def transpose_permutation(self):
+        """T with entry k = (r, c) -> the position of (c, r): vals[T] are the values of the transposed matrix on the SAME
+        structure (square, structurally symmetric matrices only -- the bipartite adjacency).  Cached."""
+        if getattr(self, "_tperm", None) is None:
+            if self.n_rows != self.n_cols:
+                raise RecadError("transpose_permutation: the matrix is not square")
+            with torch.cuda.device(self.device):
+                rows = torch.repeat_interleave(torch.arange(self.n_rows, device=self.device), self.rowptr[1:] - self.rowptr[:-1])
+                cols = self.colidx.long()
+                keys = rows * self.n_cols + cols                              # ascending: CSR order with sorted columns
+                T = torch.searchsorted(keys, cols * self.n_cols + rows)
+                if self.nnz and not bool((keys[T.clamp_(max=self.nnz - 1)] == cols * self.n_cols + rows).all()):
+                    raise RecadError("transpose_permutation: the structure is not symmetric")
+            self._tperm = T
+        return self._tperm
+
+    def set_values(self, vals):
+        with torch.cuda.device(self.device):
+            self.vals.copy_(vals)
+            check(_lib.lib().recad_spmm_pack_cv(_ptr(self.colidx), _ptr(self.vals), self.nnz, _ptr(self.cv), _stream(self.device)),
+                  "recad_spmm_pack_cv")
+
     # -- export --------------------------------------------------------------- #
     def to_numpy(self):
         return (self.rowptr.cpu().numpy(), self.colidx.cpu().numpy().astype(np.int64), self.vals.cpu().numpy())

@@ -26,8 +26,10 @@ class LightGCN(BaseVictim):
         self.logger = get_logger(__name__, config["logging_level"])
         if config["A_split"]:
             raise ValueError("A_split is not support in LightGCN yet")          # lightgcn.py:38-39
-        if config["dropout"]:
-            raise NotImplementedError("graph dropout (lightgcn.py:62-80) is off by default and not implemented")
+        # graph dropout (lightgcn.py:62-80, off by default): every computer() call of a model in training mode -- one per
+        # batch, and, since the reference never calls eval(), one per forward -- draws a fresh mask over the nnz entries
+        self.dropout, self.keep_prob = bool(config["dropout"]), float(config["keep_prob"])
+        self._drop_graph = self._drop_graph_t = self._st_drop = None
         if str(config["optim"]).lower() != "adam":
             raise ValueError("optimizer not supported")                          # only Adam is on the hot path
         info = self.dataset.info_describe()
@@ -91,6 +93,7 @@ class LightGCN(BaseVictim):
         for k in ("E", "m", "v", "O", "X0", "X1", "g", "cnt", "loss_acc"):
             setattr(st, k, getattr(self, k).data_ptr())
         self._st = st
+        self._drop_graph = self._drop_graph_t = self._st_drop = None
         self._O_valid = False      # O was just (re)allocated: never score from it before a propagate
 
     def load_state_dict(self, *args, **kwargs):
@@ -112,13 +115,43 @@ class LightGCN(BaseVictim):
                 raise ops.RecadError("the dataset graph lives on another device")
             self._alloc(dev, self.E[:self.num_users], self.E[self.num_users:], self.m, self.v)
 
+    # ------------------------------------------------------------------ graph dropout
+    def _dropped_state(self):
+        """lightgcn.py:62-80 `__dropout_x`: keep an entry when int(rand + keep_prob) is 1, rescale the kept values by
+        1 / keep_prob.  The mask is drawn exactly as the reference draws it -- torch.rand(nnz) on the CPU generator, in the
+        coalesced (row-major) entry order, which is the CSR order -- so a seeded run drops the same entries.  Dropped
+        entries keep their place in the structure with value 0 (the plan and both SpMM directions are unchanged): the
+        state returned is this model's with the graph swapped for that matrix."""
+        g = self.Graph
+        keep = (torch.rand(g.nnz) + self.keep_prob).int().bool()
+        with torch.cuda.device(self._dev):
+            keep = keep.to(self._dev)
+            vals = torch.where(keep, g.vals / self.keep_prob, torch.zeros((), dtype=g.vals.dtype, device=self._dev))
+            # (u, i) and (i, u) are dropped independently: the dropped matrix is not symmetric and autograd's backward
+            # multiplies by its TRANSPOSE -- the same structure with the values permuted
+            vals_t = vals[g.transpose_permutation()]
+            if self._drop_graph is None:
+                self._drop_graph, self._drop_graph_t = g.with_values(vals), g.with_values(vals_t)
+                st = _lib.LightGCN()
+                C.memmove(C.byref(st), C.byref(self._st), C.sizeof(st))
+                st.graph = C.pointer(self._drop_graph.struct(self.latent_dim))
+                st.graph_t = C.pointer(self._drop_graph_t.struct(self.latent_dim))
+                self._st_drop = st
+            else:
+                self._drop_graph.set_values(vals)
+                self._drop_graph_t.set_values(vals_t)
+        return self._st_drop
+
     # ------------------------------------------------------------------ compute
     def computer(self):
-        """lightgcn.py:82-113: (users, items) propagated embeddings = mean of the layer outputs."""
+        """lightgcn.py:82-113: (users, items) propagated embeddings = mean of the layer outputs (over a freshly dropped
+        graph when dropout is on and the module is in training mode)."""
         self._require_instance("computer")
+        dropped = self.dropout and self.training
+        st = self._dropped_state() if dropped else self._st
         with torch.cuda.device(self._dev):
-            self._check(_lib.lib().recad_lightgcn_propagate(C.byref(self._st), ops._stream(self._dev)), "recad_lightgcn_propagate")
-        self._O_valid = True
+            self._check(_lib.lib().recad_lightgcn_propagate(C.byref(st), ops._stream(self._dev)), "recad_lightgcn_propagate")
+        self._O_valid = not dropped      # a dropped propagation is never reused: the next call draws a new mask
         return self.O[:self.num_users], self.O[self.num_users:]
 
     def getUsersRating(self, users):
@@ -135,8 +168,20 @@ class LightGCN(BaseVictim):
         if n == 0:
             raise ops.RecadError("LightGCN.train_step: the sampler produced no training triple")
         B = int(self.dataset.config["pairwise_batch_size"]) if hasattr(self.dataset, "config") else 1024
-        self.run_epoch(samples, perm, B)
         n_batches = (n + B - 1) // B
+        if self.dropout:
+            # one mask per batch (lightgcn.py:90-92 inside getEmbedding): the epoch driver runs batch by batch, each over its
+            # own dropped graph; loss and the out-of-range flag are summed on the device
+            total = torch.zeros_like(self.loss_acc)
+            for k in range(n_batches):
+                lo, hi = k * B, min(n, (k + 1) * B)
+                rows, order = (samples, perm[lo:hi]) if perm is not None else (samples[lo:hi], None)
+                self.run_epoch(rows, order, B, st=self._dropped_state(), n=hi - lo, step0=self._steps + k)
+                total[2] += self.loss_acc[2]
+                total[3:4].view(torch.int64).bitwise_or_(self.loss_acc[3:4].view(torch.int64))
+            self.loss_acc.copy_(total)
+        else:
+            self.run_epoch(samples, perm, B)
         self._steps += n_batches
         self._O_valid = False
         pbar = config.get("progress_bar", None)
@@ -145,8 +190,9 @@ class LightGCN(BaseVictim):
             pbar.set_description(f"loss {out[0]:.5f}")
         return out
 
-    def run_epoch(self, samples, perm, B):
-        """Enqueue one epoch over device-resident rows (int64 or int32 [n, 3]) visited in the order perm (same dtype)."""
+    def run_epoch(self, samples, perm, B, st=None, n=None, step0=None):
+        """Enqueue one epoch over device-resident rows (int64 or int32 [n, 3]) visited in the order perm (same dtype).
+        st / n / step0: another state (the dropped graph), the number of rows to visit and the Adam steps taken so far."""
         L = _lib.lib()
         i32 = samples.dtype == torch.int32
         if perm is not None and perm.dtype != samples.dtype:
@@ -154,14 +200,15 @@ class LightGCN(BaseVictim):
         fn, name = (L.recad_lightgcn_train_epoch_i32, "recad_lightgcn_train_epoch_i32") if i32 else \
             (L.recad_lightgcn_train_epoch, "recad_lightgcn_train_epoch")
         with torch.cuda.device(self._dev):
-            self._check(fn(C.byref(self._st), self._vp(samples), self._vp(perm), int(samples.shape[0]), B, self._steps,
+            self._check(fn(C.byref(self._st if st is None else st), self._vp(samples), self._vp(perm),
+                           int(samples.shape[0]) if n is None else int(n), B, self._steps if step0 is None else int(step0),
                            ops._stream(self._dev)), name)
 
     def forward(self, users, items):
         """lightgcn.py:174-183: <O_u, O_i>.  The propagation is redone only when the tables changed
         (the reference redoes it on every call, i.e. once per evaluated user)."""
         self._require_instance("forward")
-        if not self._O_valid:
+        if not self._O_valid or (self.dropout and self.training):
             self.computer()
         users = users.to(self._dev).long().contiguous()
         items = items.to(self._dev).long().contiguous()
@@ -170,7 +217,7 @@ class LightGCN(BaseVictim):
     def full_rank(self, user_ids, targets, K, train_rowptr, train_col):
         """Batched evaluation entry used by recad_b200.evaluate (fused score/mask/top-K kernel)."""
         self._require_instance("full_rank")
-        if not self._O_valid:
+        if not self._O_valid or (self.dropout and self.training):
             self.computer()
         U = self.num_users
         return ops.fullrank_eval(self.O[:U], self.O[U:], user_ids, train_rowptr, train_col, targets, K) + (0.0,)

@@ -33,7 +33,7 @@ def test_struct_layouts_match_header_sizes():
     # natural alignment, 8-byte pointers: catches a field added on one side only
     import ctypes as C
     assert C.sizeof(_lib.CSR) == 13 * 8
-    assert C.sizeof(_lib.LightGCN) == 8 + 16 + 8 + 6 * 4 + 9 * 8
+    assert C.sizeof(_lib.LightGCN) == 8 + 16 + 8 + 6 * 4 + 9 * 8 + 8
     assert C.sizeof(_lib.MF) == 16 + 6 * 4 + 17 * 8
     assert C.sizeof(_lib.NCF) == 16 + 8 + 16 + 8 + 4 * 8 + 8 + 8 + 8 + 8 + 8
     assert C.sizeof(_lib.Aush) == 8 + 2 * 4 + 4 * 4 + 9 * 8

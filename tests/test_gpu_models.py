@@ -465,3 +465,30 @@ def test_ncf_lazy_adam_rows_left_alone_for_a_thousand_steps_match_the_dense_loop
         assert torch.equal(a, b)
     lone = runs["0"][2][(U - 1) * 8:U * 8]                 # m of the lone user's GMF row (the first table of the layout)
     assert float(lone.abs().max()) < 2.0 ** -90 and float(runs["0"][3][(U - 1) * 8:U * 8].max()) > 0
+
+
+def test_lightgcn_graph_dropout_matches_the_reference():
+    """lightgcn.py:62-80 with dropout = 1, keep_prob = 0.6 (off by default in the reference): the masks are torch.rand(nnz) draws
+    of the CPU generator in coalesced entry order, one per batch and one per training-mode forward.  Under the golden run's
+    torch.manual_seed the init AND every mask are replayed: losses, tables, a training-mode forward (fresh mask) and an
+    eval-mode forward (full graph) against the live reference (tests/golden/make_golden_dropout.py)."""
+    from recad_b200 import model
+    z = util.load("lightgcn_dropout_dev.npz")
+    g, U, I = _dev_graph()
+    assert g.nnz == int(z["nnz"])
+    batches = util.split_batches(z, ("batch_users", "batch_pos", "batch_neg"))
+    data = StubData(U, I, batches, ("users", "positive_items", "negative_items"), g, bs=128)
+    data.per_epoch = len(batches) // 2
+    torch.manual_seed(int(z["seed"]))
+    m = model.from_config("victim", "lightgcn", latent_dim_rec=32, lightGCN_n_layers=2, dropout=1, keep_prob=float(z["keep_prob"]),
+                          device=torch.device(DEV)).I(dataset=data)
+    assert np.array_equal(m.embedding_user.weight.cpu().numpy(), z["init_user"])          # the CPU stream is where the reference's was
+    losses = [m.train_step()[0] for _ in range(2)]
+    _close(losses, z["losses"], rtol=1e-4, atol=0)
+    _close(m.E.cpu().numpy(), np.concatenate([z["final_user"], z["final_item"]]), rtol=1e-4, atol=2e-6)
+    s = m(torch.as_tensor(z["q_users"]), torch.as_tensor(z["q_items"]))
+    _close(s.cpu(), z["q_scores_train"], rtol=1e-4, atol=1e-6)
+    m.eval()
+    s = m(torch.as_tensor(z["q_users"]), torch.as_tensor(z["q_items"]))
+    _close(s.cpu(), z["q_scores_eval"], rtol=1e-4, atol=1e-6)
+    assert float(np.abs(z["q_scores_train"] - z["q_scores_eval"]).max()) > 1e-3                # (the two forwards do differ)

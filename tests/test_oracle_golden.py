@@ -165,6 +165,33 @@ def test_lightgcn_autograd_oracle_matches_reference():
     assert np.allclose(m.forward(z["q_users"], z["q_items"]).numpy(), z["q_scores"], rtol=1e-4, atol=2e-6)
 
 
+def test_lightgcn_dropout_oracle_matches_reference():
+    """Graph dropout (lightgcn.py:62-80; golden from make_golden_dropout.py): with the golden run's torch seed the oracle draws
+    the reference's init and every mask -- one per batch, one for the training-mode forward, none in eval mode."""
+    z = util.load("lightgcn_dropout_dev.npz")
+    U, I = META["dev"]["n_users"], META["dev"]["n_items"]
+    tr, _, _ = util.dicts("dev")
+    u, i, _, _ = og.flatten_dict(tr)
+    ptr, col, val, _, _ = og.norm_adj_csr(u, i, U, I)
+    g = olg.csr_to_torch_coo(ptr, col, val, U + I)
+    assert g._nnz() == int(z["nnz"])
+    torch.manual_seed(int(z["seed"]))
+    eu, ei = torch.nn.Embedding(U, 32), torch.nn.Embedding(I, 32)              # lightgcn.py:40-48: N(0, 1) draws, then std 0.1
+    torch.nn.init.normal_(eu.weight, std=0.1)
+    torch.nn.init.normal_(ei.weight, std=0.1)
+    assert np.array_equal(eu.weight.detach().numpy(), z["init_user"]) and np.array_equal(ei.weight.detach().numpy(), z["init_item"])
+    m = olg.LightGCNOracle(g, eu.weight.detach(), ei.weight.detach(), n_layers=2, lam=1e-4, lr=1e-3, keep_prob=float(z["keep_prob"]))
+    batches = util.split_batches(z, ("batch_users", "batch_pos", "batch_neg"))
+    per_epoch = len(batches) // 2
+    losses = [m.train_epoch(batches[e * per_epoch:(e + 1) * per_epoch]) for e in range(2)]
+    assert np.allclose(losses, z["losses"], rtol=1e-5)
+    assert np.allclose(m.user_emb.detach().numpy(), z["final_user"], rtol=1e-4, atol=2e-6)
+    assert np.allclose(m.item_emb.detach().numpy(), z["final_item"], rtol=1e-4, atol=2e-6)
+    assert np.allclose(m.forward(z["q_users"], z["q_items"]).numpy(), z["q_scores_train"], rtol=1e-4, atol=2e-6)
+    m.training = False
+    assert np.allclose(m.forward(z["q_users"], z["q_items"]).numpy(), z["q_scores_eval"], rtol=1e-4, atol=2e-6)
+
+
 def test_lightgcn_manual_closed_form_matches_reference():
     z = util.load("lightgcn_dev.npz")
     U = META["dev"]["n_users"]
