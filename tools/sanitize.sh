@@ -3,6 +3,7 @@
 # WMF / NCF / MF / evaluation / graph tests, racecheck on the shared-memory heavy ones.  Summaries -> gpurun_out/sanitizer_*.log
 #   bash tools/sanitize.sh            (1 GPU)
 #   bash tools/sanitize.sh dist       (2 GPUs: memcheck of the peer-memory epoch, both ranks)
+#   bash tools/sanitize.sh ncf        (NCF epoch strategies + graph dropout; NOT yet run: added after the round's GPU budget was spent)
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
@@ -21,6 +22,12 @@ fi
 if [ "${1:-}" = "aush" ]; then
   run aush memcheck python -m pytest tests/test_gpu_aush.py -x -q -k "bit_stable or train_step"
   run aush racecheck python -m pytest tests/test_gpu_aush.py -x -q -k "bit_stable"
+  exit 0
+fi
+if [ "${1:-}" = "ncf" ]; then
+  # the NCF epoch strategies (graph replay, lazy embedding Adam, duplicate links, out-of-range ids) and LightGCN graph dropout
+  run ncf_epoch memcheck python -m pytest tests/test_gpu_models.py -x -q -k "bit_for_bit or out_of_range or dropout"
+  run ncf_epoch racecheck python -m pytest tests/test_gpu_models.py -x -q -k "out_of_range"
   exit 0
 fi
 run smoke memcheck python -c "import __graft_entry__ as g; g.smoke()"
