@@ -312,7 +312,7 @@ int recad_mt19937_pairwise(uint32_t* key, int32_t* pos, int64_t n_users, int64_t
 // is accepted from line 0 alone.  The parse is bound by the cache misses it can keep in flight (about ten line-fill
 // buffers per core), hence everything a sample needs -- row bounds and the decisive filter bits -- sits in one line.
 constexpr int kFilterWords = 16;
-constexpr uint32_t kBitsA = 448, kBitsB = 512;
+constexpr uint32_t kBitsA = 448;             // region A; region B is the 512 bits that follow (9-bit probes, below)
 constexpr int64_t kLight = 32;
 static inline uint32_t probe_a(uint32_t item) { return 64u + (uint32_t)(((uint64_t)(item * 0x9E3779B1u) * kBitsA) >> 32); }
 static inline void probes_bc(uint32_t item, bool light, uint32_t& b, uint32_t& c) {
